@@ -1,0 +1,144 @@
+/*
+ * pointdsc_b200 — C ABI of the B200-native PointDSC testing-mode forward engine.
+ *
+ * This is the drop-in boundary for ONE path of the reference: `PointDSC.forward` with the
+ * 'testing' key set (reference models/PointDSC.py:128-197).  The reference has no FFI of its
+ * own (it is pure Python/PyTorch); the binding a maintainer adds is the ctypes stub in
+ * pointdsc_b200/_capi.py (shown in INTEGRATION.md), driven by a torch.nn.Module with the
+ * reference's constructor, forward(dict)->dict and state_dict keys (pointdsc_b200/model.py).
+ *
+ * Conventions
+ *   - plain C types only; every entry point returns 0 on success or a pdsc_status code and
+ *     records a message retrievable with pdsc_last_error() (thread-local).
+ *   - "d_" pointers are device pointers on the engine's device, "h_" pointers host pointers.
+ *   - all device work is enqueued on the caller's stream; pdsc_forward() performs NO host
+ *     synchronisation and no allocation, so it can be captured in a CUDA graph.
+ *   - tensors are dense, row-major, fp32 unless stated; B = number of correspondence sets
+ *     in the call, N = correspondences per set (the same N for the whole call).
+ *   - a batched call is, by definition, the loop of per-set testing forwards (the reference
+ *     asserts bs == 1 in testing mode, PointDSC.py:210, :414); in particular the power
+ *     iteration's early exit is decided per set (PointDSC.py:354).
+ */
+#ifndef POINTDSC_B200_H_
+#define POINTDSC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pdsc_engine pdsc_engine;
+
+typedef enum pdsc_status {
+  PDSC_OK = 0,
+  PDSC_ERR_INVALID_ARGUMENT = 1,
+  PDSC_ERR_UNKNOWN_PARAM = 2,
+  PDSC_ERR_SHAPE = 3,
+  PDSC_ERR_NOT_COMMITTED = 4,
+  PDSC_ERR_WORKSPACE = 5,
+  PDSC_ERR_CUDA = 6,
+  PDSC_ERR_UNSUPPORTED = 7
+} pdsc_status;
+
+/* Arithmetic of the encoder's contractions (stage ii).  All other stages are fp32. */
+typedef enum pdsc_precision {
+  PDSC_FP32_SIMT = 0, /* fp32 FFMA kernels: the exact-arithmetic path                              */
+  PDSC_BF16X3 = 1,    /* tcgen05 kind::f16, bf16 hi/lo operand split, 3 products, fp32 accumulate:
+                         fp32-grade results on tensor cores (default; meets the 1e-4 R/t bar)        */
+  PDSC_BF16 = 2       /* tcgen05 kind::f16, single bf16 operands, fp32 accumulate: throughput mode;
+                         the 12-layer near-argmax attention amplifies bf16 rounding, so R/t may
+                         deviate from the reference by > 1e-4 on some sets           */
+} pdsc_precision;
+
+/* Mirrors PointDSC.__init__ (reference models/PointDSC.py:81-91) plus the engine's precision. */
+typedef struct pdsc_config {
+  int32_t in_dim;            /* 6                                                        */
+  int32_t num_layers;        /* 12 in the released snapshots (ctor default 6)            */
+  int32_t num_channels;      /* 128 (only value supported by the kernels)                */
+  int32_t num_iterations;    /* power-iteration cap, 10                                  */
+  float ratio;               /* seeds = int(N * ratio), 0.1                              */
+  float inlier_threshold;    /* hypothesis scoring threshold; also selects the refinement
+                                threshold: 0.10 iff == 0.10f else 1.2 (PointDSC.py:415)   */
+  float sigma_d;             /* initial value of the `sigma_spat` buffer; a loaded
+                                state dict overrides it, as in the reference              */
+  int32_t k;                 /* neighbourhood size of the NSM module, 40                 */
+  float nms_radius;          /* seed NMS radius                                          */
+  int32_t precision;         /* pdsc_precision                                           */
+  int32_t device;            /* CUDA device ordinal                                      */
+} pdsc_config;
+
+/* Optional taps and injection points at the stage boundaries of SURVEY.md §8(a).  Every pointer may
+ * be NULL.  `in_*` tensors REPLACE the engine's own result of that stage (used by the parity tests
+ * to feed a stage the reference's upstream tensors); `out_*` tensors receive a copy. */
+typedef struct pdsc_stage_io {
+  /* injection */
+  const float* in_features;     /* [B,N,C]  un-normalised encoder output (skips stages i-ii)         */
+  const float* in_confidence;   /* [B,N]    confidence logits (requires in_features)                 */
+  const int32_t* in_seeds;      /* [B,S]    seed indices                                            */
+  const int32_t* in_knn_idx;    /* [B,S,k]  neighbourhoods                                          */
+  const float* in_seed_trans;   /* [B,S,4,4] hypotheses                                             */
+  /* taps */
+  float* out_sc;                /* [B,N,N]  spatial-consistency matrix (a1)                          */
+  float* out_features;          /* [B,N,C]  encoder output (a2-a3)                                   */
+  float* out_normed;            /* [B,N,C]  L2-normalised features (a4)                              */
+  float* out_confidence;        /* [B,N]    (a5)                                                     */
+  int32_t* out_seeds;           /* [B,S]    (a6)                                                     */
+  int32_t* out_knn_idx;         /* [B,S,k]  (a7)                                                     */
+  float* out_compat;            /* [B,S,k,k] (a8)                                                    */
+  float* out_eig;               /* [B,S,k]  leading eigenvector at the set's exit iteration (a9)     */
+  int32_t* out_power_iters;     /* [B]      iterations run per set (a9)                              */
+  float* out_seed_trans;        /* [B,S,4,4] (a10)                                                   */
+  int32_t* out_inlier_counts;   /* [B,S]    inlier count of every hypothesis (a11)                   */
+  int32_t* out_best;            /* [B]      selected hypothesis (a11)                                */
+  float* out_init_trans;        /* [B,4,4]  selected hypothesis before refinement (a11)              */
+  int32_t* out_refine_solves;   /* [B]      Kabsch solves done by the refinement (a12)               */
+  int32_t layer_tap;            /* if out_layer_features != NULL: which encoder layer to copy        */
+  float* out_layer_features;    /* [B,N,C]  output of encoder layer `layer_tap`                      */
+} pdsc_stage_io;
+
+/* ---- lifetime --------------------------------------------------------------------------------- */
+int pdsc_create(const pdsc_config* cfg, pdsc_engine** out);
+int pdsc_destroy(pdsc_engine* e);
+const char* pdsc_last_error(void);
+const char* pdsc_version(void);
+
+/* ---- parameters: the reference's state dict, key for key (PointDSC.py:93-113) ------------------
+ * `name` is a state-dict key ("encoder.layer0.weight", "sigma_spat", ...); `h_data` holds `count`
+ * fp32 values in the tensor's own row-major order.  Keys the path does not use
+ * (num_batches_tracked, the stray `gamma`) are accepted and ignored, so a released snapshot can be
+ * pushed unfiltered.  pdsc_commit_params() folds eval-mode BatchNorm into the preceding 1x1 conv,
+ * builds the device-side operand images and must be called before pdsc_forward(). */
+int pdsc_set_param(pdsc_engine* e, const char* name, const float* h_data, int64_t count);
+int pdsc_commit_params(pdsc_engine* e);
+int pdsc_set_precision(pdsc_engine* e, int32_t precision);
+
+/* ---- sizes ------------------------------------------------------------------------------------- */
+int32_t pdsc_num_seeds(const pdsc_engine* e, int32_t N);       /* S = int(N * ratio)          */
+int32_t pdsc_num_neighbours(const pdsc_engine* e, int32_t N);  /* k = min(cfg.k, N - 1)       */
+size_t pdsc_workspace_bytes(const pdsc_engine* e, int32_t B, int32_t N);
+
+/* ---- the path: PointDSC.forward, testing mode (PointDSC.py:128-197) ---------------------------
+ * d_corr_pos [B,N,6], d_src_keypts [B,N,3], d_tgt_keypts [B,N,3]  ->
+ * d_final_trans [B,4,4] (maps src onto tgt), d_final_labels [B,N] in {0,1}.
+ * `io` may be NULL.  `d_workspace` must hold pdsc_workspace_bytes(e,B,N) bytes, 256-byte aligned,
+ * and is only used for the duration of the enqueued work. */
+int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, const float* d_src_keypts,
+                 const float* d_tgt_keypts, float* d_final_trans, float* d_final_labels,
+                 const pdsc_stage_io* io, void* d_workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* Same call with HOST buffers (the end-to-end form): copies the inputs host->device, runs
+ * pdsc_forward, copies the two outputs device->host and synchronises the stream before returning.
+ * Device staging and workspace are owned by the engine and grown on demand. */
+int pdsc_forward_host(pdsc_engine* e, int32_t B, int32_t N, const float* h_corr_pos, const float* h_src_keypts,
+                      const float* h_tgt_keypts, float* h_final_trans, float* h_final_labels, void* cuda_stream);
+
+/* Number of kernels one pdsc_forward(B,N) call launches at the current precision (bench.py's
+ * `gpu_launches`). */
+int32_t pdsc_launches_per_forward(const pdsc_engine* e, int32_t B, int32_t N);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POINTDSC_B200_H_ */

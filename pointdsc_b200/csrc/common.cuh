@@ -1,0 +1,46 @@
+// Shared device helpers for the pointdsc_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pdsc {
+
+constexpr int kC = 128;          // feature channels (num_channels of the released models)
+constexpr int kMaxK = 128;       // largest supported NSM neighbourhood size
+constexpr int kMaxIters = 16;    // largest supported power-iteration cap
+
+__host__ __device__ __forceinline__ int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Euclidean length the way the reference's fp32 torch ops produce it: three rounded squares,
+// two rounded adds, one IEEE sqrt (no FMA contraction), reference models/PointDSC.py:151.
+__device__ __forceinline__ float length3(float dx, float dy, float dz) {
+  return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+}
+
+// max(0, 1 - d^2 / s2) with every operation rounded separately (PointDSC.py:153, :270).
+__device__ __forceinline__ float consistency(float d, float s2) {
+  return fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fmul_rn(d, d), s2)), 0.0f);
+}
+
+}  // namespace pdsc

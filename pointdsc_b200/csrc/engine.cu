@@ -1,0 +1,522 @@
+// Host side of the engine: parameter store (state-dict keys), BatchNorm folding, workspace carving,
+// stage orchestration for PointDSC.forward in testing mode (reference models/PointDSC.py:128-197),
+// and the C ABI declared in include/pointdsc_b200.h.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pointdsc_b200.h"
+#include "common.cuh"
+#include "encoder_tc.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define PDSC_CUDA(expr)                                                                      \
+  do {                                                                                       \
+    cudaError_t err__ = (expr);                                                              \
+    if (err__ != cudaSuccess)                                                                \
+      return fail(PDSC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+constexpr double kBnEps = 1e-5;  // torch.nn.BatchNorm1d default (reference PointDSC.py:14, :59)
+
+struct LayerOffsets {  // offsets (in floats) into the device weight arena
+  size_t w1, b1, wq, bq, wk, bk, wv, bv, wm0, bm0, wm1, bm1, wm2, bm2;
+};
+
+}  // namespace
+
+struct pdsc_engine {
+  pdsc_config cfg{};
+  std::map<std::string, std::vector<float>> params;
+  bool committed = false;
+  float sigma = 1.0f;       // learned `sigma`      (PointDSC.py:97)
+  float sigma_spat = 0.1f;  // buffer `sigma_spat`  (PointDSC.py:98)
+  // device weight arena (fp32, BatchNorm folded)
+  float* d_weights = nullptr;
+  size_t weights_floats = 0;
+  size_t off_l0w = 0, off_l0b = 0;
+  std::vector<LayerOffsets> layers;
+  size_t off_c0t = 0, off_c0b = 0, off_c2t = 0, off_c2b = 0, off_c4 = 0, off_c4b = 0;
+  pdsc::TcWeights tc;  // tensor-core operand images (encoder_tc.cu)
+  // engine-owned buffers for pdsc_forward_host
+  void* host_ws = nullptr;
+  size_t host_ws_bytes = 0;
+  float* host_io = nullptr;
+  size_t host_io_floats = 0;
+};
+
+namespace {
+
+using pdsc::kC;
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+struct Workspace {
+  float *sc, *feat_a, *feat_b, *q, *k, *v, *msg, *h1, *h2, *normed, *conf, *key, *seedfeat, *dist, *iterates,
+      *seed_trans;
+  int32_t *seeds, *knn, *counts;
+  uint32_t* conv_mask;
+  unsigned long long* best_key;
+  void* tc_scratch;
+  size_t bytes;
+};
+
+Workspace carve(const pdsc_engine* e, void* ptr, int B, int N) {
+  Workspace w{};
+  Carver c(ptr);
+  const size_t R = (size_t)B * N;
+  const int NS = pdsc::round_up(N, 64);
+  const int S = pdsc_num_seeds(e, N), k = pdsc_num_neighbours(e, N);
+  const int T = e->cfg.num_iterations;
+  w.sc = c.take<float>(R * NS);
+  w.feat_a = c.take<float>(R * kC);
+  w.feat_b = c.take<float>(R * kC);
+  w.msg = c.take<float>(R * kC);
+  if (e->cfg.precision == PDSC_FP32_SIMT) {
+    w.q = c.take<float>(R * kC);
+    w.k = c.take<float>(R * kC);
+    w.v = c.take<float>(R * kC);
+    w.h1 = c.take<float>(R * 64);
+    w.h2 = c.take<float>(R * 64);
+    w.tc_scratch = nullptr;
+  } else {
+    w.tc_scratch = c.take<char>(pdsc::tc_scratch_bytes(B, N));
+  }
+  w.normed = c.take<float>(R * kC);
+  w.conf = c.take<float>(R);
+  w.key = c.take<float>(R);
+  w.seeds = c.take<int32_t>((size_t)B * S + 1);
+  w.seedfeat = c.take<float>((size_t)B * S * kC + 1);
+  w.dist = c.take<float>((size_t)B * S * N + 1);
+  w.knn = c.take<int32_t>((size_t)B * S * k + 1);
+  w.iterates = c.take<float>((size_t)B * S * T * k + 1);
+  w.seed_trans = c.take<float>((size_t)B * S * 16 + 16);
+  w.counts = c.take<int32_t>((size_t)B * S + 1);
+  w.conv_mask = c.take<uint32_t>(B);
+  w.best_key = c.take<unsigned long long>(B);
+  w.bytes = (c.off + 255) & ~size_t(255);
+  return w;
+}
+
+const std::vector<float>* find(const pdsc_engine* e, const std::string& name, size_t count, std::string* missing) {
+  auto it = e->params.find(name);
+  if (it == e->params.end() || it->second.size() != count) {
+    if (missing->empty()) {
+      *missing = name + (it == e->params.end() ? " (not set)" : " (wrong element count)");
+    }
+    return nullptr;
+  }
+  return &it->second;
+}
+
+// conv [Cout,Cin] (+ optional eval BatchNorm `bn`) -> folded weight/bias appended to the arena
+bool fold_conv(const pdsc_engine* e, const std::string& conv, const std::string& bn, int cout, int cin,
+               std::vector<float>* arena, size_t* off_w, size_t* off_b, std::string* missing) {
+  const auto* w = find(e, conv + ".weight", (size_t)cout * cin, missing);
+  const auto* b = find(e, conv + ".bias", cout, missing);
+  const std::vector<float>*g = nullptr, *beta = nullptr, *mean = nullptr, *var = nullptr;
+  if (!bn.empty()) {
+    g = find(e, bn + ".weight", cout, missing);
+    beta = find(e, bn + ".bias", cout, missing);
+    mean = find(e, bn + ".running_mean", cout, missing);
+    var = find(e, bn + ".running_var", cout, missing);
+  }
+  if (!w || !b || (!bn.empty() && (!g || !beta || !mean || !var))) return false;
+  *off_w = arena->size();
+  arena->resize(arena->size() + (size_t)cout * cin);
+  for (int o = 0; o < cout; ++o) {
+    const double s = bn.empty() ? 1.0 : (double)(*g)[o] / std::sqrt((double)(*var)[o] + kBnEps);
+    for (int c = 0; c < cin; ++c) (*arena)[*off_w + (size_t)o * cin + c] = (float)((double)(*w)[(size_t)o * cin + c] * s);
+  }
+  while (arena->size() % 4) arena->push_back(0.f);
+  *off_b = arena->size();
+  arena->resize(arena->size() + cout);
+  for (int o = 0; o < cout; ++o) {
+    const double s = bn.empty() ? 1.0 : (double)(*g)[o] / std::sqrt((double)(*var)[o] + kBnEps);
+    const double sh = bn.empty() ? 0.0 : (double)(*beta)[o] - (double)(*mean)[o] * s;
+    (*arena)[*off_b + o] = (float)((double)(*b)[o] * s + sh);
+  }
+  while (arena->size() % 4) arena->push_back(0.f);
+  return true;
+}
+
+void copy_tap(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (dst && bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st);
+}
+
+float refinement_threshold(float ctor_threshold) {
+  // `if self.inlier_threshold == 0.10` (PointDSC.py:415): Python compares the ctor double with 0.10
+  return (std::fabs((double)ctor_threshold - 0.10) < 1e-7) ? 0.10f : 1.2f;
+}
+
+int encoder_simt(const pdsc_engine* e, const Workspace& w, int B, int N, const float* corr_pos, const pdsc_stage_io* io,
+                 cudaStream_t st) {
+  using namespace pdsc;
+  const long long R = (long long)B * N;
+  const int NS = round_up(N, 64);
+  const float* W = e->d_weights;
+  launch_layer0(corr_pos, W + e->off_l0w, W + e->off_l0b, w.feat_a, R, e->cfg.in_dim, st);
+  auto lin = [&](const float* A, int K, size_t ow, size_t ob, const float* res, float* out, int Nout, int relu) {
+    LinearArgs a{};
+    a.A = A; a.strideA = 0; a.lda = K;
+    a.W = W + ow; a.strideW = 0; a.ldw = K;
+    a.bias = W + ob; a.res = res; a.ldres = Nout;
+    a.out = out; a.strideO = 0; a.ldo = Nout;
+    a.M = (int)R; a.K = K; a.Nout = Nout; a.relu = relu; a.epi = 0; a.batch = 1;
+    launch_linear_simt(a, st);
+  };
+  for (int l = 0; l < e->cfg.num_layers; ++l) {
+    const LayerOffsets& L = e->layers[l];
+    lin(w.feat_a, kC, L.w1, L.b1, nullptr, w.feat_b, kC, 1);            // PointCN: conv + BN + ReLU
+    lin(w.feat_b, kC, L.wq, L.bq, nullptr, w.q, kC, 0);
+    lin(w.feat_b, kC, L.wk, L.bk, nullptr, w.k, kC, 0);
+    lin(w.feat_b, kC, L.wv, L.bv, nullptr, w.v, kC, 0);
+    launch_attention_simt(w.q, w.k, w.v, w.sc, w.msg, B, N, NS, st);
+    lin(w.msg, kC, L.wm0, L.bm0, nullptr, w.h1, 64, 1);                  // fc_message.0-2
+    lin(w.h1, 64, L.wm1, L.bm1, nullptr, w.h2, 64, 1);                   // fc_message.3-5
+    lin(w.h2, 64, L.wm2, L.bm2, w.feat_b, w.feat_a, kC, 0);              // fc_message.6 + residual
+    if (io && io->out_layer_features && io->layer_tap == l)
+      copy_tap(io->out_layer_features, w.feat_a, (size_t)R * kC * sizeof(float), st);
+  }
+  return PDSC_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* pdsc_last_error(void) { return g_last_error.c_str(); }
+const char* pdsc_version(void) { return "pointdsc_b200 0.1 (sm_100a)"; }
+
+int pdsc_create(const pdsc_config* cfg, pdsc_engine** out) {
+  if (!cfg || !out) return fail(PDSC_ERR_INVALID_ARGUMENT, "pdsc_create: null argument");
+  if (cfg->num_channels != kC) return fail(PDSC_ERR_UNSUPPORTED, "num_channels must be %d, got %d", kC, cfg->num_channels);
+  if (cfg->in_dim < 1 || cfg->in_dim > 64) return fail(PDSC_ERR_UNSUPPORTED, "in_dim %d out of range", cfg->in_dim);
+  if (cfg->num_layers < 1 || cfg->num_layers > 64) return fail(PDSC_ERR_UNSUPPORTED, "num_layers %d out of range", cfg->num_layers);
+  if (cfg->num_iterations < 1 || cfg->num_iterations > pdsc::kMaxIters)
+    return fail(PDSC_ERR_UNSUPPORTED, "num_iterations must be in [1,%d]", pdsc::kMaxIters);
+  if (cfg->k < 1 || cfg->k > pdsc::kMaxK) return fail(PDSC_ERR_UNSUPPORTED, "k must be in [1,%d]", pdsc::kMaxK);
+  if (cfg->precision < PDSC_FP32_SIMT || cfg->precision > PDSC_BF16)
+    return fail(PDSC_ERR_INVALID_ARGUMENT, "unknown precision %d", cfg->precision);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(PDSC_ERR_CUDA, "no CUDA device: this engine has no CPU path");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(PDSC_ERR_INVALID_ARGUMENT, "device %d out of range", cfg->device);
+  cudaDeviceProp prop{};
+  PDSC_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(PDSC_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library holds only sm_100a code", cfg->device,
+                prop.major, prop.minor);
+  pdsc_engine* e = new pdsc_engine();
+  e->cfg = *cfg;
+  e->sigma_spat = cfg->sigma_d;
+  *out = e;
+  return PDSC_OK;
+}
+
+int pdsc_destroy(pdsc_engine* e) {
+  if (!e) return PDSC_OK;
+  DeviceGuard g(e->cfg.device);
+  cudaFree(e->d_weights);
+  pdsc::tc_free_weights(&e->tc);
+  cudaFree(e->host_ws);
+  cudaFree(e->host_io);
+  delete e;
+  return PDSC_OK;
+}
+
+int pdsc_set_param(pdsc_engine* e, const char* name, const float* h_data, int64_t count) {
+  if (!e || !name || (!h_data && count > 0) || count < 0) return fail(PDSC_ERR_INVALID_ARGUMENT, "pdsc_set_param: bad argument");
+  e->params[name].assign(h_data, h_data + count);
+  e->committed = false;
+  return PDSC_OK;
+}
+
+int pdsc_set_precision(pdsc_engine* e, int32_t precision) {
+  if (!e) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine");
+  if (precision < PDSC_FP32_SIMT || precision > PDSC_BF16) return fail(PDSC_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
+  e->cfg.precision = precision;
+  return PDSC_OK;
+}
+
+int pdsc_commit_params(pdsc_engine* e) {
+  if (!e) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine");
+  DeviceGuard g(e->cfg.device);
+  std::string missing;
+  std::vector<float> arena;
+  arena.reserve(1 << 21);
+  const int L = e->cfg.num_layers;
+  e->layers.assign(L, LayerOffsets{});
+  bool ok = fold_conv(e, "encoder.layer0", "", kC, e->cfg.in_dim, &arena, &e->off_l0w, &e->off_l0b, &missing);
+  for (int l = 0; l < L; ++l) {
+    const std::string pc = "encoder.blocks.PointCN_layer_" + std::to_string(l);
+    const std::string nl = "encoder.blocks.NonLocal_layer_" + std::to_string(l);
+    LayerOffsets& o = e->layers[l];
+    ok &= fold_conv(e, pc + ".0", pc + ".1", kC, kC, &arena, &o.w1, &o.b1, &missing);
+    ok &= fold_conv(e, nl + ".projection_q", "", kC, kC, &arena, &o.wq, &o.bq, &missing);
+    ok &= fold_conv(e, nl + ".projection_k", "", kC, kC, &arena, &o.wk, &o.bk, &missing);
+    ok &= fold_conv(e, nl + ".projection_v", "", kC, kC, &arena, &o.wv, &o.bv, &missing);
+    ok &= fold_conv(e, nl + ".fc_message.0", nl + ".fc_message.1", 64, kC, &arena, &o.wm0, &o.bm0, &missing);
+    ok &= fold_conv(e, nl + ".fc_message.3", nl + ".fc_message.4", 64, 64, &arena, &o.wm1, &o.bm1, &missing);
+    ok &= fold_conv(e, nl + ".fc_message.6", "", kC, 64, &arena, &o.wm2, &o.bm2, &missing);
+  }
+  // classification head, first two layers stored transposed ([in][out]) for the warp-per-point kernel
+  size_t c0w, c0b, c2w, c2b, c4w, c4b;
+  ok &= fold_conv(e, "classification.0", "", 32, kC, &arena, &c0w, &c0b, &missing);
+  ok &= fold_conv(e, "classification.2", "", 32, 32, &arena, &c2w, &c2b, &missing);
+  ok &= fold_conv(e, "classification.4", "", 1, 32, &arena, &c4w, &c4b, &missing);
+  if (!ok) return fail(PDSC_ERR_UNKNOWN_PARAM, "pdsc_commit_params: state-dict entry missing or mis-sized: %s", missing.c_str());
+  e->off_c0t = arena.size();
+  arena.resize(arena.size() + (size_t)kC * 32);
+  for (int c = 0; c < kC; ++c)
+    for (int o = 0; o < 32; ++o) arena[e->off_c0t + (size_t)c * 32 + o] = arena[c0w + (size_t)o * kC + c];
+  e->off_c2t = arena.size();
+  arena.resize(arena.size() + 32 * 32);
+  for (int c = 0; c < 32; ++c)
+    for (int o = 0; o < 32; ++o) arena[e->off_c2t + (size_t)c * 32 + o] = arena[c2w + (size_t)o * 32 + c];
+  e->off_c0b = c0b; e->off_c2b = c2b; e->off_c4 = c4w; e->off_c4b = c4b;
+
+  auto s1 = e->params.find("sigma");
+  if (s1 != e->params.end() && s1->second.size() == 1) e->sigma = s1->second[0];
+  auto s2 = e->params.find("sigma_spat");
+  if (s2 != e->params.end() && s2->second.size() == 1) e->sigma_spat = s2->second[0];
+
+  cudaFree(e->d_weights);
+  e->d_weights = nullptr;
+  PDSC_CUDA(cudaMalloc(&e->d_weights, arena.size() * sizeof(float)));
+  PDSC_CUDA(cudaMemcpy(e->d_weights, arena.data(), arena.size() * sizeof(float), cudaMemcpyHostToDevice));
+  e->weights_floats = arena.size();
+
+  // tensor-core operand images of the same folded weights
+  std::vector<pdsc::TcLayerHost> tl(L);
+  for (int l = 0; l < L; ++l) {
+    const LayerOffsets& o = e->layers[l];
+    tl[l] = pdsc::TcLayerHost{arena.data() + o.w1, arena.data() + o.b1, arena.data() + o.wq, arena.data() + o.bq,
+                              arena.data() + o.wk, arena.data() + o.bk, arena.data() + o.wv, arena.data() + o.bv,
+                              arena.data() + o.wm0, arena.data() + o.bm0, arena.data() + o.wm1, arena.data() + o.bm1,
+                              arena.data() + o.wm2, arena.data() + o.bm2};
+  }
+  const int rc = pdsc::tc_build_weights(tl.data(), L, &e->tc);
+  if (rc != 0) return fail(PDSC_ERR_CUDA, "building tensor-core weight images failed: %s", cudaGetErrorString((cudaError_t)rc));
+  e->committed = true;
+  return PDSC_OK;
+}
+
+int32_t pdsc_num_seeds(const pdsc_engine* e, int32_t N) {
+  if (!e || N < 0) return 0;
+  // int(num_corr * self.ratio) in double precision, as Python evaluates it (PointDSC.py:174)
+  return (int32_t)((double)N * (double)e->cfg.ratio);
+}
+int32_t pdsc_num_neighbours(const pdsc_engine* e, int32_t N) {
+  if (!e) return 0;
+  const int k = e->cfg.k < N - 1 ? e->cfg.k : N - 1;  // k = min(self.k, num_corr - 1)  (PointDSC.py:250)
+  return k < 0 ? 0 : k;
+}
+
+size_t pdsc_workspace_bytes(const pdsc_engine* e, int32_t B, int32_t N) {
+  if (!e || B <= 0 || N <= 0) return 0;
+  return carve(e, nullptr, B, N).bytes;
+}
+
+int32_t pdsc_launches_per_forward(const pdsc_engine* e, int32_t B, int32_t N) {
+  if (!e) return 0;
+  const int L = e->cfg.num_layers;
+  const int enc = (e->cfg.precision == PDSC_FP32_SIMT) ? (1 + 8 * L) : pdsc::tc_launches(L);
+  // sc, encoder, head, nms, sort, gather, dist gemm, knn select, 2 fills, nsm, hypotheses, refine
+  return 1 + enc + 1 + 2 + 3 + 2 + 3;
+}
+
+int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, const float* d_src, const float* d_tgt,
+                 float* d_final_trans, float* d_final_labels, const pdsc_stage_io* io, void* d_workspace,
+                 size_t workspace_bytes, void* cuda_stream) {
+  using namespace pdsc;
+  if (!e) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine");
+  if (!e->committed) return fail(PDSC_ERR_NOT_COMMITTED, "pdsc_commit_params() has not been called since the last pdsc_set_param()");
+  if (B <= 0 || N <= 1) return fail(PDSC_ERR_SHAPE, "need B >= 1 and N >= 2 (got B=%d N=%d)", B, N);
+  if (N > pick_seeds_max_n()) return fail(PDSC_ERR_UNSUPPORTED, "N=%d exceeds the supported maximum %d", N, pick_seeds_max_n());
+  if (!d_src || !d_tgt || !d_final_trans || !d_final_labels) return fail(PDSC_ERR_INVALID_ARGUMENT, "null tensor pointer");
+  const bool inject_feat = io && io->in_features;
+  if (!inject_feat && !d_corr_pos) return fail(PDSC_ERR_INVALID_ARGUMENT, "corr_pos is null");
+  if (io && io->in_confidence && !inject_feat) return fail(PDSC_ERR_INVALID_ARGUMENT, "in_confidence requires in_features");
+  const size_t need = pdsc_workspace_bytes(e, B, N);
+  if (!d_workspace || workspace_bytes < need)
+    return fail(PDSC_ERR_WORKSPACE, "workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
+  if (reinterpret_cast<uintptr_t>(d_workspace) % 256) return fail(PDSC_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  DeviceGuard g(e->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const Workspace w = carve(e, d_workspace, B, N);
+  const size_t R = (size_t)B * N;
+  const int NS = round_up(N, 64);
+  const int S = pdsc_num_seeds(e, N), k = pdsc_num_neighbours(e, N), T = e->cfg.num_iterations;
+  const float* W = e->d_weights;
+
+  // ---- stages i + ii ------------------------------------------------------------------------------
+  if (!inject_feat) {
+    launch_sc_matrix(d_src, d_tgt, w.sc, B, N, NS, e->sigma_spat, st);
+    if (io && io->out_sc)
+      cudaMemcpy2DAsync(io->out_sc, (size_t)N * sizeof(float), w.sc, (size_t)NS * sizeof(float), (size_t)N * sizeof(float),
+                        R, cudaMemcpyDeviceToDevice, st);
+    if (e->cfg.precision == PDSC_FP32_SIMT) {
+      const int rc = encoder_simt(e, w, B, N, d_corr_pos, io, st);
+      if (rc) return rc;
+    } else {
+      TcForwardArgs a{};
+      a.B = B; a.N = N; a.NS = NS; a.in_dim = e->cfg.in_dim; a.num_layers = e->cfg.num_layers;
+      a.split = (e->cfg.precision == PDSC_BF16X3) ? 1 : 0;
+      a.corr_pos = d_corr_pos; a.l0w = W + e->off_l0w; a.l0b = W + e->off_l0b;
+      a.sc = w.sc; a.feat = w.feat_a; a.feat1 = w.feat_b; a.msg = w.msg; a.scratch = w.tc_scratch;
+      a.layer_tap = (io && io->out_layer_features) ? io->layer_tap : -1;
+      a.layer_tap_out = io ? io->out_layer_features : nullptr;
+      const int rc = tc_encoder_forward(e->tc, a, st);
+      if (rc) return fail(PDSC_ERR_CUDA, "tensor-core encoder launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    }
+  } else {
+    PDSC_CUDA(cudaMemcpyAsync(w.feat_a, io->in_features, R * kC * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  if (io) copy_tap(io->out_features, w.feat_a, R * kC * sizeof(float), st);
+
+  // ---- a4 + a5 ------------------------------------------------------------------------------------
+  HeadWeights hw{W + e->off_c0t, W + e->off_c0b, W + e->off_c2t, W + e->off_c2b, W + e->off_c4, W + e->off_c4b};
+  const bool inject_conf = io && io->in_confidence;
+  launch_head(w.feat_a, hw, w.normed, w.conf, (long long)R, inject_conf ? 0 : 1, st);
+  if (inject_conf) PDSC_CUDA(cudaMemcpyAsync(w.conf, io->in_confidence, R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (io) {
+    copy_tap(io->out_normed, w.normed, R * kC * sizeof(float), st);
+    copy_tap(io->out_confidence, w.conf, R * sizeof(float), st);
+  }
+
+  // ---- a6 -----------------------------------------------------------------------------------------
+  if (S > 0) {
+    if (io && io->in_seeds)
+      PDSC_CUDA(cudaMemcpyAsync(w.seeds, io->in_seeds, (size_t)B * S * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    else
+      launch_pick_seeds(d_src, w.conf, w.seeds, w.key, B, N, S, e->cfg.nms_radius, st);
+    if (io) copy_tap(io->out_seeds, w.seeds, (size_t)B * S * sizeof(int32_t), st);
+
+    // ---- a7 ---------------------------------------------------------------------------------------
+    if (io && io->in_knn_idx) {
+      PDSC_CUDA(cudaMemcpyAsync(w.knn, io->in_knn_idx, (size_t)B * S * k * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    } else {
+      launch_gather_rows(w.normed, w.seeds, w.seedfeat, B, N, S, st);
+      LinearArgs a{};
+      a.A = w.seedfeat; a.strideA = (long long)S * kC; a.lda = kC;
+      a.W = w.normed; a.strideW = (long long)N * kC; a.ldw = kC;
+      a.bias = nullptr; a.res = nullptr; a.ldres = 0;
+      a.out = w.dist; a.strideO = (long long)S * N; a.ldo = N;
+      a.M = S; a.K = kC; a.Nout = N; a.relu = 0; a.epi = 1; a.batch = B;
+      launch_linear_simt(a, st);
+      launch_knn_select(w.dist, w.knn, B, N, S, k, st);
+    }
+    if (io) copy_tap(io->out_knn_idx, w.knn, (size_t)B * S * k * sizeof(int32_t), st);
+
+    // ---- a8 + a9 ----------------------------------------------------------------------------------
+    launch_fill_u32(w.conv_mask, 0xFFFFFFFFu, B, st);
+    launch_fill_u64(w.best_key, 0ull, B, st);
+    launch_nsm_power(w.normed, d_src, d_tgt, w.knn, w.iterates, w.conv_mask, io ? io->out_compat : nullptr, B, N, S, k, T,
+                     e->sigma, e->sigma_spat, st);
+    // ---- a10 + a11 --------------------------------------------------------------------------------
+    launch_seed_hypotheses(d_src, d_tgt, w.knn, w.iterates, w.conv_mask, io ? io->in_seed_trans : nullptr, w.seed_trans,
+                           w.counts, w.best_key, io ? io->out_eig : nullptr, io ? io->out_power_iters : nullptr, B, N, S,
+                           k, T, e->cfg.inlier_threshold, st);
+    if (io) {
+      copy_tap(io->out_seed_trans, w.seed_trans, (size_t)B * S * 16 * sizeof(float), st);
+      copy_tap(io->out_inlier_counts, w.counts, (size_t)B * S * sizeof(int32_t), st);
+    }
+  } else {
+    launch_fill_u64(w.best_key, 0ull, B, st);
+  }
+  // ---- a11 (labels) + a12 ---------------------------------------------------------------------------
+  launch_select_refine(d_src, d_tgt, w.seed_trans, w.best_key, d_final_trans, d_final_labels,
+                       io ? io->out_init_trans : nullptr, io ? io->out_best : nullptr,
+                       io ? io->out_refine_solves : nullptr, B, N, S, e->cfg.inlier_threshold,
+                       refinement_threshold(e->cfg.inlier_threshold), 20, st);
+  PDSC_CUDA(cudaGetLastError());
+  return PDSC_OK;
+}
+
+int pdsc_forward_host(pdsc_engine* e, int32_t B, int32_t N, const float* h_corr_pos, const float* h_src,
+                      const float* h_tgt, float* h_final_trans, float* h_final_labels, void* cuda_stream) {
+  if (!e) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine");
+  if (!h_corr_pos || !h_src || !h_tgt || !h_final_trans || !h_final_labels) return fail(PDSC_ERR_INVALID_ARGUMENT, "null host pointer");
+  if (B <= 0 || N <= 1) return fail(PDSC_ERR_SHAPE, "need B >= 1 and N >= 2 (got B=%d N=%d)", B, N);
+  DeviceGuard g(e->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const size_t R = (size_t)B * N;
+  const size_t need_ws = pdsc_workspace_bytes(e, B, N);
+  if (need_ws > e->host_ws_bytes) {
+    cudaFree(e->host_ws);
+    e->host_ws = nullptr; e->host_ws_bytes = 0;
+    PDSC_CUDA(cudaMalloc(&e->host_ws, need_ws));
+    e->host_ws_bytes = need_ws;
+  }
+  const size_t in_dim = (size_t)e->cfg.in_dim;
+  const size_t io_floats = R * (in_dim + 3 + 3 + 1) + (size_t)B * 16 + 64;
+  if (io_floats > e->host_io_floats) {
+    cudaFree(e->host_io);
+    e->host_io = nullptr; e->host_io_floats = 0;
+    PDSC_CUDA(cudaMalloc(&e->host_io, io_floats * sizeof(float)));
+    e->host_io_floats = io_floats;
+  }
+  float* d_corr = e->host_io;
+  float* d_src = d_corr + R * in_dim;
+  float* d_tgt = d_src + R * 3;
+  float* d_lab = d_tgt + R * 3;
+  float* d_tr = d_lab + R;
+  PDSC_CUDA(cudaMemcpyAsync(d_corr, h_corr_pos, R * in_dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  PDSC_CUDA(cudaMemcpyAsync(d_src, h_src, R * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  PDSC_CUDA(cudaMemcpyAsync(d_tgt, h_tgt, R * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  const int rc = pdsc_forward(e, B, N, d_corr, d_src, d_tgt, d_tr, d_lab, nullptr, e->host_ws, e->host_ws_bytes, cuda_stream);
+  if (rc) return rc;
+  PDSC_CUDA(cudaMemcpyAsync(h_final_trans, d_tr, (size_t)B * 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  PDSC_CUDA(cudaMemcpyAsync(h_final_labels, d_lab, R * sizeof(float), cudaMemcpyDeviceToHost, st));
+  PDSC_CUDA(cudaStreamSynchronize(st));
+  return PDSC_OK;
+}
+
+}  // extern "C"

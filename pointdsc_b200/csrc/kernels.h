@@ -1,0 +1,72 @@
+// Internal launch API of the pointdsc_b200 kernels.  Host-callable; every function only enqueues
+// work on `st`.  Shapes: B sets, N correspondences per set, NS = SC row stride (N rounded up to 64),
+// C = 128 channels, S seeds per set, k neighbours per seed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pdsc {
+
+// ---- stage i ------------------------------------------------------------------------------------
+void launch_sc_matrix(const float* src, const float* tgt, float* sc, int B, int N, int NS, float sigma_d,
+                      cudaStream_t st);
+
+// ---- stage ii, fp32 SIMT path -------------------------------------------------------------------
+// out[b][r][o] = epi( sum_c A[b][r][c] * W[b][o][c] )   A,W K-contiguous; K % 16 == 0.
+//   epi 0: (+bias[o]) (relu) (+res[r][o])     epi 1: 2 - 2*acc  (feature-space distance, common.py:58-61)
+struct LinearArgs {
+  const float* A; long long strideA; int lda;
+  const float* W; long long strideW; int ldw;
+  const float* bias; const float* res; int ldres;
+  float* out; long long strideO; int ldo;
+  int M, K, Nout, relu, epi, batch;
+};
+void launch_linear_simt(const LinearArgs& a, cudaStream_t st);
+void launch_layer0(const float* corr_pos, const float* W, const float* bias, float* out, long long rows, int in_dim,
+                   cudaStream_t st);
+void launch_attention_simt(const float* q, const float* k, const float* v, const float* sc, float* msg, int B, int N,
+                           int NS, cudaStream_t st);
+
+// ---- a4 + a5: normalise + classification head ---------------------------------------------------
+struct HeadWeights {
+  const float* w0t;  // [128][32]  classification.0.weight transposed
+  const float* b0;   // [32]
+  const float* w2t;  // [32][32]   classification.2.weight transposed
+  const float* b2;   // [32]
+  const float* w4;   // [32]
+  const float* b4;   // [1]
+};
+void launch_head(const float* feat, const HeadWeights& w, float* normed, float* conf, long long rows, int want_conf,
+                 cudaStream_t st);
+
+// ---- a6: seeds -----------------------------------------------------------------------------------
+void launch_pick_seeds(const float* src, const float* conf, int32_t* seeds, float* key_scratch, int B, int N, int S,
+                       float radius, cudaStream_t st);
+int pick_seeds_max_n();
+
+// ---- a7: seed-row kNN ----------------------------------------------------------------------------
+void launch_gather_rows(const float* normed, const int32_t* seeds, float* out, int B, int N, int S, cudaStream_t st);
+void launch_knn_select(const float* dist, int32_t* knn_idx, int B, int N, int S, int k, cudaStream_t st);
+
+// ---- a8 + a9: compatibility + power iteration -----------------------------------------------------
+void launch_nsm_power(const float* normed, const float* src, const float* tgt, const int32_t* knn_idx, float* iterates,
+                      uint32_t* conv_mask, float* compat_out, int B, int N, int S, int k, int iters, float sigma,
+                      float sigma_d, cudaStream_t st);
+
+// ---- a10 + a11: weighted Kabsch per seed, hypothesis scoring, selection -----------------------------
+void launch_seed_hypotheses(const float* src, const float* tgt, const int32_t* knn_idx, const float* iterates,
+                            const uint32_t* conv_mask, const float* seed_trans_in, float* seed_trans,
+                            int32_t* inlier_counts, unsigned long long* best_key, float* eig_out, int32_t* power_iters,
+                            int B, int N, int S, int k, int iters, float inlier_threshold, cudaStream_t st);
+
+// ---- a11 (labels) + a12: refinement ----------------------------------------------------------------
+void launch_select_refine(const float* src, const float* tgt, const float* seed_trans,
+                          const unsigned long long* best_key, float* final_trans, float* final_labels,
+                          float* init_trans_out, int32_t* best_out, int32_t* refine_solves, int B, int N, int S,
+                          float inlier_threshold, float refine_threshold, int max_refine, cudaStream_t st);
+
+// ---- misc ---------------------------------------------------------------------------------------
+void launch_fill_u32(uint32_t* p, uint32_t v, long long n, cudaStream_t st);
+void launch_fill_u64(unsigned long long* p, unsigned long long v, long long n, cudaStream_t st);
+
+}  // namespace pdsc

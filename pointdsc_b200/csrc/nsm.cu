@@ -1,0 +1,199 @@
+// a7, a8, a9 — the per-seed Neural Spectral Matching block up to the power iteration.
+//
+// Reference call sites:
+//   knn               models/common.py:48-69, called at models/PointDSC.py:251-252
+//   compatibility     models/PointDSC.py:257-278
+//   power iteration   models/PointDSC.py:338-358 (cal_leading_eigenvector, method='power')
+//
+// kNN: the reference builds the full N x N feature-distance matrix and a top-(k+1) for every row, then
+// keeps the S seed rows; only the seed rows are computed here (identical result, 10x less work).  The
+// S x N distance block comes from the SGEMM in encoder_simt.cu (epi 1: 2 - 2 f_s.f_j); this file selects
+// the k+1 smallest per row in ascending (distance, index) order and drops the first (ignore_self).
+//
+// Power iteration: the reference stops when torch.allclose(new, last) holds for ALL seeds of the set
+// at once (bs == 1), i.e. the exit iteration is a per-set quantity.  Each seed CTA therefore runs the
+// full `num_iterations`, stores every iterate, and ANDs a "converged at iteration t" bit mask into a
+// per-set word; the consumer (select_refine.cu) takes the iterate at the first all-converged bit.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace pdsc {
+
+// ---- seed feature rows -----------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const float* __restrict__ normed, const int32_t* __restrict__ seeds,
+                                   float* __restrict__ out, int N, int S) {
+  const int b = blockIdx.y, s = blockIdx.x, lane = threadIdx.x;
+  int idx = seeds[(size_t)b * S + s];
+  idx = min(max(idx, 0), N - 1);
+  const float4 v = *reinterpret_cast<const float4*>(normed + ((size_t)b * N + idx) * kC + lane * 4);
+  *reinterpret_cast<float4*>(out + ((size_t)b * S + s) * kC + lane * 4) = v;
+}
+void launch_gather_rows(const float* normed, const int32_t* seeds, float* out, int B, int N, int S, cudaStream_t st) {
+  if (S <= 0) return;
+  gather_rows_kernel<<<dim3(S, B), 32, 0, st>>>(normed, seeds, out, N, S);
+}
+
+// ---- top-(k+1) smallest per seed row ---------------------------------------------------------------
+__device__ __forceinline__ unsigned long long dist_key(float d, int j) {
+  uint32_t u = __float_as_uint(d);
+  if ((u & 0x7FFFFFFFu) == 0u) u = 0u;
+  u ^= (u & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u;
+  return ((unsigned long long)u << 32) | (unsigned)j;
+}
+
+__global__ void __launch_bounds__(128) knn_select_kernel(const float* __restrict__ dist, int32_t* __restrict__ knn_idx,
+                                                         int N, int S, int k) {
+  extern __shared__ unsigned long long keys[];  // [N]
+  __shared__ unsigned long long wmin[4];
+  __shared__ unsigned long long chosen;
+  const int row = blockIdx.x;  // b * S + s
+  const float* d = dist + (size_t)row * N;
+  for (int j = threadIdx.x; j < N; j += 128) keys[j] = dist_key(d[j], j);
+  __syncthreads();
+  unsigned long long prev = 0ull;
+  for (int r = 0; r <= k; ++r) {
+    unsigned long long best = ~0ull;
+    for (int j = threadIdx.x; j < N; j += 128) {
+      const unsigned long long v = keys[j];
+      if (v > prev && v < best) best = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other < best ? other : best;
+    }
+    if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long m = wmin[0];
+      for (int w = 1; w < 4; ++w) m = wmin[w] < m ? wmin[w] : m;
+      chosen = m;
+      if (r > 0) knn_idx[(size_t)row * k + (r - 1)] = (m == ~0ull) ? 0 : (int32_t)(m & 0xFFFFFFFFull);
+    }
+    __syncthreads();
+    prev = chosen;
+  }
+}
+
+void launch_knn_select(const float* dist, int32_t* knn_idx, int B, int N, int S, int k, cudaStream_t st) {
+  if (S <= 0) return;
+  const int smem = N * (int)sizeof(unsigned long long);
+  static int configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
+    configured = 16384 * 8;
+  }
+  knn_select_kernel<<<B * S, 128, smem, st>>>(dist, knn_idx, N, S, k);
+}
+
+// ---- compatibility matrix + power iteration, one CTA per seed ----------------------------------------
+constexpr int kFs = kC + 4;  // padded feature row stride (floats)
+
+__global__ void __launch_bounds__(128) nsm_power_kernel(const float* __restrict__ normed, const float* __restrict__ src,
+                                                        const float* __restrict__ tgt,
+                                                        const int32_t* __restrict__ knn_idx,
+                                                        float* __restrict__ iterates, uint32_t* __restrict__ conv_mask,
+                                                        float* __restrict__ compat_out, int N, int S, int k, int iters,
+                                                        float sigma2, float sigmad2) {
+  extern __shared__ __align__(16) float sm[];
+  const int ms = k | 1;                  // odd row stride of M: conflict-free row-per-thread reads
+  float* Fs = sm;                        // [k][kFs]
+  float* M = Fs + (size_t)k * kFs;       // [k][ms]
+  float* pa = M + (size_t)k * ms;        // [k][3]
+  float* pb = pa + k * 3;                // [k][3]
+  float* v = pb + k * 3;                 // [k]
+  float* red = v + k;                    // [4]
+  __shared__ int idx[kMaxK];
+  const int b = blockIdx.y, s = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t seed_row = (size_t)b * S + s;
+
+  for (int a = tid; a < k; a += 128) {
+    int j = knn_idx[seed_row * k + a];
+    j = min(max(j, 0), N - 1);
+    idx[a] = j;
+    const float* ps = src + ((size_t)b * N + j) * 3;
+    const float* pt = tgt + ((size_t)b * N + j) * 3;
+    pa[a * 3 + 0] = ps[0]; pa[a * 3 + 1] = ps[1]; pa[a * 3 + 2] = ps[2];
+    pb[a * 3 + 0] = pt[0]; pb[a * 3 + 1] = pt[1]; pb[a * 3 + 2] = pt[2];
+    v[a] = 1.0f;
+    M[a * ms + a] = 0.0f;  // total_knn_M[:, i, i] = 0  (PointDSC.py:278)
+  }
+  __syncthreads();
+  for (int a = warp; a < k; a += 4) {
+    const float4 f = *reinterpret_cast<const float4*>(normed + ((size_t)b * N + idx[a]) * kC + lane * 4);
+    *reinterpret_cast<float4*>(Fs + (size_t)a * kFs + lane * 4) = f;
+  }
+  __syncthreads();
+
+  // upper triangle of feature-compat * spatial-compat
+  const int npairs = k * (k - 1) / 2;
+  for (int t = tid; t < npairs; t += 128) {
+    int a = 0, rem = t;
+    while (rem >= k - 1 - a) { rem -= k - 1 - a; ++a; }
+    const int c = a + 1 + rem;
+    const float4* fa = reinterpret_cast<const float4*>(Fs + (size_t)a * kFs);
+    const float4* fc = reinterpret_cast<const float4*>(Fs + (size_t)c * kFs);
+    float g = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < kC / 4; ++q) {
+      const float4 x = fa[q], y = fc[q];
+      g = fmaf(x.x, y.x, g); g = fmaf(x.y, y.y, g); g = fmaf(x.z, y.z, g); g = fmaf(x.w, y.w, g);
+    }
+    const float fm = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fsub_rn(1.0f, g), sigma2)), 0.0f);
+    const float la = length3(pa[a * 3] - pa[c * 3], pa[a * 3 + 1] - pa[c * 3 + 1], pa[a * 3 + 2] - pa[c * 3 + 2]);
+    const float lb = length3(pb[a * 3] - pb[c * 3], pb[a * 3 + 1] - pb[c * 3 + 1], pb[a * 3 + 2] - pb[c * 3 + 2]);
+    const float val = __fmul_rn(fm, consistency(__fsub_rn(la, lb), sigmad2));
+    M[a * ms + c] = val;
+    M[c * ms + a] = val;
+  }
+  __syncthreads();
+  if (compat_out) {
+    float* dst = compat_out + seed_row * k * k;
+    for (int t = tid; t < k * k; t += 128) dst[t] = M[(t / k) * ms + (t % k)];
+  }
+
+  // power iteration from the all-ones vector; record every iterate and a convergence bit per iteration
+  uint32_t mask = 0u;
+  float* it_out = iterates + seed_row * (size_t)iters * k;
+  for (int t = 0; t < iters; ++t) {
+    float u = 0.f, vold = 0.f;
+    if (tid < k) {
+      const float* mr = M + tid * ms;
+      for (int c = 0; c < k; ++c) u = fmaf(mr[c], v[c], u);
+      vold = v[tid];
+    }
+    const float ss = warp_sum(tid < k ? u * u : 0.f);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    const float nrm = sqrtf(red[0] + red[1] + red[2] + red[3]) + 1e-6f;
+    const float vnew = u / nrm;
+    // torch.allclose(new, last): |new - last| <= atol + rtol * |last|, atol 1e-8, rtol 1e-5
+    const int ok = (tid >= k) || (fabsf(vnew - vold) <= 1e-8f + 1e-5f * fabsf(vold));
+    const int all_ok = __syncthreads_and(ok);
+    if (tid < k) {
+      v[tid] = vnew;
+      it_out[(size_t)t * k + tid] = vnew;
+    }
+    if (all_ok) mask |= (1u << t);
+    __syncthreads();
+  }
+  if (tid == 0) atomicAnd(conv_mask + b, mask);
+}
+
+void launch_nsm_power(const float* normed, const float* src, const float* tgt, const int32_t* knn_idx, float* iterates,
+                      uint32_t* conv_mask, float* compat_out, int B, int N, int S, int k, int iters, float sigma,
+                      float sigma_d, cudaStream_t st) {
+  if (S <= 0) return;
+  const int ms = k | 1;
+  const int smem = (k * kFs + k * ms + 6 * k + k + 4) * (int)sizeof(float);
+  static int configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(nsm_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    configured = 160 * 1024;
+  }
+  nsm_power_kernel<<<dim3(S, B), 128, smem, st>>>(normed, src, tgt, knn_idx, iterates, conv_mask, compat_out, N, S, k,
+                                                   iters, sigma * sigma, sigma_d * sigma_d);
+}
+
+}  // namespace pdsc

@@ -1,0 +1,243 @@
+"""Drop-in `PointDSC` module backed by the B200 engine.
+
+Boundary mirrored (reference models/PointDSC.py):
+  * constructor signature and defaults                                   :81-91
+  * parameter / buffer names, so `load_state_dict(torch.load('snapshot/<X>/models/model_best.pkl'),
+    strict=False)` reports missing=[] and unexpected=['gamma'] exactly as the reference does   :93-113
+  * `forward(data: dict) -> dict` with keys corr_pos / src_keypts / tgt_keypts and the presence of
+    'testing' selecting test mode; returns final_trans [bs,4,4], final_labels [bs,N], M=None   :128-197
+
+Differences, all deliberate:
+  * testing mode accepts bs > 1 and defines it as the loop of bs == 1 reference calls (the reference
+    asserts bs == 1, :210/:414);
+  * there is NO CPU / PyTorch fallback: the module's sub-modules are parameter containers only, the
+    arithmetic lives in libpointdsc_b200.so and every call fails loudly without it;
+  * the non-testing (training / validation) branch is outside the accelerated path and raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Iterable, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _capi
+
+DEFAULT_PRECISION = os.environ.get("POINTDSC_PRECISION", "bf16x3")
+
+_TAP_SPECS = {
+    # name: (dtype, shape as a function of (B, N, S, k, C))
+    "sc": (torch.float32, lambda B, N, S, k, c: (B, N, N)),
+    "features": (torch.float32, lambda B, N, S, k, c: (B, N, c)),
+    "normed": (torch.float32, lambda B, N, S, k, c: (B, N, c)),
+    "confidence": (torch.float32, lambda B, N, S, k, c: (B, N)),
+    "seeds": (torch.int32, lambda B, N, S, k, c: (B, S)),
+    "knn_idx": (torch.int32, lambda B, N, S, k, c: (B, S, k)),
+    "compat": (torch.float32, lambda B, N, S, k, c: (B, S, k, k)),
+    "eig": (torch.float32, lambda B, N, S, k, c: (B, S, k)),
+    "power_iters": (torch.int32, lambda B, N, S, k, c: (B,)),
+    "seed_trans": (torch.float32, lambda B, N, S, k, c: (B, S, 4, 4)),
+    "inlier_counts": (torch.int32, lambda B, N, S, k, c: (B, S)),
+    "best": (torch.int32, lambda B, N, S, k, c: (B,)),
+    "init_trans": (torch.float32, lambda B, N, S, k, c: (B, 4, 4)),
+    "refine_solves": (torch.int32, lambda B, N, S, k, c: (B,)),
+    "layer_features": (torch.float32, lambda B, N, S, k, c: (B, N, c)),
+}
+_INJECT_DTYPES = {"features": torch.float32, "confidence": torch.float32, "seeds": torch.int32,
+                  "knn_idx": torch.int32, "seed_trans": torch.float32}
+
+
+def _conv(cin, cout):
+    return nn.Conv1d(cin, cout, kernel_size=1, bias=True)
+
+
+class _NonLocalParams(nn.Module):
+    """Parameters of one SCNonlocal block, named as in the reference (PointDSC.py:9-25)."""
+
+    def __init__(self, c: int):
+        super().__init__()
+        h = c // 2
+        self.fc_message = nn.Sequential(_conv(c, h), nn.BatchNorm1d(h), nn.ReLU(inplace=True),
+                                        _conv(h, h), nn.BatchNorm1d(h), nn.ReLU(inplace=True), _conv(h, c))
+        self.projection_q = _conv(c, c)
+        self.projection_k = _conv(c, c)
+        self.projection_v = _conv(c, c)
+
+
+class _EncoderParams(nn.Module):
+    """Parameters of the NonLocalNet encoder, named as in the reference (PointDSC.py:48-63)."""
+
+    def __init__(self, in_dim: int, num_layers: int, c: int):
+        super().__init__()
+        self.num_layers = num_layers
+        self.blocks = nn.ModuleDict()
+        self.layer0 = _conv(in_dim, c)
+        for i in range(num_layers):
+            self.blocks[f"PointCN_layer_{i}"] = nn.Sequential(_conv(c, c), nn.BatchNorm1d(c), nn.ReLU(inplace=True))
+            self.blocks[f"NonLocal_layer_{i}"] = _NonLocalParams(c)
+
+
+class PointDSC(nn.Module):
+    def __init__(self, in_dim=6, num_layers=6, num_channels=128, num_iterations=10, ratio=0.1,
+                 inlier_threshold=0.10, sigma_d=0.10, k=40, nms_radius=0.10, *, precision: Optional[str] = None):
+        super().__init__()
+        self.in_dim = in_dim
+        self.num_layers = num_layers
+        self.num_iterations = num_iterations
+        self.ratio = ratio
+        self.num_channels = num_channels
+        self.inlier_threshold = inlier_threshold
+        self.k = k
+        self.nms_radius = nms_radius
+        self.precision = precision or DEFAULT_PRECISION
+        if self.precision not in _capi.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_capi.PRECISIONS)}, got {self.precision!r}")
+        self.sigma = nn.Parameter(torch.tensor([1.0], dtype=torch.float32), requires_grad=True)
+        self.sigma_spat = nn.Parameter(torch.tensor([sigma_d], dtype=torch.float32), requires_grad=False)
+        self.encoder = _EncoderParams(in_dim, num_layers, num_channels)
+        self.classification = nn.Sequential(_conv(num_channels, 32), nn.ReLU(inplace=True), _conv(32, 32),
+                                            nn.ReLU(inplace=True), _conv(32, 1))
+        for m in self.modules():  # same initialisation scheme as the reference (PointDSC.py:116-121)
+            if isinstance(m, nn.Conv1d):
+                nn.init.xavier_normal_(m.weight, gain=1)
+            elif isinstance(m, nn.BatchNorm1d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+        self._engine = None
+        self._engine_device = None
+        self._pushed_signature = None
+        self._workspace = None
+
+    # ------------------------------------------------------------------------------------------
+    # engine plumbing
+    # ------------------------------------------------------------------------------------------
+    def _device(self) -> torch.device:
+        return self.sigma.device
+
+    def _signature(self):
+        return tuple((t._version, t.data_ptr()) for t in self.state_dict(keep_vars=True).values()) + (self.precision,)
+
+    def _ensure_engine(self):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise _capi.PdscError("pointdsc_b200.PointDSC runs on a B200 only: move the module to CUDA "
+                                  "(`model.cuda()`); there is no CPU fallback")
+        lib = _capi.load()
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        if self._engine is None or self._engine_device != index:
+            self._release()
+            cfg = _capi.Config(self.in_dim, self.num_layers, self.num_channels, self.num_iterations, self.ratio,
+                               self.inlier_threshold, float(self.sigma_spat.detach().cpu()[0]), self.k,
+                               self.nms_radius, _capi.PRECISIONS[self.precision], index)
+            handle = C.c_void_p()
+            _capi.check(lib.pdsc_create(C.byref(cfg), C.byref(handle)))
+            self._engine, self._engine_device, self._pushed_signature = handle, index, None
+        sig = self._signature()
+        if sig != self._pushed_signature:
+            _capi.check(lib.pdsc_set_precision(self._engine, _capi.PRECISIONS[self.precision]))
+            for name, t in self.state_dict().items():
+                if not t.is_floating_point():
+                    continue  # num_batches_tracked
+                h = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
+                _capi.check(lib.pdsc_set_param(self._engine, name.encode(), C.c_void_p(h.data_ptr()), h.numel()))
+            _capi.check(lib.pdsc_commit_params(self._engine))
+            self._pushed_signature = sig
+        return lib
+
+    def _release(self):
+        if self._engine is not None:
+            try:
+                _capi.load().pdsc_destroy(self._engine)
+            except Exception:
+                pass
+            self._engine = None
+
+    def __del__(self):
+        self._release()
+
+    def set_precision(self, precision: str):
+        if precision not in _capi.PRECISIONS:
+            raise ValueError(precision)
+        self.precision = precision
+        self._workspace = None
+
+    def launches_per_forward(self, B: int, N: int) -> int:
+        lib = self._ensure_engine()
+        return int(lib.pdsc_launches_per_forward(self._engine, B, N))
+
+    def num_seeds(self, N: int) -> int:
+        return int(N * self.ratio)
+
+    # ------------------------------------------------------------------------------------------
+    # the path
+    # ------------------------------------------------------------------------------------------
+    def forward(self, data: Dict[str, torch.Tensor]) -> Dict[str, Optional[torch.Tensor]]:
+        testing = "testing" in data.keys()
+        if not testing:
+            raise NotImplementedError(
+                "pointdsc_b200 accelerates the testing-mode forward only (pass data['testing']); the training / "
+                "validation branch of the reference (PointDSC.py:158-165, :176) is outside this engine")
+        out = self.run(data["corr_pos"], data["src_keypts"], data["tgt_keypts"])
+        return {"final_trans": out["final_trans"], "final_labels": out["final_labels"], "M": None}
+
+    @torch.no_grad()
+    def run(self, corr_pos: torch.Tensor, src_keypts: torch.Tensor, tgt_keypts: torch.Tensor,
+            taps: Iterable[str] = (), inject: Optional[Dict[str, torch.Tensor]] = None, layer_tap: int = 0):
+        """Testing-mode forward.  `taps` / `inject` expose the stage boundaries of SURVEY.md §8(a) for the
+        parity tests (names: see _TAP_SPECS / _INJECT_DTYPES).  Host tensors take the end-to-end path
+        (pdsc_forward_host: H2D + forward + D2H inside the call) and return host tensors."""
+        if corr_pos.dim() != 3 or src_keypts.shape[:2] != corr_pos.shape[:2] or tgt_keypts.shape != src_keypts.shape \
+                or src_keypts.shape[-1] != 3 or corr_pos.shape[-1] != self.in_dim:
+            raise ValueError(f"expected corr_pos [bs,N,{self.in_dim}] and src/tgt_keypts [bs,N,3], got "
+                             f"{tuple(corr_pos.shape)}, {tuple(src_keypts.shape)}, {tuple(tgt_keypts.shape)}")
+        lib = self._ensure_engine()
+        dev = self._device()
+        B, N = int(corr_pos.shape[0]), int(corr_pos.shape[1])
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if corr_pos.device.type == "cpu":
+            if taps or inject:
+                raise ValueError("taps / inject need device tensors")
+            cp, s, t = (x.to(torch.float32).contiguous() for x in (corr_pos, src_keypts, tgt_keypts))
+            trans = torch.empty(B, 4, 4, dtype=torch.float32, pin_memory=cp.is_pinned())
+            labels = torch.empty(B, N, dtype=torch.float32, pin_memory=cp.is_pinned())
+            with torch.cuda.device(dev):
+                _capi.check(lib.pdsc_forward_host(self._engine, B, N, C.c_void_p(cp.data_ptr()), C.c_void_p(s.data_ptr()),
+                                                  C.c_void_p(t.data_ptr()), C.c_void_p(trans.data_ptr()),
+                                                  C.c_void_p(labels.data_ptr()), stream))
+            return {"final_trans": trans, "final_labels": labels}
+        if corr_pos.device != dev:
+            raise ValueError(f"inputs are on {corr_pos.device}, module is on {dev}")
+        cp, s, t = (x.to(torch.float32).contiguous() for x in (corr_pos, src_keypts, tgt_keypts))
+        S = int(lib.pdsc_num_seeds(self._engine, N))
+        k = int(lib.pdsc_num_neighbours(self._engine, N))
+        need = int(lib.pdsc_workspace_bytes(self._engine, B, N))
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
+            self._workspace = None
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        trans = torch.empty(B, 4, 4, dtype=torch.float32, device=dev)
+        labels = torch.empty(B, N, dtype=torch.float32, device=dev)
+        io_ptr, extra, keep = None, {}, []
+        if taps or inject:
+            io = _capi.StageIO()
+            for name in taps:
+                dtype, shape = _TAP_SPECS[name]
+                buf = torch.zeros(shape(B, N, S, k, self.num_channels), dtype=dtype, device=dev)
+                extra[name] = buf
+                setattr(io, "out_" + name, buf.data_ptr())
+            io.layer_tap = int(layer_tap)
+            for name, val in (inject or {}).items():
+                v = val.to(device=dev, dtype=_INJECT_DTYPES[name]).contiguous()
+                keep.append(v)
+                setattr(io, "in_" + ("knn_idx" if name == "knn_idx" else name), v.data_ptr())
+            io_ptr = C.byref(io)
+        _capi.check(lib.pdsc_forward(self._engine, B, N, C.c_void_p(cp.data_ptr()), C.c_void_p(s.data_ptr()),
+                                     C.c_void_p(t.data_ptr()), C.c_void_p(trans.data_ptr()),
+                                     C.c_void_p(labels.data_ptr()), io_ptr, C.c_void_p(self._workspace.data_ptr()),
+                                     self._workspace.numel(), stream))
+        if keep:
+            torch.cuda.current_stream(dev).synchronize()  # injected temporaries must outlive the enqueued work
+        out = {"final_trans": trans, "final_labels": labels}
+        out.update(extra)
+        return out

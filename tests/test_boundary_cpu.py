@@ -1,0 +1,95 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every declared symbol,
+the nn.Module mirrors the reference's state dict, and nothing computes without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import REPO, load_snapshot
+
+
+def _header_symbols():
+    text = open(os.path.join(REPO, "include", "pointdsc_b200.h")).read()
+    return sorted(set(re.findall(r"\b(pdsc_[a-z_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_header_symbol():
+    import __graft_entry__ as g
+    g.build()
+    from pointdsc_b200 import _capi
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    declared = _header_symbols()
+    assert len(declared) >= 13
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/pointdsc_b200.h but not exported"
+    assert sorted(_capi.SYMBOLS) == declared          # the ctypes binding covers the header, no more, no less
+    assert b"sm_100a" in _capi.load().pdsc_version()
+
+
+def test_struct_layouts_match_the_header():
+    from pointdsc_b200 import _capi
+    assert ctypes.sizeof(_capi.Config) == 11 * 4
+    # 5 injection + 14 tap pointers, int32 layer_tap (+4 pad), 1 pointer
+    assert ctypes.sizeof(_capi.StageIO) == 19 * 8 + 8 + 8
+    assert _capi.StageIO.layer_tap.offset == 19 * 8
+    assert _capi.StageIO.out_layer_features.offset == 19 * 8 + 8
+
+
+@pytest.mark.parametrize("dataset", ["3dmatch", "kitti"])
+def test_released_snapshot_loads_unchanged(dataset):
+    from pointdsc_b200 import PointDSC
+    m = PointDSC(in_dim=6, num_layers=12, num_channels=128, num_iterations=10, ratio=0.1, k=40)
+    sd = load_snapshot(dataset)
+    res = m.load_state_dict(sd, strict=False)
+    assert res.missing_keys == [] and res.unexpected_keys == ["gamma"]     # as the reference reports
+    own = m.state_dict()
+    assert len(own) == 358
+    assert sum(p.numel() for p in m.parameters()) == 1053667
+    for k, v in own.items():
+        assert torch.equal(v, sd[k]), k
+    assert m.sigma.requires_grad and not m.sigma_spat.requires_grad
+
+
+def test_constructor_defaults_match_the_reference():
+    import inspect
+
+    from pointdsc_b200 import PointDSC
+    sig = inspect.signature(PointDSC.__init__)
+    want = dict(in_dim=6, num_layers=6, num_channels=128, num_iterations=10, ratio=0.1, inlier_threshold=0.10,
+                sigma_d=0.10, k=40, nms_radius=0.10)
+    got = {k: v.default for k, v in sig.parameters.items() if k in want}
+    assert got == want
+    assert list(sig.parameters)[1:10] == list(want)    # positional order as in models/PointDSC.py:81-91
+
+
+def test_no_cpu_fallback():
+    from pointdsc_b200 import PdscError, PointDSC
+    m = PointDSC(num_layers=2)
+    data = {"corr_pos": torch.zeros(1, 16, 6), "src_keypts": torch.zeros(1, 16, 3), "tgt_keypts": torch.zeros(1, 16, 3),
+            "testing": True}
+    with pytest.raises(PdscError):
+        m(data)
+    with pytest.raises(NotImplementedError):
+        m({k: v for k, v in data.items() if k != "testing"})
+
+
+def test_engine_creation_fails_without_a_device():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pointdsc_b200 import _capi
+    lib = _capi.load()
+    cfg = _capi.Config(6, 12, 128, 10, 0.1, 0.1, 0.1, 40, 0.1, 0, 0)
+    h = ctypes.c_void_p()
+    assert lib.pdsc_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
+    assert b"no CUDA device" in lib.pdsc_last_error()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(REPO, "pointdsc_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, f)).read()
+                assert "oracle" not in text.replace("oracle/", "").replace("CPU oracle", "") or f == "synth.py", f
