@@ -32,9 +32,16 @@ __device__ __forceinline__ int warp_sum(int v) {
   return v;
 }
 
-// Euclidean length the way the reference's fp32 torch ops produce it: three rounded squares,
-// two rounded adds, one IEEE sqrt (no FMA contraction), reference models/PointDSC.py:151.
+// Euclidean length exactly as the reference's `torch.norm(x, dim=-1)` produces it on CPU (fp32 accumulate,
+// compiled with FMA contraction: x*x, then fma(y,y,.), then fma(z,z,.), IEEE sqrt) — verified bit for bit
+// against torch 2.11 on 4M vectors.  Used for src_dist / SC (reference models/PointDSC.py:151-152).
 __device__ __forceinline__ float length3(float dx, float dy, float dz) {
+  return __fsqrt_rn(__fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx))));
+}
+
+// Euclidean length as `((d) ** 2).sum(-1) ** 0.5` produces it (three rounded squares, (x+y)+z, sqrt):
+// the form used inside cal_seed_trans (reference models/PointDSC.py:268).
+__device__ __forceinline__ float length3_pow(float dx, float dy, float dz) {
   return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
 }
 

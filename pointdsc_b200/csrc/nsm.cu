@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(128) nsm_power_kernel(const float* __restrict_
       g = fmaf(x.x, y.x, g); g = fmaf(x.y, y.y, g); g = fmaf(x.z, y.z, g); g = fmaf(x.w, y.w, g);
     }
     const float fm = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fsub_rn(1.0f, g), sigma2)), 0.0f);
-    const float la = length3(pa[a * 3] - pa[c * 3], pa[a * 3 + 1] - pa[c * 3 + 1], pa[a * 3 + 2] - pa[c * 3 + 2]);
-    const float lb = length3(pb[a * 3] - pb[c * 3], pb[a * 3 + 1] - pb[c * 3 + 1], pb[a * 3 + 2] - pb[c * 3 + 2]);
+    const float la = length3_pow(pa[a * 3] - pa[c * 3], pa[a * 3 + 1] - pa[c * 3 + 1], pa[a * 3 + 2] - pa[c * 3 + 2]);
+    const float lb = length3_pow(pb[a * 3] - pb[c * 3], pb[a * 3 + 1] - pb[c * 3 + 1], pb[a * 3 + 2] - pb[c * 3 + 2]);
     const float val = __fmul_rn(fm, consistency(__fsub_rn(la, lb), sigmad2));
     M[a * ms + c] = val;
     M[c * ms + a] = val;
