@@ -96,6 +96,8 @@ typedef struct pdsc_stage_io {
   int32_t* out_refine_solves;   /* [B]      Kabsch solves done by the refinement (a12)               */
   int32_t layer_tap;            /* if out_layer_features != NULL: which encoder layer to copy        */
   float* out_layer_features;    /* [B,N,C]  output of encoder layer `layer_tap`                      */
+  float* out_layer_debug;       /* [5,B,N,C] internals of layer `layer_tap`: PointCN output, q, k, v, msg.
+                                   In the tensor-core modes q carries the folded log2(e)/sqrt(C) scale. */
 } pdsc_stage_io;
 
 /* ---- lifetime --------------------------------------------------------------------------------- */

@@ -1,9 +1,676 @@
-// placeholder: replaced by the tcgen05 kernels
+// Stage ii on the 5th-generation tensor cores (tcgen05 + TMEM), precisions PDSC_BF16X3 / PDSC_BF16.
+//
+// Reference: models/PointDSC.py:9-77 — per layer  PointCN (conv+BN+ReLU) -> Q,K,V 1x1 convs ->
+//   P = softmax_j(SC_ij * q_i.k_j / sqrt(C)), msg = P V -> fc_message (128->64->64->128) -> residual.
+//
+// Numerics.  The stack is chaotic (|logit| reaches ~2.6e3, softmax is near-argmax): tools/numerics_probe.py
+// shows single bf16 / fp16 / tf32 operands move the final R/t by up to 7e-4, above the 1e-4 bar, while a
+// bf16 hi/lo split of BOTH operands of every contraction (x ~= hi + lo, products hi*hi + hi*lo + lo*hi,
+// fp32 accumulation in TMEM) stays at the fp32 noise floor (2e-6).  PDSC_BF16X3 issues those three
+// kind::f16 MMAs per k-step; PDSC_BF16 issues only hi*hi (3x less tensor work, throughput mode).
+//
+// Operand images.  Every MMA operand is a K-major bf16 "panel": rows x 64 elements = rows x 128 B in the
+// canonical SWIZZLE_128B layout (8-row atoms of 1024 B; 16-byte chunk c of row r stored at chunk c ^ (r & 7)).
+// A 128-channel operand is two panels; "hi" panels come first, "lo" panels second.  Producers write Q / K / V^T
+// straight into this image layout in HBM, so a consumer stages a whole operand tile with ONE bulk async copy
+// (cp.async.bulk -> TMA engine, mbarrier complete_tx) and no tensor map.  Per set b:
+//     Qimg[b][qt]   qt = 128-query tile : [Qhi 32K][Qlo 32K]                       (Q pre-scaled by log2e/sqrt(C))
+//     KVimg[b][kt]  kt = 64-key tile    : [Khi 16K][Klo 16K][V^Thi 16K][V^Tlo 16K]
+//
+// Kernels per layer (all warp-specialised, one CTA per SM, mbarrier pipelines):
+//   tc_chain<PCQ>   feat  -> PointCN -> feat1 (fp32, HBM) -> Q image                 weights resident in smem
+//   tc_chain<KV>    feat1 -> K image, V^T image
+//   tc_attention    flash-style: S = Q K^T into TMEM, SC-weighted online softmax by 128 row-owner threads,
+//                   P (bf16 hi/lo) through smem, O += P V in TMEM; lazy rescale; msg (fp32, HBM)
+//   tc_chain<MSG>   msg -> fc_message chain -> + feat1 -> feat (fp32, HBM)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
 #include "encoder_tc.h"
+#include "kernels.h"
+#include "tc_ptx.cuh"
+
 namespace pdsc {
-int tc_build_weights(const TcLayerHost*, int num_layers, TcWeights* out) { out->num_layers = num_layers; return 0; }
-void tc_free_weights(TcWeights* w) { if (w->arena) cudaFree(w->arena); w->arena = nullptr; }
-size_t tc_scratch_bytes(int, int) { return 256; }
-int tc_launches(int) { return 0; }
-int tc_encoder_forward(const TcWeights&, const TcForwardArgs&, cudaStream_t) { return (int)cudaErrorNotSupported; }
+
+using namespace ptx;
+
+// ---- weight arena layout (bytes, per layer) ------------------------------------------------------------
+constexpr size_t kW1 = 0, kWq = 65536, kWk = 131072, kWv = 196608, kWm0 = 262144, kWm1 = 294912, kWm2 = 311296,
+                 kBias = 344064, kLayerBytes = 348160;
+// bias block (floats): b1[128] bq[128] bk[128] bv[128] bm0[64] bm1[64] bm2[128]
+constexpr int kB1 = 0, kBq = 128, kBk = 256, kBv = 384, kBm0 = 512, kBm1 = 576, kBm2 = 640, kBiasFloats = 768;
+
+constexpr float kQScale = 1.4426950408889634f / 11.313708498984761f;  // log2(e) / sqrt(128)
+
+static uint16_t bf16_bits(float x) {
+  __nv_bfloat16 h = __float2bfloat16_rn(x);
+  uint16_t b;
+  std::memcpy(&b, &h, 2);
+  return b;
+}
+static float bf16_to_float(uint16_t b) {
+  uint32_t u = (uint32_t)b << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
+// W [rows][K] fp32 (row-major) * scale  ->  [hi panels][lo panels]
+static void build_image(const float* W, int rows, int K, double scale, uint8_t* dst) {
+  const int panels = K / 64;
+  const size_t panel_bytes = (size_t)rows * 128;
+  uint8_t* hi = dst;
+  uint8_t* lo = dst + panels * panel_bytes;
+  for (int r = 0; r < rows; ++r)
+    for (int k = 0; k < K; ++k) {
+      const float x = (float)((double)W[(size_t)r * K + k] * scale);
+      const uint16_t h = bf16_bits(x);
+      const uint16_t l = bf16_bits(x - bf16_to_float(h));
+      const size_t off = (size_t)(k / 64) * panel_bytes + sw128_offset((uint32_t)r, (uint32_t)(k % 64));
+      std::memcpy(hi + off, &h, 2);
+      std::memcpy(lo + off, &l, 2);
+    }
+}
+
+int tc_build_weights(const TcLayerHost* layers, int num_layers, TcWeights* out) {
+  tc_free_weights(out);
+  std::vector<uint8_t> host((size_t)num_layers * kLayerBytes, 0);
+  for (int l = 0; l < num_layers; ++l) {
+    uint8_t* base = host.data() + (size_t)l * kLayerBytes;
+    const TcLayerHost& L = layers[l];
+    build_image(L.w1, 128, 128, 1.0, base + kW1);
+    build_image(L.wq, 128, 128, (double)kQScale, base + kWq);
+    build_image(L.wk, 128, 128, 1.0, base + kWk);
+    build_image(L.wv, 128, 128, 1.0, base + kWv);
+    build_image(L.wm0, 64, 128, 1.0, base + kWm0);
+    build_image(L.wm1, 64, 64, 1.0, base + kWm1);
+    build_image(L.wm2, 128, 64, 1.0, base + kWm2);
+    float* b = reinterpret_cast<float*>(base + kBias);
+    for (int i = 0; i < 128; ++i) {
+      b[kB1 + i] = L.b1[i];
+      b[kBq + i] = (float)((double)L.bq[i] * (double)kQScale);
+      b[kBk + i] = L.bk[i];
+      b[kBv + i] = L.bv[i];
+      b[kBm2 + i] = L.bm2[i];
+    }
+    for (int i = 0; i < 64; ++i) {
+      b[kBm0 + i] = L.bm0[i];
+      b[kBm1 + i] = L.bm1[i];
+    }
+  }
+  cudaError_t err = cudaMalloc(&out->arena, host.size());
+  if (err != cudaSuccess) return (int)err;
+  err = cudaMemcpy(out->arena, host.data(), host.size(), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) return (int)err;
+  out->arena_bytes = host.size();
+  out->num_layers = num_layers;
+  return 0;
+}
+
+void tc_free_weights(TcWeights* w) {
+  if (w->arena) cudaFree(w->arena);
+  w->arena = nullptr;
+  w->arena_bytes = 0;
+}
+
+static inline int q_tiles(int N) { return (N + 127) / 128; }
+static inline int k_tiles(int N) { return (N + 63) / 64; }
+
+size_t tc_scratch_bytes(int B, int N) {
+  return ((size_t)B * q_tiles(N) + (size_t)B * k_tiles(N)) * 65536 + 1024;
+}
+
+int tc_launches(int num_layers) { return 2 + 4 * num_layers; }  // layer0 + pad clear + 4 per layer
+
+// =========================================================================================================
+// tc_chain: fused row-tile GEMM chains with resident weights
+// =========================================================================================================
+enum ChainMode { kPCQ = 0, kKV = 1, kMSG = 2 };
+
+struct ChainArgs {
+  long long rows;        // B * N
+  int N, QT, KT, split;
+  const float* in;       // [rows][128] fp32 A operand
+  const float* res;      // MSG: feat1 (residual)
+  float* out_f32;        // PCQ: feat1, MSG: feat
+  uint8_t* qimg;
+  uint8_t* kvimg;
+  const uint8_t* wimg;   // this kernel's weight images (contiguous)
+  const float* bias;     // the layer's bias block
+  int wbytes;            // bytes of weight images to stage
+};
+
+constexpr int kChainAbuf = 65536;
+constexpr int kChainSmem = kChainAbuf + 131072 + kBiasFloats * 4 + 64 + 1024;  // + alignment slack
+constexpr int kChainThreads = 160;
+
+// issue one GEMM step: D[128 x Nout] (+)= A[128 x K] * W[Nout x K]^T, optionally as three hi/lo products
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_panel_bytes,
+                                           uint32_t b_hi, uint32_t b_lo, uint32_t b_panel_bytes, int K, int Nout,
+                                           int split, uint32_t accumulate) {
+  const uint32_t idesc = idesc_bf16_f32(128, Nout);
+  const int terms = split ? 3 : 1;
+  uint32_t acc = accumulate;
+  for (int t = 0; t < terms; ++t) {
+    const uint32_t a = (t == 2) ? a_lo : a_hi;
+    const uint32_t b = (t == 1) ? b_lo : b_hi;
+    for (int p = 0; p < K / 64; ++p) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        mma_bf16(d_tmem, smem_desc_sw128(a + p * a_panel_bytes + ks * 32), smem_desc_sw128(b + p * b_panel_bytes + ks * 32),
+                 idesc, acc);
+        acc = 1;
+      }
+    }
+  }
+}
+
+// 8 consecutive fp32 values -> one 16-byte hi chunk and one 16-byte lo chunk
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
+  split_pair(x[0], x[1], hi.x, lo.x);
+  split_pair(x[2], x[3], hi.y, lo.y);
+  split_pair(x[4], x[5], hi.z, lo.z);
+  split_pair(x[6], x[7], hi.w, lo.w);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Abuf = smem;                       // [hi p0 16K][hi p1 16K][lo p0 16K][lo p1 16K]
+  uint8_t* Wbuf = smem + kChainAbuf;          // weight images, contiguous as in the arena
+  float* bias = reinterpret_cast<float*>(Wbuf + 131072);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias + kBiasFloats);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const uint32_t bar_w = smem_u32(bars + 0), bar_a = smem_u32(bars + 1), bar_d = smem_u32(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t a_base = smem_u32(Abuf), w_base = smem_u32(Wbuf);
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_a, 128);
+    mbar_init(bar_d, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), 256);
+  for (int i = tid; i < kBiasFloats; i += kChainThreads) bias[i] = a.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {  // stage the resident weights with one bulk copy per 32 KB
+    mbar_expect_tx(bar_w, (uint32_t)a.wbytes);
+    for (int off = 0; off < a.wbytes; off += 32768)
+      bulk_g2s(w_base + off, a.wimg + off, (uint32_t)min(32768, a.wbytes - off), bar_w);
+  }
+
+  const long long num_tiles = (a.rows + 127) / 128;
+  constexpr int kSteps = (MODE == kMSG) ? 3 : 2;
+
+  if (warp == 4) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      mbar_wait(bar_w, 0);
+      uint32_t pa = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int step = 0; step < kSteps; ++step) {
+          mbar_wait(bar_a, pa);
+          pa ^= 1;
+          tc_fence_after();
+          if (MODE == kPCQ) {
+            // step 0: W1 (Wbuf + 0), step 1: Wq (Wbuf + 64K); both 128 x 128
+            const uint32_t wb = w_base + step * 65536;
+            issue_gemm(tmem + step * 128, a_base, a_base + 32768, 16384, wb, wb + 32768, 16384, 128, 128, a.split, 0);
+          } else if (MODE == kKV) {
+            const uint32_t wb = w_base + step * 65536;  // Wk, Wv
+            issue_gemm(tmem + step * 128, a_base, a_base + 32768, 16384, wb, wb + 32768, 16384, 128, 128, a.split, 0);
+          } else {
+            if (step == 0) {         // Wm0: 64 x 128  (hi 16K, lo 16K; panel = 64 rows * 128 B = 8K)
+              issue_gemm(tmem + 0, a_base, a_base + 32768, 16384, w_base, w_base + 16384, 8192, 128, 64, a.split, 0);
+            } else if (step == 1) {  // Wm1: 64 x 64   (hi 8K, lo 8K)
+              issue_gemm(tmem + 64, a_base, a_base + 32768, 16384, w_base + 32768, w_base + 32768 + 8192, 8192, 64, 64,
+                         a.split, 0);
+            } else {                 // Wm2: 128 x 64  (hi 16K, lo 16K)
+              issue_gemm(tmem + 128, a_base, a_base + 32768, 16384, w_base + 49152, w_base + 49152 + 16384, 16384, 64,
+                         128, a.split, 0);
+            }
+          }
+          mma_commit(bar_d);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== row threads: tile loader + epilogues; thread <-> row of the 128-row tile, TMEM lane = row =====
+    const int r = tid;  // 0..127
+    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    uint32_t pd = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const long long row0 = tile * 128;
+      // ---- coalesced fp32 tile load -> hi/lo split -> swizzled A image ----
+#pragma unroll 4
+      for (int rr = 0; rr < 32; ++rr) {
+        const int lr = warp * 32 + rr;
+        const long long grow = row0 + lr;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (grow < a.rows) v = *reinterpret_cast<const float4*>(a.in + grow * kC + lane * 4);
+        uint32_t h0, l0, h1, l1;
+        split_pair(v.x, v.y, h0, l0);
+        split_pair(v.z, v.w, h1, l1);
+        const uint32_t off = (uint32_t)(lane >> 4) * 16384u + sw128_offset((uint32_t)lr, (uint32_t)(lane & 15) * 4u);
+        *reinterpret_cast<uint2*>(Abuf + off) = make_uint2(h0, h1);
+        if (a.split) *reinterpret_cast<uint2*>(Abuf + 32768 + off) = make_uint2(l0, l1);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_a);
+
+      const long long grow = row0 + r;
+      const bool live = grow < a.rows;
+      const int bidx = live ? (int)(grow / a.N) : 0;
+      const int n = live ? (int)(grow % a.N) : 0;
+
+      for (int step = 0; step < kSteps; ++step) {
+        mbar_wait(bar_d, pd);
+        pd ^= 1;
+        tc_fence_after();
+        const int ncols = (MODE == kMSG && step < 2) ? 64 : 128;
+        const uint32_t dcol = (MODE == kMSG) ? (step == 0 ? 0u : (step == 1 ? 64u : 128u)) : (uint32_t)step * 128u;
+        const float* bvec = bias + ((MODE == kPCQ) ? (step == 0 ? kB1 : kBq)
+                                    : (MODE == kKV) ? (step == 0 ? kBk : kBv)
+                                                    : (step == 0 ? kBm0 : (step == 1 ? kBm1 : kBm2)));
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(tmem + lane_base + dcol + c0, raw);
+          tmem_ld_wait();
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(raw[i]) + bvec[c0 + i];
+          const bool relu = (MODE == kPCQ && step == 0) || (MODE == kMSG && step < 2);
+          if (relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
+          }
+          if (MODE == kMSG && step == 2) {  // residual: feat = feat1 + fc_message(msg)
+            if (live) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 rv = *reinterpret_cast<const float4*>(a.res + grow * kC + c0 + i);
+                x[i] += rv.x; x[i + 1] += rv.y; x[i + 2] += rv.z; x[i + 3] += rv.w;
+              }
+            }
+          }
+          const bool to_f32 = (MODE == kPCQ && step == 0) || (MODE == kMSG && step == 2);
+          if (to_f32 && live) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(a.out_f32 + grow * kC + c0 + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+          }
+          const bool to_abuf = (MODE == kPCQ && step == 0) || (MODE == kMSG && step < 2);
+          if (to_abuf) {  // next step's A operand
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 hi, lo;
+              split8(x + g * 8, hi, lo);
+              const uint32_t kk = (uint32_t)(c0 + g * 8);
+              const uint32_t off = (kk >> 6) * 16384u + sw128_offset((uint32_t)r, kk & 63u);
+              *reinterpret_cast<uint4*>(Abuf + off) = hi;
+              if (a.split) *reinterpret_cast<uint4*>(Abuf + 32768 + off) = lo;
+            }
+          }
+          if (MODE == kPCQ && step == 1 && live) {  // Q image
+            uint8_t* base = a.qimg + ((size_t)bidx * a.QT + (n >> 7)) * 65536;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 hi, lo;
+              split8(x + g * 8, hi, lo);
+              const uint32_t kk = (uint32_t)(c0 + g * 8);
+              const uint32_t off = (kk >> 6) * 16384u + sw128_offset((uint32_t)(n & 127), kk & 63u);
+              *reinterpret_cast<uint4*>(base + off) = hi;
+              if (a.split) *reinterpret_cast<uint4*>(base + 32768 + off) = lo;
+            }
+          }
+          if (MODE == kKV && step == 0 && live) {  // K image: 64-key tiles, panel = 64 rows * 128 B
+            uint8_t* base = a.kvimg + ((size_t)bidx * a.KT + (n >> 6)) * 65536;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 hi, lo;
+              split8(x + g * 8, hi, lo);
+              const uint32_t kk = (uint32_t)(c0 + g * 8);
+              const uint32_t off = (kk >> 6) * 8192u + sw128_offset((uint32_t)(n & 63), kk & 63u);
+              *reinterpret_cast<uint4*>(base + off) = hi;
+              if (a.split) *reinterpret_cast<uint4*>(base + 16384 + off) = lo;
+            }
+          }
+          if (MODE == kKV && step == 1 && live) {  // V^T image: row = channel, column = key within the tile
+            uint8_t* base = a.kvimg + ((size_t)bidx * a.KT + (n >> 6)) * 65536 + 32768;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const __nv_bfloat16 h = __float2bfloat16_rn(x[i]);
+              const uint32_t off = sw128_offset((uint32_t)(c0 + i), (uint32_t)(n & 63));
+              *reinterpret_cast<__nv_bfloat16*>(base + off) = h;
+              if (a.split) *reinterpret_cast<__nv_bfloat16*>(base + 16384 + off) = __float2bfloat16_rn(x[i] - __bfloat162float(h));
+            }
+          }
+        }
+        if (step + 1 < kSteps) {
+          fence_proxy_async_smem();  // A image written through the generic proxy, read by the tensor core
+          tc_fence_before();
+          mbar_arrive(bar_a);
+        }
+      }
+      tc_fence_before();  // this tile's TMEM reads are ordered before the next tile's first arrive
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 256);
+}
+
+// =========================================================================================================
+// tc_attention
+// =========================================================================================================
+struct AttnArgs {
+  int N, NS, QT, KT, split;
+  const uint8_t* qimg;
+  const uint8_t* kvimg;
+  const float* sc;
+  float* msg;
+};
+
+constexpr int kAttnThreads = 192;
+constexpr int kAttnQ = 0, kAttnK = 65536, kAttnV = 131072, kAttnP = 196608, kAttnBars = 229376;
+constexpr int kAttnSmemTc = kAttnBars + 256 + 1024;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays below 2^8 before the reference max is advanced
+
+__global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAttnBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t s0 = smem_u32(smem);
+  const uint32_t q_full = smem_u32(bars + 0);
+  const uint32_t k_full[2] = {smem_u32(bars + 1), smem_u32(bars + 2)};
+  const uint32_t k_empty[2] = {smem_u32(bars + 3), smem_u32(bars + 4)};
+  const uint32_t v_full[2] = {smem_u32(bars + 5), smem_u32(bars + 6)};
+  const uint32_t v_empty[2] = {smem_u32(bars + 7), smem_u32(bars + 8)};
+  const uint32_t s_full[2] = {smem_u32(bars + 9), smem_u32(bars + 10)};
+  const uint32_t s_empty[2] = {smem_u32(bars + 11), smem_u32(bars + 12)};
+  const uint32_t p_full = smem_u32(bars + 13), p_empty = smem_u32(bars + 14);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / a.QT, qt = blockIdx.x % a.QT;
+  const int T = a.KT;
+
+  if (tid == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(k_full[i], 1); mbar_init(k_empty[i], 1);
+      mbar_init(v_full[i], 1); mbar_init(v_empty[i], 1);
+      mbar_init(s_full[i], 1); mbar_init(s_empty[i], 128);
+    }
+    mbar_init(p_full, 128);
+    mbar_init(p_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS[2] = {tmem + 0, tmem + 64};
+  const uint32_t tO = tmem + 128;
+
+  if (warp == 0) {
+    // ===== loader: bulk async copies of ready-made operand images =====
+    if (lane == 0) {
+      const uint8_t* qsrc = a.qimg + ((size_t)b * a.QT + qt) * 65536;
+      const uint32_t qbytes = a.split ? 65536u : 32768u;
+      mbar_expect_tx(q_full, qbytes);
+      bulk_g2s(s0 + kAttnQ, qsrc, 32768u, q_full);
+      if (a.split) bulk_g2s(s0 + kAttnQ + 32768, qsrc + 32768, 32768u, q_full);
+      const uint32_t half = a.split ? 32768u : 16384u;
+      for (int j = 0; j < T; ++j) {
+        const int s = j & 1, u = j >> 1;
+        const uint8_t* src = a.kvimg + ((size_t)b * a.KT + j) * 65536;
+        if (j >= 2) mbar_wait(k_empty[s], (uint32_t)((u - 1) & 1));
+        mbar_expect_tx(k_full[s], half);
+        bulk_g2s(s0 + kAttnK + s * 32768, src, half, k_full[s]);
+        if (j >= 2) mbar_wait(v_empty[s], (uint32_t)((u - 1) & 1));
+        mbar_expect_tx(v_full[s], half);
+        bulk_g2s(s0 + kAttnV + s * 32768, src + 32768, half, v_full[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t q_hi = s0 + kAttnQ, q_lo = s0 + kAttnQ + 32768;
+      const uint32_t p_hi = s0 + kAttnP, p_lo = s0 + kAttnP + 16384;
+      mbar_wait(q_full, 0);
+      mbar_wait(k_full[0], 0);
+      tc_fence_after();
+      issue_gemm(tS[0], q_hi, q_lo, 16384, s0 + kAttnK, s0 + kAttnK + 16384, 8192, 128, 64, a.split, 0);
+      mma_commit(s_full[0]);
+      mma_commit(k_empty[0]);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) {
+          const int s1 = (j + 1) & 1, u1 = (j + 1) >> 1;
+          mbar_wait(k_full[s1], (uint32_t)(u1 & 1));
+          if (j + 1 >= 2) mbar_wait(s_empty[s1], (uint32_t)((u1 - 1) & 1));
+          tc_fence_after();
+          const uint32_t kb = s0 + kAttnK + s1 * 32768;
+          issue_gemm(tS[s1], q_hi, q_lo, 16384, kb, kb + 16384, 8192, 128, 64, a.split, 0);
+          mma_commit(s_full[s1]);
+          mma_commit(k_empty[s1]);
+        }
+        const int s = j & 1, u = j >> 1;
+        mbar_wait(p_full, (uint32_t)(j & 1));
+        mbar_wait(v_full[s], (uint32_t)(u & 1));
+        tc_fence_after();
+        const uint32_t vb = s0 + kAttnV + s * 32768;
+        issue_gemm(tO, p_hi, p_lo, 16384, vb, vb + 16384, 16384, 64, 128, a.split, j > 0 ? 1u : 0u);
+        mma_commit(p_empty);
+        mma_commit(v_empty[s]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== softmax: one thread owns one query row (TMEM lane) =====
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
+    const int qi = qt * 128 + r;
+    const int qic = min(qi, a.N - 1);
+    const float* scb = a.sc + (size_t)b * a.N * a.NS + qic;  // SC is symmetric: read column qi, coalesced over r
+    uint8_t* Pbuf = smem + kAttnP;
+    float m_ref = -INFINITY, l_sum = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const int s = j & 1, u = j >> 1;
+      const int j0 = j * 64;
+      float scv[64];
+#pragma unroll
+      for (int c = 0; c < 64; ++c) scv[c] = (j0 + c < a.N) ? __ldg(scb + (size_t)(j0 + c) * a.NS) : 0.f;
+      mbar_wait(s_full[s], (uint32_t)(u & 1));
+      tc_fence_after();
+      uint32_t raw0[32], raw1[32];
+      tmem_ld32(tS[s] + lane_base, raw0);
+      tmem_ld32(tS[s] + lane_base + 32, raw1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_empty[s]);
+      float p[64];
+      float tmax = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        const float sv = __uint_as_float(c < 32 ? raw0[c & 31] : raw1[c & 31]);
+        p[c] = (j0 + c < a.N) ? sv * scv[c] : -INFINITY;
+        tmax = fmaxf(tmax, p[c]);
+      }
+      const bool advance = (j == 0) || (tmax > m_ref + kRescaleThreshold);
+      const float new_ref = advance ? tmax : m_ref;
+      float rsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        p[c] = exp2f(p[c] - new_ref);
+        rsum += p[c];
+      }
+      const bool rescale_any = __any_sync(0xffffffffu, advance && j > 0);
+      if (j > 0) {
+        mbar_wait(p_empty, (uint32_t)((j - 1) & 1));  // PV_{j-1} done: P smem free, O quiescent
+        tc_fence_after();
+      }
+      if (rescale_any) {
+        const float scale = (advance && j > 0) ? exp2f(m_ref - new_ref) : 1.0f;
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t o[32];
+          tmem_ld32(tO + lane_base + c0, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * scale);
+          tmem_st32(tO + lane_base + c0, o);
+        }
+        tmem_st_wait();
+        l_sum *= scale;
+      }
+      m_ref = new_ref;
+      l_sum += rsum;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 hi, lo;
+        split8(p + g * 8, hi, lo);
+        const uint32_t off = sw128_offset((uint32_t)r, (uint32_t)(g * 8));
+        *reinterpret_cast<uint4*>(Pbuf + off) = hi;
+        if (a.split) *reinterpret_cast<uint4*>(Pbuf + 16384 + off) = lo;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(p_empty, (uint32_t)((T - 1) & 1));
+    tc_fence_after();
+    const float inv_l = 1.0f / l_sum;
+    float* dst = a.msg + ((size_t)b * a.N + qi) * kC;
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t o[32];
+      tmem_ld32(tO + lane_base + c0, o);
+      tmem_ld_wait();
+      if (qi < a.N) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(dst + c0 + i) =
+              make_float4(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l,
+                          __uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 256);
+}
+
+// ---- zero the never-written pad rows/columns of the last key tile of every set ---------------------------
+__global__ void tc_clear_pads_kernel(uint8_t* kvimg, int N, int KT) {
+  const int b = blockIdx.x;
+  const int first_pad = N & 63;
+  if (first_pad == 0) return;
+  uint8_t* base = kvimg + ((size_t)b * KT + (KT - 1)) * 65536;
+  const int pads = 64 - first_pad;
+  // K rows n in [first_pad, 64): both panels, hi and lo;  V^T columns likewise for all 128 channel rows
+  for (int t = threadIdx.x; t < pads * 128; t += blockDim.x) {
+    const uint32_t n = (uint32_t)(first_pad + t / 128), c = (uint32_t)(t % 128);
+    const uint32_t koff = (c >> 6) * 8192u + sw128_offset(n, c & 63u);
+    *reinterpret_cast<uint16_t*>(base + koff) = 0;
+    *reinterpret_cast<uint16_t*>(base + 16384 + koff) = 0;
+    const uint32_t voff = sw128_offset(c, n);
+    *reinterpret_cast<uint16_t*>(base + 32768 + voff) = 0;
+    *reinterpret_cast<uint16_t*>(base + 49152 + voff) = 0;
+  }
+}
+
+// ---- debug: decode operand images back to fp32 [B*N][128] -------------------------------------------------
+__global__ void tc_decode_kernel(const uint8_t* qimg, const uint8_t* kvimg, float* q, float* k, float* v, long long rows,
+                                 int N, int QT, int KT, int split) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = idx / kC;
+  const uint32_t c = (uint32_t)(idx % kC);
+  if (row >= rows) return;
+  const int b = (int)(row / N), n = (int)(row % N);
+  auto rd = [](const uint8_t* p) { return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p)); };
+  const uint8_t* qb = qimg + ((size_t)b * QT + (n >> 7)) * 65536;
+  const uint32_t qo = (c >> 6) * 16384u + sw128_offset((uint32_t)(n & 127), c & 63u);
+  q[idx] = rd(qb + qo) + (split ? rd(qb + 32768 + qo) : 0.f);
+  const uint8_t* kb = kvimg + ((size_t)b * KT + (n >> 6)) * 65536;
+  const uint32_t ko = (c >> 6) * 8192u + sw128_offset((uint32_t)(n & 63), c & 63u);
+  k[idx] = rd(kb + ko) + (split ? rd(kb + 16384 + ko) : 0.f);
+  const uint32_t vo = sw128_offset(c, (uint32_t)(n & 63));
+  v[idx] = rd(kb + 32768 + vo) + (split ? rd(kb + 49152 + vo) : 0.f);
+}
+
+// =========================================================================================================
+// host orchestration
+// =========================================================================================================
+static int g_num_sms = 0;
+
+static cudaError_t tc_configure() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  cudaError_t e;
+  int dev = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if ((e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(tc_chain_kernel<kPCQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem))) return e;
+  if ((e = cudaFuncSetAttribute(tc_chain_kernel<kKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem))) return e;
+  if ((e = cudaFuncSetAttribute(tc_chain_kernel<kMSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem))) return e;
+  if ((e = cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTc))) return e;
+  done = true;
+  return cudaSuccess;
+}
+
+int tc_encoder_forward(const TcWeights& w, const TcForwardArgs& a, cudaStream_t st) {
+  cudaError_t e = tc_configure();
+  if (e != cudaSuccess) return (int)e;
+  const long long rows = (long long)a.B * a.N;
+  const int QT = q_tiles(a.N), KT = k_tiles(a.N);
+  uint8_t* qimg = static_cast<uint8_t*>(a.scratch);
+  qimg = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(qimg) + 1023) & ~uintptr_t(1023));
+  uint8_t* kvimg = qimg + (size_t)a.B * QT * 65536;
+  const long long tiles = (rows + 127) / 128;
+  const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+
+  launch_layer0(a.corr_pos, a.l0w, a.l0b, a.feat, rows, a.in_dim, st);
+  tc_clear_pads_kernel<<<a.B, 256, 0, st>>>(kvimg, a.N, KT);
+  for (int l = 0; l < a.num_layers; ++l) {
+    const uint8_t* base = static_cast<const uint8_t*>(w.arena) + (size_t)l * kLayerBytes;
+    ChainArgs c{};
+    c.rows = rows; c.N = a.N; c.QT = QT; c.KT = KT; c.split = a.split;
+    c.qimg = qimg; c.kvimg = kvimg; c.bias = reinterpret_cast<const float*>(base + kBias);
+    // PointCN + Q
+    c.in = a.feat; c.res = nullptr; c.out_f32 = a.feat1; c.wimg = base + kW1; c.wbytes = 131072;
+    tc_chain_kernel<kPCQ><<<grid, kChainThreads, kChainSmem, st>>>(c);
+    // K + V
+    c.in = a.feat1; c.out_f32 = nullptr; c.wimg = base + kWk; c.wbytes = 131072;
+    tc_chain_kernel<kKV><<<grid, kChainThreads, kChainSmem, st>>>(c);
+    // attention
+    AttnArgs at{a.N, a.NS, QT, KT, a.split, qimg, kvimg, a.sc, a.msg};
+    tc_attention_kernel<<<a.B * QT, kAttnThreads, kAttnSmemTc, st>>>(at);
+    if (a.debug_out && a.debug_layer == l) {
+      const size_t plane = (size_t)rows * kC;
+      cudaMemcpyAsync(a.debug_out, a.feat1, plane * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      tc_decode_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(qimg, kvimg, a.debug_out + plane, a.debug_out + 2 * plane,
+                                                                        a.debug_out + 3 * plane, rows, a.N, QT, KT, a.split);
+      cudaMemcpyAsync(a.debug_out + 4 * plane, a.msg, plane * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    }
+    // fc_message + residual
+    c.in = a.msg; c.res = a.feat1; c.out_f32 = a.feat; c.wimg = base + kWm0; c.wbytes = 81920;
+    tc_chain_kernel<kMSG><<<grid, kChainThreads, kChainSmem, st>>>(c);
+    if (a.layer_tap_out && a.layer_tap == l)
+      cudaMemcpyAsync(a.layer_tap_out, a.feat, (size_t)rows * kC * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  }
+  return (int)cudaGetLastError();
+}
+
 }  // namespace pdsc

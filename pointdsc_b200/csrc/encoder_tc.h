@@ -30,6 +30,8 @@ struct TcForwardArgs {
   void* scratch;             // tc_scratch_bytes(B, N)
   int layer_tap;             // -1 or layer index to copy out
   float* layer_tap_out;
+  int debug_layer;           // layer whose internals are decoded into debug_out
+  float* debug_out;          // [5][B*N][128]: feat1, q (scaled by log2e/sqrt(C)), k, v, msg — or nullptr
 };
 
 int tc_build_weights(const TcLayerHost* layers, int num_layers, TcWeights* out);  // returns cudaError_t

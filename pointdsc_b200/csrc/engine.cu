@@ -215,6 +215,11 @@ int encoder_simt(const pdsc_engine* e, const Workspace& w, int B, int N, const f
     lin(w.feat_b, kC, L.wk, L.bk, nullptr, w.k, kC, 0);
     lin(w.feat_b, kC, L.wv, L.bv, nullptr, w.v, kC, 0);
     launch_attention_simt(w.q, w.k, w.v, w.sc, w.msg, B, N, NS, st);
+    if (io && io->out_layer_debug && io->layer_tap == l) {
+      const size_t plane = (size_t)R * kC;
+      const float* srcs[5] = {w.feat_b, w.q, w.k, w.v, w.msg};
+      for (int i = 0; i < 5; ++i) copy_tap(io->out_layer_debug + i * plane, srcs[i], plane * sizeof(float), st);
+    }
     lin(w.msg, kC, L.wm0, L.bm0, nullptr, w.h1, 64, 1);                  // fc_message.0-2
     lin(w.h1, 64, L.wm1, L.bm1, nullptr, w.h2, 64, 1);                   // fc_message.3-5
     lin(w.h2, 64, L.wm2, L.bm2, w.feat_b, w.feat_a, kC, 0);              // fc_message.6 + residual
@@ -413,6 +418,8 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
       a.sc = w.sc; a.feat = w.feat_a; a.feat1 = w.feat_b; a.msg = w.msg; a.scratch = w.tc_scratch;
       a.layer_tap = (io && io->out_layer_features) ? io->layer_tap : -1;
       a.layer_tap_out = io ? io->out_layer_features : nullptr;
+      a.debug_layer = io ? io->layer_tap : -1;
+      a.debug_out = io ? io->out_layer_debug : nullptr;
       const int rc = tc_encoder_forward(e->tc, a, st);
       if (rc) return fail(PDSC_ERR_CUDA, "tensor-core encoder launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     }

@@ -44,6 +44,7 @@ _TAP_SPECS = {
     "init_trans": (torch.float32, lambda B, N, S, k, c: (B, 4, 4)),
     "refine_solves": (torch.int32, lambda B, N, S, k, c: (B,)),
     "layer_features": (torch.float32, lambda B, N, S, k, c: (B, N, c)),
+    "layer_debug": (torch.float32, lambda B, N, S, k, c: (5, B, N, c)),
 }
 _INJECT_DTYPES = {"features": torch.float32, "confidence": torch.float32, "seeds": torch.int32,
                   "knn_idx": torch.int32, "seed_trans": torch.float32}
