@@ -136,6 +136,27 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
 int pdsc_forward_host(pdsc_engine* e, int32_t B, int32_t N, const float* h_corr_pos, const float* h_src_keypts,
                       const float* h_tgt_keypts, float* h_final_trans, float* h_final_labels, void* cuda_stream);
 
+/* ---- live profiling with CUDA events on the caller's stream ------------------------------------------
+ * When enabled, pdsc_forward() records an event pair around each stage below (and around EVERY launch of
+ * the dominant kernel, the per-layer attention).  pdsc_profile_read() waits for the last forward's events
+ * and returns, per span, the accumulated milliseconds and the number of launches since the last read.
+ * Not capturable in a CUDA graph; costs two event records per span. */
+typedef enum pdsc_span {
+  PDSC_SPAN_SC = 0,          /* a1  sc_matrix                                   */
+  PDSC_SPAN_LINEAR = 1,      /* a2  layer0 + PointCN/QKV/fc_message kernels     */
+  PDSC_SPAN_ATTENTION = 2,   /* a3  attention kernel (one span per layer)       */
+  PDSC_SPAN_HEAD = 3,        /* a4+a5                                           */
+  PDSC_SPAN_SEEDS = 4,       /* a6                                              */
+  PDSC_SPAN_KNN = 5,         /* a7                                              */
+  PDSC_SPAN_NSM = 6,         /* a8+a9                                           */
+  PDSC_SPAN_HYPOTHESES = 7,  /* a10+a11                                         */
+  PDSC_SPAN_REFINE = 8,      /* a11 labels + a12                                */
+  PDSC_SPAN_TOTAL = 9,       /* whole pdsc_forward                              */
+  PDSC_SPAN_COUNT = 10
+} pdsc_span;
+int pdsc_profile_enable(pdsc_engine* e, int32_t enable);
+int pdsc_profile_read(pdsc_engine* e, float* ms_out /* [PDSC_SPAN_COUNT] */, int32_t* launches_out /* [PDSC_SPAN_COUNT] */);
+
 /* Number of kernels one pdsc_forward(B,N) call launches at the current precision (bench.py's
  * `gpu_launches`). */
 int32_t pdsc_launches_per_forward(const pdsc_engine* e, int32_t B, int32_t N);

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpointdsc_b200.so")
 
 PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+SPANS = ["sc", "linear", "attention", "head", "seeds", "knn", "nsm", "hypotheses", "refine", "total"]
 
 
 class PdscError(RuntimeError):
@@ -59,6 +60,8 @@ SYMBOLS = {
     "pdsc_forward_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "pdsc_launches_per_forward": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
+    "pdsc_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
+    "pdsc_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
 
 _lib = None

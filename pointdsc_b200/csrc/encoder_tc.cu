@@ -656,7 +656,9 @@ int tc_encoder_forward(const TcWeights& w, const TcForwardArgs& a, cudaStream_t 
     tc_chain_kernel<kKV><<<grid, kChainThreads, kChainSmem, st>>>(c);
     // attention
     AttnArgs at{a.N, a.NS, QT, KT, a.split, qimg, kvimg, a.sc, a.msg};
+    if (a.attn_events) cudaEventRecord(a.attn_events[2 * l], st);
     tc_attention_kernel<<<a.B * QT, kAttnThreads, kAttnSmemTc, st>>>(at);
+    if (a.attn_events) cudaEventRecord(a.attn_events[2 * l + 1], st);
     if (a.debug_out && a.debug_layer == l) {
       const size_t plane = (size_t)rows * kC;
       cudaMemcpyAsync(a.debug_out, a.feat1, plane * sizeof(float), cudaMemcpyDeviceToDevice, st);

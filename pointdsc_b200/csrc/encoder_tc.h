@@ -32,6 +32,7 @@ struct TcForwardArgs {
   float* layer_tap_out;
   int debug_layer;           // layer whose internals are decoded into debug_out
   float* debug_out;          // [5][B*N][128]: feat1, q (scaled by log2e/sqrt(C)), k, v, msg — or nullptr
+  cudaEvent_t* attn_events;  // nullptr or 2 events per layer, recorded around the attention launch
 };
 
 int tc_build_weights(const TcLayerHost* layers, int num_layers, TcWeights* out);  // returns cudaError_t

@@ -75,6 +75,12 @@ struct pdsc_engine {
   size_t host_ws_bytes = 0;
   float* host_io = nullptr;
   size_t host_io_floats = 0;
+  // live profiling (pdsc_profile_*)
+  bool profiling = false;
+  bool profile_pending = false;
+  std::vector<cudaEvent_t> ev;          // [0..2L) attention pairs, then stage boundary events
+  float span_ms[PDSC_SPAN_COUNT] = {};
+  int span_launches[PDSC_SPAN_COUNT] = {};
 };
 
 namespace {
@@ -193,7 +199,7 @@ float refinement_threshold(float ctor_threshold) {
 }
 
 int encoder_simt(const pdsc_engine* e, const Workspace& w, int B, int N, const float* corr_pos, const pdsc_stage_io* io,
-                 cudaStream_t st) {
+                 cudaEvent_t* attn_events, cudaStream_t st) {
   using namespace pdsc;
   const long long R = (long long)B * N;
   const int NS = round_up(N, 64);
@@ -214,7 +220,9 @@ int encoder_simt(const pdsc_engine* e, const Workspace& w, int B, int N, const f
     lin(w.feat_b, kC, L.wq, L.bq, nullptr, w.q, kC, 0);
     lin(w.feat_b, kC, L.wk, L.bk, nullptr, w.k, kC, 0);
     lin(w.feat_b, kC, L.wv, L.bv, nullptr, w.v, kC, 0);
+    if (attn_events) cudaEventRecord(attn_events[2 * l], st);
     launch_attention_simt(w.q, w.k, w.v, w.sc, w.msg, B, N, NS, st);
+    if (attn_events) cudaEventRecord(attn_events[2 * l + 1], st);
     if (io && io->out_layer_debug && io->layer_tap == l) {
       const size_t plane = (size_t)R * kC;
       const float* srcs[5] = {w.feat_b, w.q, w.k, w.v, w.msg};
@@ -272,6 +280,7 @@ int pdsc_destroy(pdsc_engine* e) {
   pdsc::tc_free_weights(&e->tc);
   cudaFree(e->host_ws);
   cudaFree(e->host_io);
+  for (auto& ev : e->ev) cudaEventDestroy(ev);
   delete e;
   return PDSC_OK;
 }
@@ -400,15 +409,26 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
   const int NS = round_up(N, 64);
   const int S = pdsc_num_seeds(e, N), k = pdsc_num_neighbours(e, N), T = e->cfg.num_iterations;
   const float* W = e->d_weights;
+  const int L = e->cfg.num_layers;
+  cudaEvent_t* attn_ev = nullptr;
+  cudaEvent_t* bev = nullptr;  // boundary events: 0 start, 1 sc, 2 encoder, 3 head, 4 seeds, 5 knn, 6 nsm, 7 hyp, 8 end
+  if (e->profiling) {
+    if (e->profile_pending) pdsc_profile_read(e, nullptr, nullptr);  // fold the previous forward before reusing events
+    attn_ev = inject_feat ? nullptr : e->ev.data();
+    bev = e->ev.data() + 2 * L;
+    cudaEventRecord(bev[0], st);
+  }
+  auto mark = [&](int i) { if (bev) cudaEventRecord(bev[i], st); };
 
   // ---- stages i + ii ------------------------------------------------------------------------------
   if (!inject_feat) {
     launch_sc_matrix(d_src, d_tgt, w.sc, B, N, NS, e->sigma_spat, st);
+    mark(1);
     if (io && io->out_sc)
       cudaMemcpy2DAsync(io->out_sc, (size_t)N * sizeof(float), w.sc, (size_t)NS * sizeof(float), (size_t)N * sizeof(float),
                         R, cudaMemcpyDeviceToDevice, st);
     if (e->cfg.precision == PDSC_FP32_SIMT) {
-      const int rc = encoder_simt(e, w, B, N, d_corr_pos, io, st);
+      const int rc = encoder_simt(e, w, B, N, d_corr_pos, io, attn_ev, st);
       if (rc) return rc;
     } else {
       TcForwardArgs a{};
@@ -420,12 +440,15 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
       a.layer_tap_out = io ? io->out_layer_features : nullptr;
       a.debug_layer = io ? io->layer_tap : -1;
       a.debug_out = io ? io->out_layer_debug : nullptr;
+      a.attn_events = attn_ev;
       const int rc = tc_encoder_forward(e->tc, a, st);
       if (rc) return fail(PDSC_ERR_CUDA, "tensor-core encoder launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     }
   } else {
     PDSC_CUDA(cudaMemcpyAsync(w.feat_a, io->in_features, R * kC * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
+  if (inject_feat) mark(1);
+  mark(2);
   if (io) copy_tap(io->out_features, w.feat_a, R * kC * sizeof(float), st);
 
   // ---- a4 + a5 ------------------------------------------------------------------------------------
@@ -438,6 +461,7 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
     copy_tap(io->out_confidence, w.conf, R * sizeof(float), st);
   }
 
+  mark(3);
   // ---- a6 -----------------------------------------------------------------------------------------
   if (S > 0) {
     if (io && io->in_seeds)
@@ -445,6 +469,7 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
     else
       launch_pick_seeds(d_src, w.conf, w.seeds, w.key, B, N, S, e->cfg.nms_radius, st);
     if (io) copy_tap(io->out_seeds, w.seeds, (size_t)B * S * sizeof(int32_t), st);
+    mark(4);
 
     // ---- a7 ---------------------------------------------------------------------------------------
     if (io && io->in_knn_idx) {
@@ -461,12 +486,14 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
       launch_knn_select(w.dist, w.knn, B, N, S, k, st);
     }
     if (io) copy_tap(io->out_knn_idx, w.knn, (size_t)B * S * k * sizeof(int32_t), st);
+    mark(5);
 
     // ---- a8 + a9 ----------------------------------------------------------------------------------
     launch_fill_u32(w.conv_mask, 0xFFFFFFFFu, B, st);
     launch_fill_u64(w.best_key, 0ull, B, st);
     launch_nsm_power(w.normed, d_src, d_tgt, w.knn, w.iterates, w.conv_mask, io ? io->out_compat : nullptr, B, N, S, k, T,
                      e->sigma, e->sigma_spat, st);
+    mark(6);
     // ---- a10 + a11 --------------------------------------------------------------------------------
     launch_seed_hypotheses(d_src, d_tgt, w.knn, w.iterates, w.conv_mask, io ? io->in_seed_trans : nullptr, w.seed_trans,
                            w.counts, w.best_key, io ? io->out_eig : nullptr, io ? io->out_power_iters : nullptr, B, N, S,
@@ -475,15 +502,73 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
       copy_tap(io->out_seed_trans, w.seed_trans, (size_t)B * S * 16 * sizeof(float), st);
       copy_tap(io->out_inlier_counts, w.counts, (size_t)B * S * sizeof(int32_t), st);
     }
+    mark(7);
   } else {
     launch_fill_u64(w.best_key, 0ull, B, st);
+    mark(4); mark(5); mark(6); mark(7);
   }
   // ---- a11 (labels) + a12 ---------------------------------------------------------------------------
   launch_select_refine(d_src, d_tgt, w.seed_trans, w.best_key, d_final_trans, d_final_labels,
                        io ? io->out_init_trans : nullptr, io ? io->out_best : nullptr,
                        io ? io->out_refine_solves : nullptr, B, N, S, e->cfg.inlier_threshold,
                        refinement_threshold(e->cfg.inlier_threshold), 20, st);
+  mark(8);
+  if (bev) {
+    e->profile_pending = true;
+    e->span_launches[PDSC_SPAN_ATTENTION] += inject_feat ? 0 : L;
+    e->span_launches[PDSC_SPAN_TOTAL] += 1;
+  }
   PDSC_CUDA(cudaGetLastError());
+  return PDSC_OK;
+}
+
+int pdsc_profile_enable(pdsc_engine* e, int32_t enable) {
+  if (!e) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine");
+  DeviceGuard g(e->cfg.device);
+  if (enable && e->ev.empty()) {
+    e->ev.resize(2 * e->cfg.num_layers + 9);
+    for (auto& ev : e->ev) PDSC_CUDA(cudaEventCreate(&ev));
+  }
+  e->profiling = enable != 0;
+  e->profile_pending = false;
+  for (int i = 0; i < PDSC_SPAN_COUNT; ++i) { e->span_ms[i] = 0.f; e->span_launches[i] = 0; }
+  return PDSC_OK;
+}
+
+int pdsc_profile_read(pdsc_engine* e, float* ms_out, int32_t* launches_out) {
+  if (!e) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine");
+  DeviceGuard g(e->cfg.device);
+  if (e->profile_pending) {
+    const int L = e->cfg.num_layers;
+    cudaEvent_t* bev = e->ev.data() + 2 * L;
+    PDSC_CUDA(cudaEventSynchronize(bev[8]));
+    float attn = 0.f, t = 0.f;
+    for (int l = 0; l < L; ++l) {
+      if (cudaEventElapsedTime(&t, e->ev[2 * l], e->ev[2 * l + 1]) == cudaSuccess) attn += t;
+    }
+    cudaGetLastError();  // attention events are not recorded when features are injected
+    auto span = [&](int a, int b) { float v = 0.f; cudaEventElapsedTime(&v, bev[a], bev[b]); return v; };
+    const float enc = span(1, 2);
+    e->span_ms[PDSC_SPAN_SC] += span(0, 1);
+    e->span_ms[PDSC_SPAN_ATTENTION] += attn;
+    e->span_ms[PDSC_SPAN_LINEAR] += enc > attn ? enc - attn : 0.f;
+    e->span_ms[PDSC_SPAN_HEAD] += span(2, 3);
+    e->span_ms[PDSC_SPAN_SEEDS] += span(3, 4);
+    e->span_ms[PDSC_SPAN_KNN] += span(4, 5);
+    e->span_ms[PDSC_SPAN_NSM] += span(5, 6);
+    e->span_ms[PDSC_SPAN_HYPOTHESES] += span(6, 7);
+    e->span_ms[PDSC_SPAN_REFINE] += span(7, 8);
+    e->span_ms[PDSC_SPAN_TOTAL] += span(0, 8);
+    e->profile_pending = false;
+  }
+  if (ms_out && launches_out) {
+    for (int i = 0; i < PDSC_SPAN_COUNT; ++i) {
+      ms_out[i] = e->span_ms[i];
+      launches_out[i] = e->span_launches[i];
+      e->span_ms[i] = 0.f;
+      e->span_launches[i] = 0;
+    }
+  }
   return PDSC_OK;
 }
 

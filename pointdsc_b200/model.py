@@ -168,6 +168,19 @@ class PointDSC(nn.Module):
         lib = self._ensure_engine()
         return int(lib.pdsc_launches_per_forward(self._engine, B, N))
 
+    def profile(self, enable: bool):
+        """Turn the engine's CUDA-event stage profiling on/off (pdsc_profile_enable)."""
+        lib = self._ensure_engine()
+        _capi.check(lib.pdsc_profile_enable(self._engine, 1 if enable else 0))
+
+    def profile_read(self):
+        """{span: (milliseconds, launches)} accumulated since the last read (pdsc_profile_read)."""
+        lib = self._ensure_engine()
+        ms = (C.c_float * len(_capi.SPANS))()
+        cnt = (C.c_int32 * len(_capi.SPANS))()
+        _capi.check(lib.pdsc_profile_read(self._engine, ms, cnt))
+        return {n: (float(ms[i]), int(cnt[i])) for i, n in enumerate(_capi.SPANS)}
+
     def num_seeds(self, N: int) -> int:
         return int(N * self.ratio)
 
