@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--n", type=int, default=1000)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--dataset", default="3dmatch", choices=["3dmatch", "kitti"])
-    ap.add_argument("--precision", default=os.environ.get("POINTDSC_PRECISION", "bf16x3"))
+    ap.add_argument("--precision", default=os.environ.get("POINTDSC_PRECISION", "fp16x3"))
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -263,7 +263,7 @@ def run_engine(args, rank, world, local_rank):
         traffic = tj.get(key, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
-    executed = {"bf16x3": 3, "bf16": 1, "fp32": 1}[args.precision]
+    executed = {"bf16x3": 3, "fp16x3": 3, "bf16": 1, "fp32": 1}[args.precision]
     roofline = {"kernel": "tc_attention_kernel" if args.precision != "fp32" else "attention_simt_kernel",
                 "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "peak_source": peak_src,
@@ -286,7 +286,7 @@ def run_engine(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"bf16x3": "bf16 hi/lo split (3 products) with f32 accumulate", "bf16": "bf16 with f32 accumulate",
-                  "fp32": "f32"}[args.precision],
+                  "fp16x3": "fp16 hi/lo split (3 products) with f32 accumulate", "fp32": "f32"}[args.precision],
         "data": "synthetic", "config": config_of(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "stages": stages,

@@ -46,10 +46,12 @@ typedef enum pdsc_status {
 typedef enum pdsc_precision {
   PDSC_FP32_SIMT = 0, /* fp32 FFMA kernels: the exact-arithmetic path                              */
   PDSC_BF16X3 = 1,    /* tcgen05 kind::f16, bf16 hi/lo operand split, 3 products, fp32 accumulate:
-                         fp32-grade results on tensor cores (default; meets the 1e-4 R/t bar)        */
-  PDSC_BF16 = 2       /* tcgen05 kind::f16, single bf16 operands, fp32 accumulate: throughput mode;
+                         16 significant bits per operand                                             */
+  PDSC_BF16 = 2,      /* tcgen05 kind::f16, single bf16 operands, fp32 accumulate: throughput mode;
                          the 12-layer near-argmax attention amplifies bf16 rounding, so R/t may
                          deviate from the reference by > 1e-4 on some sets           */
+  PDSC_FP16X3 = 3     /* tcgen05 kind::f16, fp16 hi/lo operand split, 3 products, fp32 accumulate:
+                         22 significant bits per operand — fp32-grade results on the tensor cores   */
 } pdsc_precision;
 
 /* Mirrors PointDSC.__init__ (reference models/PointDSC.py:81-91) plus the engine's precision. */

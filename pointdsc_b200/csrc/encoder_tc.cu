@@ -24,6 +24,7 @@
 //                   P (bf16 hi/lo) through smem, O += P V in TMEM; lazy rescale; msg (fp32, HBM)
 //   tc_chain<MSG>   msg -> fc_message chain -> + feat1 -> feat (fp32, HBM)
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -47,20 +48,8 @@ constexpr int kB1 = 0, kBq = 128, kBk = 256, kBv = 384, kBm0 = 512, kBm1 = 576, 
 
 constexpr float kQScale = 1.4426950408889634f / 11.313708498984761f;  // log2(e) / sqrt(128)
 
-static uint16_t bf16_bits(float x) {
-  __nv_bfloat16 h = __float2bfloat16_rn(x);
-  uint16_t b;
-  std::memcpy(&b, &h, 2);
-  return b;
-}
-static float bf16_to_float(uint16_t b) {
-  uint32_t u = (uint32_t)b << 16;
-  float f;
-  std::memcpy(&f, &u, 4);
-  return f;
-}
-
-// W [rows][K] fp32 (row-major) * scale  ->  [hi panels][lo panels]
+// W [rows][K] fp32 (row-major) * scale  ->  [hi panels][lo panels] in the 16-bit format FMT
+template <int FMT>
 static void build_image(const float* W, int rows, int K, double scale, uint8_t* dst) {
   const int panels = K / 64;
   const size_t panel_bytes = (size_t)rows * 128;
@@ -69,40 +58,47 @@ static void build_image(const float* W, int rows, int K, double scale, uint8_t* 
   for (int r = 0; r < rows; ++r)
     for (int k = 0; k < K; ++k) {
       const float x = (float)((double)W[(size_t)r * K + k] * scale);
-      const uint16_t h = bf16_bits(x);
-      const uint16_t l = bf16_bits(x - bf16_to_float(h));
+      const uint16_t h = to_16<FMT>(x);
+      const uint16_t l = to_16<FMT>(x - from_16<FMT>(h));
       const size_t off = (size_t)(k / 64) * panel_bytes + sw128_offset((uint32_t)r, (uint32_t)(k % 64));
       std::memcpy(hi + off, &h, 2);
       std::memcpy(lo + off, &l, 2);
     }
 }
 
+template <int FMT>
+static void build_layer(const TcLayerHost& L, uint8_t* base) {
+  build_image<FMT>(L.w1, 128, 128, 1.0, base + kW1);
+  build_image<FMT>(L.wq, 128, 128, (double)kQScale, base + kWq);
+  build_image<FMT>(L.wk, 128, 128, 1.0, base + kWk);
+  build_image<FMT>(L.wv, 128, 128, 1.0, base + kWv);
+  build_image<FMT>(L.wm0, 64, 128, 1.0, base + kWm0);
+  build_image<FMT>(L.wm1, 64, 64, 1.0, base + kWm1);
+  build_image<FMT>(L.wm2, 128, 64, 1.0, base + kWm2);
+}
+
 int tc_build_weights(const TcLayerHost* layers, int num_layers, TcWeights* out) {
   tc_free_weights(out);
-  std::vector<uint8_t> host((size_t)num_layers * kLayerBytes, 0);
-  for (int l = 0; l < num_layers; ++l) {
-    uint8_t* base = host.data() + (size_t)l * kLayerBytes;
-    const TcLayerHost& L = layers[l];
-    build_image(L.w1, 128, 128, 1.0, base + kW1);
-    build_image(L.wq, 128, 128, (double)kQScale, base + kWq);
-    build_image(L.wk, 128, 128, 1.0, base + kWk);
-    build_image(L.wv, 128, 128, 1.0, base + kWv);
-    build_image(L.wm0, 64, 128, 1.0, base + kWm0);
-    build_image(L.wm1, 64, 64, 1.0, base + kWm1);
-    build_image(L.wm2, 128, 64, 1.0, base + kWm2);
-    float* b = reinterpret_cast<float*>(base + kBias);
-    for (int i = 0; i < 128; ++i) {
-      b[kB1 + i] = L.b1[i];
-      b[kBq + i] = (float)((double)L.bq[i] * (double)kQScale);
-      b[kBk + i] = L.bk[i];
-      b[kBv + i] = L.bv[i];
-      b[kBm2 + i] = L.bm2[i];
+  const size_t per_fmt = (size_t)num_layers * kLayerBytes;
+  std::vector<uint8_t> host(2 * per_fmt, 0);  // [fp16 images][bf16 images]
+  for (int fmt = 0; fmt < 2; ++fmt)
+    for (int l = 0; l < num_layers; ++l) {
+      uint8_t* base = host.data() + fmt * per_fmt + (size_t)l * kLayerBytes;
+      const TcLayerHost& L = layers[l];
+      if (fmt == kFmtF16) build_layer<kFmtF16>(L, base); else build_layer<kFmtBF16>(L, base);
+      float* b = reinterpret_cast<float*>(base + kBias);
+      for (int i = 0; i < 128; ++i) {
+        b[kB1 + i] = L.b1[i];
+        b[kBq + i] = (float)((double)L.bq[i] * (double)kQScale);
+        b[kBk + i] = L.bk[i];
+        b[kBv + i] = L.bv[i];
+        b[kBm2 + i] = L.bm2[i];
+      }
+      for (int i = 0; i < 64; ++i) {
+        b[kBm0 + i] = L.bm0[i];
+        b[kBm1 + i] = L.bm1[i];
+      }
     }
-    for (int i = 0; i < 64; ++i) {
-      b[kBm0 + i] = L.bm0[i];
-      b[kBm1 + i] = L.bm1[i];
-    }
-  }
   cudaError_t err = cudaMalloc(&out->arena, host.size());
   if (err != cudaSuccess) return (int)err;
   err = cudaMemcpy(out->arena, host.data(), host.size(), cudaMemcpyHostToDevice);
@@ -152,8 +148,8 @@ constexpr int kChainThreads = 160;
 // issue one GEMM step: D[128 x Nout] (+)= A[128 x K] * W[Nout x K]^T, optionally as three hi/lo products
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_panel_bytes,
                                            uint32_t b_hi, uint32_t b_lo, uint32_t b_panel_bytes, int K, int Nout,
-                                           int split, uint32_t accumulate) {
-  const uint32_t idesc = idesc_bf16_f32(128, Nout);
+                                           int split, uint32_t accumulate, int fmt) {
+  const uint32_t idesc = idesc_f16kind(128, Nout, fmt);
   const int terms = split ? 3 : 1;
   uint32_t acc = accumulate;
   for (int t = 0; t < terms; ++t) {
@@ -171,14 +167,15 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint3
 }
 
 // 8 consecutive fp32 values -> one 16-byte hi chunk and one 16-byte lo chunk
+template <int FMT>
 __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
-  split_pair(x[0], x[1], hi.x, lo.x);
-  split_pair(x[2], x[3], hi.y, lo.y);
-  split_pair(x[4], x[5], hi.z, lo.z);
-  split_pair(x[6], x[7], hi.w, lo.w);
+  split_pair<FMT>(x[0], x[1], hi.x, lo.x);
+  split_pair<FMT>(x[2], x[3], hi.y, lo.y);
+  split_pair<FMT>(x[4], x[5], hi.z, lo.z);
+  split_pair<FMT>(x[6], x[7], hi.w, lo.w);
 }
 
-template <int MODE>
+template <int MODE, int FMT>
 __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -225,19 +222,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           if (MODE == kPCQ) {
             // step 0: W1 (Wbuf + 0), step 1: Wq (Wbuf + 64K); both 128 x 128
             const uint32_t wb = w_base + step * 65536;
-            issue_gemm(tmem + step * 128, a_base, a_base + 32768, 16384, wb, wb + 32768, 16384, 128, 128, a.split, 0);
+            issue_gemm(tmem + step * 128, a_base, a_base + 32768, 16384, wb, wb + 32768, 16384, 128, 128, a.split, 0, FMT);
           } else if (MODE == kKV) {
             const uint32_t wb = w_base + step * 65536;  // Wk, Wv
-            issue_gemm(tmem + step * 128, a_base, a_base + 32768, 16384, wb, wb + 32768, 16384, 128, 128, a.split, 0);
+            issue_gemm(tmem + step * 128, a_base, a_base + 32768, 16384, wb, wb + 32768, 16384, 128, 128, a.split, 0, FMT);
           } else {
             if (step == 0) {         // Wm0: 64 x 128  (hi 16K, lo 16K; panel = 64 rows * 128 B = 8K)
-              issue_gemm(tmem + 0, a_base, a_base + 32768, 16384, w_base, w_base + 16384, 8192, 128, 64, a.split, 0);
+              issue_gemm(tmem + 0, a_base, a_base + 32768, 16384, w_base, w_base + 16384, 8192, 128, 64, a.split, 0, FMT);
             } else if (step == 1) {  // Wm1: 64 x 64   (hi 8K, lo 8K)
               issue_gemm(tmem + 64, a_base, a_base + 32768, 16384, w_base + 32768, w_base + 32768 + 8192, 8192, 64, 64,
-                         a.split, 0);
+                         a.split, 0, FMT);
             } else {                 // Wm2: 128 x 64  (hi 16K, lo 16K)
               issue_gemm(tmem + 128, a_base, a_base + 32768, 16384, w_base + 49152, w_base + 49152 + 16384, 16384, 64,
-                         128, a.split, 0);
+                         128, a.split, 0, FMT);
             }
           }
           mma_commit(bar_d);
@@ -260,8 +257,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (grow < a.rows) v = *reinterpret_cast<const float4*>(a.in + grow * kC + lane * 4);
         uint32_t h0, l0, h1, l1;
-        split_pair(v.x, v.y, h0, l0);
-        split_pair(v.z, v.w, h1, l1);
+        split_pair<FMT>(v.x, v.y, h0, l0);
+        split_pair<FMT>(v.z, v.w, h1, l1);
         const uint32_t off = (uint32_t)(lane >> 4) * 16384u + sw128_offset((uint32_t)lr, (uint32_t)(lane & 15) * 4u);
         *reinterpret_cast<uint2*>(Abuf + off) = make_uint2(h0, h1);
         if (a.split) *reinterpret_cast<uint2*>(Abuf + 32768 + off) = make_uint2(l0, l1);
@@ -315,7 +312,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint4 hi, lo;
-              split8(x + g * 8, hi, lo);
+              split8<FMT>(x + g * 8, hi, lo);
               const uint32_t kk = (uint32_t)(c0 + g * 8);
               const uint32_t off = (kk >> 6) * 16384u + sw128_offset((uint32_t)r, kk & 63u);
               *reinterpret_cast<uint4*>(Abuf + off) = hi;
@@ -327,7 +324,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint4 hi, lo;
-              split8(x + g * 8, hi, lo);
+              split8<FMT>(x + g * 8, hi, lo);
               const uint32_t kk = (uint32_t)(c0 + g * 8);
               const uint32_t off = (kk >> 6) * 16384u + sw128_offset((uint32_t)(n & 127), kk & 63u);
               *reinterpret_cast<uint4*>(base + off) = hi;
@@ -339,7 +336,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint4 hi, lo;
-              split8(x + g * 8, hi, lo);
+              split8<FMT>(x + g * 8, hi, lo);
               const uint32_t kk = (uint32_t)(c0 + g * 8);
               const uint32_t off = (kk >> 6) * 8192u + sw128_offset((uint32_t)(n & 63), kk & 63u);
               *reinterpret_cast<uint4*>(base + off) = hi;
@@ -350,10 +347,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
             uint8_t* base = a.kvimg + ((size_t)bidx * a.KT + (n >> 6)) * 65536 + 32768;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const __nv_bfloat16 h = __float2bfloat16_rn(x[i]);
+              const uint16_t h = to_16<FMT>(x[i]);
               const uint32_t off = sw128_offset((uint32_t)(c0 + i), (uint32_t)(n & 63));
-              *reinterpret_cast<__nv_bfloat16*>(base + off) = h;
-              if (a.split) *reinterpret_cast<__nv_bfloat16*>(base + 16384 + off) = __float2bfloat16_rn(x[i] - __bfloat162float(h));
+              *reinterpret_cast<uint16_t*>(base + off) = h;
+              if (a.split) *reinterpret_cast<uint16_t*>(base + 16384 + off) = to_16<FMT>(x[i] - from_16<FMT>(h));
             }
           }
         }
@@ -387,6 +384,7 @@ constexpr int kAttnQ = 0, kAttnK = 65536, kAttnV = 131072, kAttnP = 196608, kAtt
 constexpr int kAttnSmemTc = kAttnBars + 256 + 1024;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays below 2^8 before the reference max is advanced
 
+template <int FMT>
 __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -453,7 +451,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
       mbar_wait(q_full, 0);
       mbar_wait(k_full[0], 0);
       tc_fence_after();
-      issue_gemm(tS[0], q_hi, q_lo, 16384, s0 + kAttnK, s0 + kAttnK + 16384, 8192, 128, 64, a.split, 0);
+      issue_gemm(tS[0], q_hi, q_lo, 16384, s0 + kAttnK, s0 + kAttnK + 16384, 8192, 128, 64, a.split, 0, FMT);
       mma_commit(s_full[0]);
       mma_commit(k_empty[0]);
       for (int j = 0; j < T; ++j) {
@@ -463,7 +461,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
           if (j + 1 >= 2) mbar_wait(s_empty[s1], (uint32_t)((u1 - 1) & 1));
           tc_fence_after();
           const uint32_t kb = s0 + kAttnK + s1 * 32768;
-          issue_gemm(tS[s1], q_hi, q_lo, 16384, kb, kb + 16384, 8192, 128, 64, a.split, 0);
+          issue_gemm(tS[s1], q_hi, q_lo, 16384, kb, kb + 16384, 8192, 128, 64, a.split, 0, FMT);
           mma_commit(s_full[s1]);
           mma_commit(k_empty[s1]);
         }
@@ -472,7 +470,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
         mbar_wait(v_full[s], (uint32_t)(u & 1));
         tc_fence_after();
         const uint32_t vb = s0 + kAttnV + s * 32768;
-        issue_gemm(tO, p_hi, p_lo, 16384, vb, vb + 16384, 16384, 64, 128, a.split, j > 0 ? 1u : 0u);
+        issue_gemm(tO, p_hi, p_lo, 16384, vb, vb + 16384, 16384, 64, 128, a.split, j > 0 ? 1u : 0u, FMT);
         mma_commit(p_empty);
         mma_commit(v_empty[s]);
       }
@@ -541,7 +539,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         uint4 hi, lo;
-        split8(p + g * 8, hi, lo);
+        split8<FMT>(p + g * 8, hi, lo);
         const uint32_t off = sw128_offset((uint32_t)r, (uint32_t)(g * 8));
         *reinterpret_cast<uint4*>(Pbuf + off) = hi;
         if (a.split) *reinterpret_cast<uint4*>(Pbuf + 16384 + off) = lo;
@@ -592,6 +590,7 @@ __global__ void tc_clear_pads_kernel(uint8_t* kvimg, int N, int KT) {
 }
 
 // ---- debug: decode operand images back to fp32 [B*N][128] -------------------------------------------------
+template <int FMT>
 __global__ void tc_decode_kernel(const uint8_t* qimg, const uint8_t* kvimg, float* q, float* k, float* v, long long rows,
                                  int N, int QT, int KT, int split) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -599,7 +598,7 @@ __global__ void tc_decode_kernel(const uint8_t* qimg, const uint8_t* kvimg, floa
   const uint32_t c = (uint32_t)(idx % kC);
   if (row >= rows) return;
   const int b = (int)(row / N), n = (int)(row % N);
-  auto rd = [](const uint8_t* p) { return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p)); };
+  auto rd = [](const uint8_t* p) { return from_16<FMT>(*reinterpret_cast<const uint16_t*>(p)); };
   const uint8_t* qb = qimg + ((size_t)b * QT + (n >> 7)) * 65536;
   const uint32_t qo = (c >> 6) * 16384u + sw128_offset((uint32_t)(n & 127), c & 63u);
   q[idx] = rd(qb + qo) + (split ? rd(qb + 32768 + qo) : 0.f);
@@ -615,6 +614,16 @@ __global__ void tc_decode_kernel(const uint8_t* qimg, const uint8_t* kvimg, floa
 // =========================================================================================================
 static int g_num_sms = 0;
 
+template <int FMT>
+static cudaError_t tc_configure_fmt() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(tc_chain_kernel<kPCQ, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem))) return e;
+  if ((e = cudaFuncSetAttribute(tc_chain_kernel<kKV, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem))) return e;
+  if ((e = cudaFuncSetAttribute(tc_chain_kernel<kMSG, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem))) return e;
+  if ((e = cudaFuncSetAttribute(tc_attention_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTc))) return e;
+  return cudaSuccess;
+}
+
 static cudaError_t tc_configure() {
   static bool done = false;
   if (done) return cudaSuccess;
@@ -622,17 +631,14 @@ static cudaError_t tc_configure() {
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(tc_chain_kernel<kPCQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem))) return e;
-  if ((e = cudaFuncSetAttribute(tc_chain_kernel<kKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem))) return e;
-  if ((e = cudaFuncSetAttribute(tc_chain_kernel<kMSG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem))) return e;
-  if ((e = cudaFuncSetAttribute(tc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTc))) return e;
+  if ((e = tc_configure_fmt<kFmtF16>()) != cudaSuccess) return e;
+  if ((e = tc_configure_fmt<kFmtBF16>()) != cudaSuccess) return e;
   done = true;
   return cudaSuccess;
 }
 
-int tc_encoder_forward(const TcWeights& w, const TcForwardArgs& a, cudaStream_t st) {
-  cudaError_t e = tc_configure();
-  if (e != cudaSuccess) return (int)e;
+template <int FMT>
+static int tc_encoder_forward_fmt(const TcWeights& w, const TcForwardArgs& a, cudaStream_t st) {
   const long long rows = (long long)a.B * a.N;
   const int QT = q_tiles(a.N), KT = k_tiles(a.N);
   uint8_t* qimg = static_cast<uint8_t*>(a.scratch);
@@ -640,39 +646,46 @@ int tc_encoder_forward(const TcWeights& w, const TcForwardArgs& a, cudaStream_t 
   uint8_t* kvimg = qimg + (size_t)a.B * QT * 65536;
   const long long tiles = (rows + 127) / 128;
   const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+  const uint8_t* arena = static_cast<const uint8_t*>(w.arena) + (size_t)FMT * w.num_layers * kLayerBytes;
 
   launch_layer0(a.corr_pos, a.l0w, a.l0b, a.feat, rows, a.in_dim, st);
   tc_clear_pads_kernel<<<a.B, 256, 0, st>>>(kvimg, a.N, KT);
   for (int l = 0; l < a.num_layers; ++l) {
-    const uint8_t* base = static_cast<const uint8_t*>(w.arena) + (size_t)l * kLayerBytes;
+    const uint8_t* base = arena + (size_t)l * kLayerBytes;
     ChainArgs c{};
     c.rows = rows; c.N = a.N; c.QT = QT; c.KT = KT; c.split = a.split;
     c.qimg = qimg; c.kvimg = kvimg; c.bias = reinterpret_cast<const float*>(base + kBias);
     // PointCN + Q
     c.in = a.feat; c.res = nullptr; c.out_f32 = a.feat1; c.wimg = base + kW1; c.wbytes = 131072;
-    tc_chain_kernel<kPCQ><<<grid, kChainThreads, kChainSmem, st>>>(c);
+    tc_chain_kernel<kPCQ, FMT><<<grid, kChainThreads, kChainSmem, st>>>(c);
     // K + V
     c.in = a.feat1; c.out_f32 = nullptr; c.wimg = base + kWk; c.wbytes = 131072;
-    tc_chain_kernel<kKV><<<grid, kChainThreads, kChainSmem, st>>>(c);
+    tc_chain_kernel<kKV, FMT><<<grid, kChainThreads, kChainSmem, st>>>(c);
     // attention
     AttnArgs at{a.N, a.NS, QT, KT, a.split, qimg, kvimg, a.sc, a.msg};
     if (a.attn_events) cudaEventRecord(a.attn_events[2 * l], st);
-    tc_attention_kernel<<<a.B * QT, kAttnThreads, kAttnSmemTc, st>>>(at);
+    tc_attention_kernel<FMT><<<a.B * QT, kAttnThreads, kAttnSmemTc, st>>>(at);
     if (a.attn_events) cudaEventRecord(a.attn_events[2 * l + 1], st);
     if (a.debug_out && a.debug_layer == l) {
       const size_t plane = (size_t)rows * kC;
       cudaMemcpyAsync(a.debug_out, a.feat1, plane * sizeof(float), cudaMemcpyDeviceToDevice, st);
-      tc_decode_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(qimg, kvimg, a.debug_out + plane, a.debug_out + 2 * plane,
-                                                                        a.debug_out + 3 * plane, rows, a.N, QT, KT, a.split);
+      tc_decode_kernel<FMT><<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(qimg, kvimg, a.debug_out + plane, a.debug_out + 2 * plane,
+                                                                             a.debug_out + 3 * plane, rows, a.N, QT, KT, a.split);
       cudaMemcpyAsync(a.debug_out + 4 * plane, a.msg, plane * sizeof(float), cudaMemcpyDeviceToDevice, st);
     }
     // fc_message + residual
     c.in = a.msg; c.res = a.feat1; c.out_f32 = a.feat; c.wimg = base + kWm0; c.wbytes = 81920;
-    tc_chain_kernel<kMSG><<<grid, kChainThreads, kChainSmem, st>>>(c);
+    tc_chain_kernel<kMSG, FMT><<<grid, kChainThreads, kChainSmem, st>>>(c);
     if (a.layer_tap_out && a.layer_tap == l)
       cudaMemcpyAsync(a.layer_tap_out, a.feat, (size_t)rows * kC * sizeof(float), cudaMemcpyDeviceToDevice, st);
   }
   return (int)cudaGetLastError();
+}
+
+int tc_encoder_forward(const TcWeights& w, const TcForwardArgs& a, cudaStream_t st) {
+  cudaError_t e = tc_configure();
+  if (e != cudaSuccess) return (int)e;
+  return a.fmt == kFmtBF16 ? tc_encoder_forward_fmt<kFmtBF16>(w, a, st) : tc_encoder_forward_fmt<kFmtF16>(w, a, st);
 }
 
 }  // namespace pdsc

@@ -20,7 +20,8 @@ struct TcWeights {
 
 struct TcForwardArgs {
   int B, N, NS, in_dim, num_layers;
-  int split;                 // 1: bf16 hi/lo operand split (3 products)   0: single bf16 operands
+  int split;                 // 1: hi/lo operand split (3 products)   0: single 16-bit operands
+  int fmt;                   // operand format of the kind::f16 MMAs: 0 = fp16, 1 = bf16
   const float* corr_pos;     // [B*N][in_dim]
   const float *l0w, *l0b;    // layer0 weights (fp32, device)
   const float* sc;           // [B][N][NS]

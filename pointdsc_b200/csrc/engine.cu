@@ -255,7 +255,7 @@ int pdsc_create(const pdsc_config* cfg, pdsc_engine** out) {
   if (cfg->num_iterations < 1 || cfg->num_iterations > pdsc::kMaxIters)
     return fail(PDSC_ERR_UNSUPPORTED, "num_iterations must be in [1,%d]", pdsc::kMaxIters);
   if (cfg->k < 1 || cfg->k > pdsc::kMaxK) return fail(PDSC_ERR_UNSUPPORTED, "k must be in [1,%d]", pdsc::kMaxK);
-  if (cfg->precision < PDSC_FP32_SIMT || cfg->precision > PDSC_BF16)
+  if (cfg->precision < PDSC_FP32_SIMT || cfg->precision > PDSC_FP16X3)
     return fail(PDSC_ERR_INVALID_ARGUMENT, "unknown precision %d", cfg->precision);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -294,7 +294,7 @@ int pdsc_set_param(pdsc_engine* e, const char* name, const float* h_data, int64_
 
 int pdsc_set_precision(pdsc_engine* e, int32_t precision) {
   if (!e) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine");
-  if (precision < PDSC_FP32_SIMT || precision > PDSC_BF16) return fail(PDSC_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
+  if (precision < PDSC_FP32_SIMT || precision > PDSC_FP16X3) return fail(PDSC_ERR_INVALID_ARGUMENT, "unknown precision %d", precision);
   e->cfg.precision = precision;
   return PDSC_OK;
 }
@@ -433,7 +433,8 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
     } else {
       TcForwardArgs a{};
       a.B = B; a.N = N; a.NS = NS; a.in_dim = e->cfg.in_dim; a.num_layers = e->cfg.num_layers;
-      a.split = (e->cfg.precision == PDSC_BF16X3) ? 1 : 0;
+      a.split = (e->cfg.precision == PDSC_BF16X3 || e->cfg.precision == PDSC_FP16X3) ? 1 : 0;
+      a.fmt = (e->cfg.precision == PDSC_FP16X3) ? 0 : 1;
       a.corr_pos = d_corr_pos; a.l0w = W + e->off_l0w; a.l0b = W + e->off_l0b;
       a.sc = w.sc; a.feat = w.feat_a; a.feat1 = w.feat_b; a.msg = w.msg; a.scratch = w.tc_scratch;
       a.layer_tap = (io && io->out_layer_features) ? io->layer_tap : -1;

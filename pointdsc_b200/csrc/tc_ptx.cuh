@@ -4,6 +4,7 @@
 // descriptor); the canonical SWIZZLE_128B K-major operand layout is described in encoder_tc.cu.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -78,9 +79,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M x N tile.
-__host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::f16 instruction descriptor: D = f32, A and B both `fmt` (0 = fp16, 1 = bf16), both K-major, M x N tile.
+__host__ __device__ constexpr uint32_t idesc_f16kind(int M, int N, int fmt) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---- MMA issue / commit (one thread) ---------------------------------------------------------------------
@@ -128,20 +129,46 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// ---- bf16 hi/lo split ----------------------------------------------------------------------------------------
-// x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi): 16 significant bits, so three bf16 products
-// (hi*hi + hi*lo + lo*hi) reproduce the fp32 product to ~2^-16 relative.
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);  // .x = a (low half), .y = b (high half)
-  return *reinterpret_cast<uint32_t*>(&v);
-}
+// ---- 16-bit hi/lo operand split ---------------------------------------------------------------------------
+// x ~= hi + lo with hi = round16(x), lo = round16(x - hi); three products hi*hi + hi*lo + lo*hi.
+//   FMT 1 (bf16, 8-bit significand): 16 significant bits, per-product error ~2^-18
+//   FMT 0 (fp16, 11-bit significand): 22 significant bits, per-product error ~2^-23 — fp32-grade, provided
+//          |x| < 65504 (true for this network's activations) ; tiny |x| lose relative, not absolute, accuracy.
+constexpr int kFmtF16 = 0, kFmtBF16 = 1;
+
+template <int FMT>
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-  const float ra = a - __bfloat162float(ha), rb = b - __bfloat162float(hb);
-  __nv_bfloat162 h;
-  h.x = ha; h.y = hb;
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  lo = pack_bf16x2(ra, rb);
+  if (FMT == kFmtBF16) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);  // .x = a (low half)
+    const float2 f = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  } else {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
+}
+template <int FMT>
+__host__ __device__ __forceinline__ uint16_t to_16(float x) {
+  if (FMT == kFmtBF16) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    return *reinterpret_cast<const uint16_t*>(&h);
+  } else {
+    const __half h = __float2half_rn(x);
+    return *reinterpret_cast<const uint16_t*>(&h);
+  }
+}
+template <int FMT>
+__host__ __device__ __forceinline__ float from_16(uint16_t b) {
+  if (FMT == kFmtBF16) {
+    return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&b));
+  } else {
+    return __half2float(*reinterpret_cast<const __half*>(&b));
+  }
 }
 
 // byte offset of element (row, kk) inside one SWIZZLE_128B K-major panel (64 bf16 = 128 B per row)

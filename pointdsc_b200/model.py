@@ -25,7 +25,7 @@ import torch.nn as nn
 
 from . import _capi
 
-DEFAULT_PRECISION = os.environ.get("POINTDSC_PRECISION", "bf16x3")
+DEFAULT_PRECISION = os.environ.get("POINTDSC_PRECISION", "fp16x3")
 
 _TAP_SPECS = {
     # name: (dtype, shape as a function of (B, N, S, k, C))
