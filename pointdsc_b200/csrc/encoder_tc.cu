@@ -34,19 +34,12 @@
 #include "common.cuh"
 #include "encoder_tc.h"
 #include "kernels.h"
+#include "tc_attention.cuh"
+#include "tc_chain.cuh"
+#include "tc_common.cuh"
 #include "tc_ptx.cuh"
 
 namespace pdsc {
-
-using namespace ptx;
-
-// ---- weight arena layout (bytes, per layer) ------------------------------------------------------------
-constexpr size_t kW1 = 0, kWq = 65536, kWk = 131072, kWv = 196608, kWm0 = 262144, kWm1 = 294912, kWm2 = 311296,
-                 kBias = 344064, kLayerBytes = 348160;
-// bias block (floats): b1[128] bq[128] bk[128] bv[128] bm0[64] bm1[64] bm2[128]
-constexpr int kB1 = 0, kBq = 128, kBk = 256, kBv = 384, kBm0 = 512, kBm1 = 576, kBm2 = 640, kBiasFloats = 768;
-
-constexpr float kQScale = 1.4426950408889634f / 11.313708498984761f;  // log2(e) / sqrt(128)
 
 // W [rows][K] fp32 (row-major) * scale  ->  [hi panels][lo panels] in the 16-bit format FMT
 template <int FMT>
@@ -122,453 +115,6 @@ size_t tc_scratch_bytes(int B, int N) {
 }
 
 int tc_launches(int num_layers) { return 2 + 4 * num_layers; }  // layer0 + pad clear + 4 per layer
-
-// =========================================================================================================
-// tc_chain: fused row-tile GEMM chains with resident weights
-// =========================================================================================================
-enum ChainMode { kPCQ = 0, kKV = 1, kMSG = 2 };
-
-struct ChainArgs {
-  long long rows;        // B * N
-  int N, QT, KT, split;
-  const float* in;       // [rows][128] fp32 A operand
-  const float* res;      // MSG: feat1 (residual)
-  float* out_f32;        // PCQ: feat1, MSG: feat
-  uint8_t* qimg;
-  uint8_t* kvimg;
-  const uint8_t* wimg;   // this kernel's weight images (contiguous)
-  const float* bias;     // the layer's bias block
-  int wbytes;            // bytes of weight images to stage
-};
-
-constexpr int kChainAbuf = 65536;
-constexpr int kChainSmem = kChainAbuf + 131072 + kBiasFloats * 4 + 64 + 1024;  // + alignment slack
-constexpr int kChainThreads = 160;
-
-// issue one GEMM step: D[128 x Nout] (+)= A[128 x K] * W[Nout x K]^T, optionally as three hi/lo products
-__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_panel_bytes,
-                                           uint32_t b_hi, uint32_t b_lo, uint32_t b_panel_bytes, int K, int Nout,
-                                           int split, uint32_t accumulate, int fmt) {
-  const uint32_t idesc = idesc_f16kind(128, Nout, fmt);
-  const int terms = split ? 3 : 1;
-  uint32_t acc = accumulate;
-  for (int t = 0; t < terms; ++t) {
-    const uint32_t a = (t == 2) ? a_lo : a_hi;
-    const uint32_t b = (t == 1) ? b_lo : b_hi;
-    for (int p = 0; p < K / 64; ++p) {
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        mma_bf16(d_tmem, smem_desc_sw128(a + p * a_panel_bytes + ks * 32), smem_desc_sw128(b + p * b_panel_bytes + ks * 32),
-                 idesc, acc);
-        acc = 1;
-      }
-    }
-  }
-}
-
-// 8 consecutive fp32 values -> one 16-byte hi chunk and one 16-byte lo chunk
-template <int FMT>
-__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
-  split_pair<FMT>(x[0], x[1], hi.x, lo.x);
-  split_pair<FMT>(x[2], x[3], hi.y, lo.y);
-  split_pair<FMT>(x[4], x[5], hi.z, lo.z);
-  split_pair<FMT>(x[6], x[7], hi.w, lo.w);
-}
-
-template <int MODE, int FMT>
-__global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Abuf = smem;                       // [hi p0 16K][hi p1 16K][lo p0 16K][lo p1 16K]
-  uint8_t* Wbuf = smem + kChainAbuf;          // weight images, contiguous as in the arena
-  float* bias = reinterpret_cast<float*>(Wbuf + 131072);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias + kBiasFloats);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  const uint32_t bar_w = smem_u32(bars + 0), bar_a = smem_u32(bars + 1), bar_d = smem_u32(bars + 2);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t a_base = smem_u32(Abuf), w_base = smem_u32(Wbuf);
-
-  if (tid == 0) {
-    mbar_init(bar_w, 1);
-    mbar_init(bar_a, 128);
-    mbar_init(bar_d, 1);
-    fence_barrier_init();
-  }
-  if (warp == 4) tmem_alloc(smem_u32(tmem_slot), 256);
-  for (int i = tid; i < kBiasFloats; i += kChainThreads) bias[i] = a.bias[i];
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  if (tid == 0) {  // stage the resident weights with one bulk copy per 32 KB
-    mbar_expect_tx(bar_w, (uint32_t)a.wbytes);
-    for (int off = 0; off < a.wbytes; off += 32768)
-      bulk_g2s(w_base + off, a.wimg + off, (uint32_t)min(32768, a.wbytes - off), bar_w);
-  }
-
-  const long long num_tiles = (a.rows + 127) / 128;
-  constexpr int kSteps = (MODE == kMSG) ? 3 : 2;
-
-  if (warp == 4) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      mbar_wait(bar_w, 0);
-      uint32_t pa = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int step = 0; step < kSteps; ++step) {
-          mbar_wait(bar_a, pa);
-          pa ^= 1;
-          tc_fence_after();
-          if (MODE == kPCQ) {
-            // step 0: W1 (Wbuf + 0), step 1: Wq (Wbuf + 64K); both 128 x 128
-            const uint32_t wb = w_base + step * 65536;
-            issue_gemm(tmem + step * 128, a_base, a_base + 32768, 16384, wb, wb + 32768, 16384, 128, 128, a.split, 0, FMT);
-          } else if (MODE == kKV) {
-            const uint32_t wb = w_base + step * 65536;  // Wk, Wv
-            issue_gemm(tmem + step * 128, a_base, a_base + 32768, 16384, wb, wb + 32768, 16384, 128, 128, a.split, 0, FMT);
-          } else {
-            if (step == 0) {         // Wm0: 64 x 128  (hi 16K, lo 16K; panel = 64 rows * 128 B = 8K)
-              issue_gemm(tmem + 0, a_base, a_base + 32768, 16384, w_base, w_base + 16384, 8192, 128, 64, a.split, 0, FMT);
-            } else if (step == 1) {  // Wm1: 64 x 64   (hi 8K, lo 8K)
-              issue_gemm(tmem + 64, a_base, a_base + 32768, 16384, w_base + 32768, w_base + 32768 + 8192, 8192, 64, 64,
-                         a.split, 0, FMT);
-            } else {                 // Wm2: 128 x 64  (hi 16K, lo 16K)
-              issue_gemm(tmem + 128, a_base, a_base + 32768, 16384, w_base + 49152, w_base + 49152 + 16384, 16384, 64,
-                         128, a.split, 0, FMT);
-            }
-          }
-          mma_commit(bar_d);
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===== row threads: tile loader + epilogues; thread <-> row of the 128-row tile, TMEM lane = row =====
-    const int r = tid;  // 0..127
-    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
-    uint32_t pd = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const long long row0 = tile * 128;
-      // ---- coalesced fp32 tile load -> hi/lo split -> swizzled A image ----
-#pragma unroll 4
-      for (int rr = 0; rr < 32; ++rr) {
-        const int lr = warp * 32 + rr;
-        const long long grow = row0 + lr;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (grow < a.rows) v = *reinterpret_cast<const float4*>(a.in + grow * kC + lane * 4);
-        uint32_t h0, l0, h1, l1;
-        split_pair<FMT>(v.x, v.y, h0, l0);
-        split_pair<FMT>(v.z, v.w, h1, l1);
-        const uint32_t off = (uint32_t)(lane >> 4) * 16384u + sw128_offset((uint32_t)lr, (uint32_t)(lane & 15) * 4u);
-        *reinterpret_cast<uint2*>(Abuf + off) = make_uint2(h0, h1);
-        if (a.split) *reinterpret_cast<uint2*>(Abuf + 32768 + off) = make_uint2(l0, l1);
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(bar_a);
-
-      const long long grow = row0 + r;
-      const bool live = grow < a.rows;
-      const int bidx = live ? (int)(grow / a.N) : 0;
-      const int n = live ? (int)(grow % a.N) : 0;
-
-      for (int step = 0; step < kSteps; ++step) {
-        mbar_wait(bar_d, pd);
-        pd ^= 1;
-        tc_fence_after();
-        const int ncols = (MODE == kMSG && step < 2) ? 64 : 128;
-        const uint32_t dcol = (MODE == kMSG) ? (step == 0 ? 0u : (step == 1 ? 64u : 128u)) : (uint32_t)step * 128u;
-        const float* bvec = bias + ((MODE == kPCQ) ? (step == 0 ? kB1 : kBq)
-                                    : (MODE == kKV) ? (step == 0 ? kBk : kBv)
-                                                    : (step == 0 ? kBm0 : (step == 1 ? kBm1 : kBm2)));
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-          uint32_t raw[32];
-          tmem_ld32(tmem + lane_base + dcol + c0, raw);
-          tmem_ld_wait();
-          float x[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(raw[i]) + bvec[c0 + i];
-          const bool relu = (MODE == kPCQ && step == 0) || (MODE == kMSG && step < 2);
-          if (relu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
-          }
-          if (MODE == kMSG && step == 2) {  // residual: feat = feat1 + fc_message(msg)
-            if (live) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 rv = *reinterpret_cast<const float4*>(a.res + grow * kC + c0 + i);
-                x[i] += rv.x; x[i + 1] += rv.y; x[i + 2] += rv.z; x[i + 3] += rv.w;
-              }
-            }
-          }
-          const bool to_f32 = (MODE == kPCQ && step == 0) || (MODE == kMSG && step == 2);
-          if (to_f32 && live) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(a.out_f32 + grow * kC + c0 + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
-          }
-          const bool to_abuf = (MODE == kPCQ && step == 0) || (MODE == kMSG && step < 2);
-          if (to_abuf) {  // next step's A operand
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 hi, lo;
-              split8<FMT>(x + g * 8, hi, lo);
-              const uint32_t kk = (uint32_t)(c0 + g * 8);
-              const uint32_t off = (kk >> 6) * 16384u + sw128_offset((uint32_t)r, kk & 63u);
-              *reinterpret_cast<uint4*>(Abuf + off) = hi;
-              if (a.split) *reinterpret_cast<uint4*>(Abuf + 32768 + off) = lo;
-            }
-          }
-          if (MODE == kPCQ && step == 1 && live) {  // Q image
-            uint8_t* base = a.qimg + ((size_t)bidx * a.QT + (n >> 7)) * 65536;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 hi, lo;
-              split8<FMT>(x + g * 8, hi, lo);
-              const uint32_t kk = (uint32_t)(c0 + g * 8);
-              const uint32_t off = (kk >> 6) * 16384u + sw128_offset((uint32_t)(n & 127), kk & 63u);
-              *reinterpret_cast<uint4*>(base + off) = hi;
-              if (a.split) *reinterpret_cast<uint4*>(base + 32768 + off) = lo;
-            }
-          }
-          if (MODE == kKV && step == 0 && live) {  // K image: 64-key tiles, panel = 64 rows * 128 B
-            uint8_t* base = a.kvimg + ((size_t)bidx * a.KT + (n >> 6)) * 65536;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 hi, lo;
-              split8<FMT>(x + g * 8, hi, lo);
-              const uint32_t kk = (uint32_t)(c0 + g * 8);
-              const uint32_t off = (kk >> 6) * 8192u + sw128_offset((uint32_t)(n & 63), kk & 63u);
-              *reinterpret_cast<uint4*>(base + off) = hi;
-              if (a.split) *reinterpret_cast<uint4*>(base + 16384 + off) = lo;
-            }
-          }
-          if (MODE == kKV && step == 1 && live) {  // V^T image: row = channel, column = key within the tile
-            uint8_t* base = a.kvimg + ((size_t)bidx * a.KT + (n >> 6)) * 65536 + 32768;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const uint16_t h = to_16<FMT>(x[i]);
-              const uint32_t off = sw128_offset((uint32_t)(c0 + i), (uint32_t)(n & 63));
-              *reinterpret_cast<uint16_t*>(base + off) = h;
-              if (a.split) *reinterpret_cast<uint16_t*>(base + 16384 + off) = to_16<FMT>(x[i] - from_16<FMT>(h));
-            }
-          }
-        }
-        if (step + 1 < kSteps) {
-          fence_proxy_async_smem();  // A image written through the generic proxy, read by the tensor core
-          tc_fence_before();
-          mbar_arrive(bar_a);
-        }
-      }
-      tc_fence_before();  // this tile's TMEM reads are ordered before the next tile's first arrive
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 256);
-}
-
-// =========================================================================================================
-// tc_attention
-// =========================================================================================================
-struct AttnArgs {
-  int N, NS, QT, KT, split;
-  const uint8_t* qimg;
-  const uint8_t* kvimg;
-  const float* sc;
-  float* msg;
-};
-
-constexpr int kAttnThreads = 192;
-constexpr int kAttnQ = 0, kAttnK = 65536, kAttnV = 131072, kAttnP = 196608, kAttnBars = 229376;
-constexpr int kAttnSmemTc = kAttnBars + 256 + 1024;
-constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays below 2^8 before the reference max is advanced
-
-template <int FMT>
-__global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAttnBars);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  const uint32_t s0 = smem_u32(smem);
-  const uint32_t q_full = smem_u32(bars + 0);
-  const uint32_t k_full[2] = {smem_u32(bars + 1), smem_u32(bars + 2)};
-  const uint32_t k_empty[2] = {smem_u32(bars + 3), smem_u32(bars + 4)};
-  const uint32_t v_full[2] = {smem_u32(bars + 5), smem_u32(bars + 6)};
-  const uint32_t v_empty[2] = {smem_u32(bars + 7), smem_u32(bars + 8)};
-  const uint32_t s_full[2] = {smem_u32(bars + 9), smem_u32(bars + 10)};
-  const uint32_t s_empty[2] = {smem_u32(bars + 11), smem_u32(bars + 12)};
-  const uint32_t p_full = smem_u32(bars + 13), p_empty = smem_u32(bars + 14);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x / a.QT, qt = blockIdx.x % a.QT;
-  const int T = a.KT;
-
-  if (tid == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(k_full[i], 1); mbar_init(k_empty[i], 1);
-      mbar_init(v_full[i], 1); mbar_init(v_empty[i], 1);
-      mbar_init(s_full[i], 1); mbar_init(s_empty[i], 128);
-    }
-    mbar_init(p_full, 128);
-    mbar_init(p_empty, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tS[2] = {tmem + 0, tmem + 64};
-  const uint32_t tO = tmem + 128;
-
-  if (warp == 0) {
-    // ===== loader: bulk async copies of ready-made operand images =====
-    if (lane == 0) {
-      const uint8_t* qsrc = a.qimg + ((size_t)b * a.QT + qt) * 65536;
-      const uint32_t qbytes = a.split ? 65536u : 32768u;
-      mbar_expect_tx(q_full, qbytes);
-      bulk_g2s(s0 + kAttnQ, qsrc, 32768u, q_full);
-      if (a.split) bulk_g2s(s0 + kAttnQ + 32768, qsrc + 32768, 32768u, q_full);
-      const uint32_t half = a.split ? 32768u : 16384u;
-      for (int j = 0; j < T; ++j) {
-        const int s = j & 1, u = j >> 1;
-        const uint8_t* src = a.kvimg + ((size_t)b * a.KT + j) * 65536;
-        if (j >= 2) mbar_wait(k_empty[s], (uint32_t)((u - 1) & 1));
-        mbar_expect_tx(k_full[s], half);
-        bulk_g2s(s0 + kAttnK + s * 32768, src, half, k_full[s]);
-        if (j >= 2) mbar_wait(v_empty[s], (uint32_t)((u - 1) & 1));
-        mbar_expect_tx(v_full[s], half);
-        bulk_g2s(s0 + kAttnV + s * 32768, src + 32768, half, v_full[s]);
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t q_hi = s0 + kAttnQ, q_lo = s0 + kAttnQ + 32768;
-      const uint32_t p_hi = s0 + kAttnP, p_lo = s0 + kAttnP + 16384;
-      mbar_wait(q_full, 0);
-      mbar_wait(k_full[0], 0);
-      tc_fence_after();
-      issue_gemm(tS[0], q_hi, q_lo, 16384, s0 + kAttnK, s0 + kAttnK + 16384, 8192, 128, 64, a.split, 0, FMT);
-      mma_commit(s_full[0]);
-      mma_commit(k_empty[0]);
-      for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) {
-          const int s1 = (j + 1) & 1, u1 = (j + 1) >> 1;
-          mbar_wait(k_full[s1], (uint32_t)(u1 & 1));
-          if (j + 1 >= 2) mbar_wait(s_empty[s1], (uint32_t)((u1 - 1) & 1));
-          tc_fence_after();
-          const uint32_t kb = s0 + kAttnK + s1 * 32768;
-          issue_gemm(tS[s1], q_hi, q_lo, 16384, kb, kb + 16384, 8192, 128, 64, a.split, 0, FMT);
-          mma_commit(s_full[s1]);
-          mma_commit(k_empty[s1]);
-        }
-        const int s = j & 1, u = j >> 1;
-        mbar_wait(p_full, (uint32_t)(j & 1));
-        mbar_wait(v_full[s], (uint32_t)(u & 1));
-        tc_fence_after();
-        const uint32_t vb = s0 + kAttnV + s * 32768;
-        issue_gemm(tO, p_hi, p_lo, 16384, vb, vb + 16384, 16384, 64, 128, a.split, j > 0 ? 1u : 0u, FMT);
-        mma_commit(p_empty);
-        mma_commit(v_empty[s]);
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===== softmax: one thread owns one query row (TMEM lane) =====
-    const int q4 = warp & 3;
-    const int r = q4 * 32 + lane;
-    const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
-    const int qi = qt * 128 + r;
-    const int qic = min(qi, a.N - 1);
-    const float* scb = a.sc + (size_t)b * a.N * a.NS + qic;  // SC is symmetric: read column qi, coalesced over r
-    uint8_t* Pbuf = smem + kAttnP;
-    float m_ref = -INFINITY, l_sum = 0.f;
-    for (int j = 0; j < T; ++j) {
-      const int s = j & 1, u = j >> 1;
-      const int j0 = j * 64;
-      float scv[64];
-#pragma unroll
-      for (int c = 0; c < 64; ++c) scv[c] = (j0 + c < a.N) ? __ldg(scb + (size_t)(j0 + c) * a.NS) : 0.f;
-      mbar_wait(s_full[s], (uint32_t)(u & 1));
-      tc_fence_after();
-      uint32_t raw0[32], raw1[32];
-      tmem_ld32(tS[s] + lane_base, raw0);
-      tmem_ld32(tS[s] + lane_base + 32, raw1);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(s_empty[s]);
-      float p[64];
-      float tmax = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        const float sv = __uint_as_float(c < 32 ? raw0[c & 31] : raw1[c & 31]);
-        p[c] = (j0 + c < a.N) ? sv * scv[c] : -INFINITY;
-        tmax = fmaxf(tmax, p[c]);
-      }
-      const bool advance = (j == 0) || (tmax > m_ref + kRescaleThreshold);
-      const float new_ref = advance ? tmax : m_ref;
-      float rsum = 0.f;
-#pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        p[c] = exp2f(p[c] - new_ref);
-        rsum += p[c];
-      }
-      const bool rescale_any = __any_sync(0xffffffffu, advance && j > 0);
-      if (j > 0) {
-        mbar_wait(p_empty, (uint32_t)((j - 1) & 1));  // PV_{j-1} done: P smem free, O quiescent
-        tc_fence_after();
-      }
-      if (rescale_any) {
-        const float scale = (advance && j > 0) ? exp2f(m_ref - new_ref) : 1.0f;
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t o[32];
-          tmem_ld32(tO + lane_base + c0, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * scale);
-          tmem_st32(tO + lane_base + c0, o);
-        }
-        tmem_st_wait();
-        l_sum *= scale;
-      }
-      m_ref = new_ref;
-      l_sum += rsum;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint4 hi, lo;
-        split8<FMT>(p + g * 8, hi, lo);
-        const uint32_t off = sw128_offset((uint32_t)r, (uint32_t)(g * 8));
-        *reinterpret_cast<uint4*>(Pbuf + off) = hi;
-        if (a.split) *reinterpret_cast<uint4*>(Pbuf + 16384 + off) = lo;
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(p_full);
-    }
-    mbar_wait(p_empty, (uint32_t)((T - 1) & 1));
-    tc_fence_after();
-    const float inv_l = 1.0f / l_sum;
-    float* dst = a.msg + ((size_t)b * a.N + qi) * kC;
-    for (int c0 = 0; c0 < 128; c0 += 32) {
-      uint32_t o[32];
-      tmem_ld32(tO + lane_base + c0, o);
-      tmem_ld_wait();
-      if (qi < a.N) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(dst + c0 + i) =
-              make_float4(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l,
-                          __uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
-}
 
 // ---- zero the never-written pad rows/columns of the last key tile of every set ---------------------------
 __global__ void tc_clear_pads_kernel(uint8_t* kvimg, int N, int KT) {
