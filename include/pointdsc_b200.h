@@ -100,6 +100,8 @@ typedef struct pdsc_stage_io {
   float* out_layer_features;    /* [B,N,C]  output of encoder layer `layer_tap`                      */
   float* out_layer_debug;       /* [5,B,N,C] internals of layer `layer_tap`: PointCN output, q, k, v, msg.
                                    In the tensor-core modes q carries the folded log2(e)/sqrt(C) scale. */
+  int64_t* out_timeline;        /* [2,16,4,8] clock64() stamps of CTA 0 of the layer-`layer_tap` PointCN+Q chain
+                                   kernel and attention kernel (tensor-core modes; developer tool)            */
 } pdsc_stage_io;
 
 /* ---- lifetime --------------------------------------------------------------------------------- */

@@ -39,7 +39,7 @@ class StageIO(C.Structure):
         ("out_compat", C.c_void_p), ("out_eig", C.c_void_p), ("out_power_iters", C.c_void_p),
         ("out_seed_trans", C.c_void_p), ("out_inlier_counts", C.c_void_p), ("out_best", C.c_void_p),
         ("out_init_trans", C.c_void_p), ("out_refine_solves", C.c_void_p),
-        ("layer_tap", C.c_int32), ("out_layer_features", C.c_void_p), ("out_layer_debug", C.c_void_p),
+        ("layer_tap", C.c_int32), ("out_layer_features", C.c_void_p), ("out_layer_debug", C.c_void_p), ("out_timeline", C.c_void_p),
     ]
 
 

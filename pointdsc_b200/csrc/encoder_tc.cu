@@ -186,6 +186,7 @@ static cudaError_t tc_configure() {
 template <int FMT>
 static int tc_encoder_forward_fmt(const TcWeights& w, const TcForwardArgs& a, cudaStream_t st) {
   const long long rows = (long long)a.B * a.N;
+  if (rows >= (1LL << 31)) return (int)cudaErrorInvalidValue;  // kernels index rows with 32-bit arithmetic
   const int QT = q_tiles(a.N), KT = k_tiles(a.N);
   uint8_t* qimg = static_cast<uint8_t*>(a.scratch);
   qimg = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(qimg) + 1023) & ~uintptr_t(1023));
@@ -203,12 +204,14 @@ static int tc_encoder_forward_fmt(const TcWeights& w, const TcForwardArgs& a, cu
     c.qimg = qimg; c.kvimg = kvimg; c.bias = reinterpret_cast<const float*>(base + kBias);
     // PointCN + Q
     c.in = a.feat; c.res = nullptr; c.out_f32 = a.feat1; c.wimg = base + kW1; c.wbytes = 131072;
+    c.dbg = (a.timeline && a.debug_layer == l) ? a.timeline : nullptr;
     tc_chain_kernel<kPCQ, FMT><<<grid, kChainThreads, kChainSmem, st>>>(c);
     // K + V
-    c.in = a.feat1; c.out_f32 = nullptr; c.wimg = base + kWk; c.wbytes = 131072;
+    c.in = a.feat1; c.out_f32 = nullptr; c.wimg = base + kWk; c.wbytes = 131072; c.dbg = nullptr;
     tc_chain_kernel<kKV, FMT><<<grid, kChainThreads, kChainSmem, st>>>(c);
     // attention
-    AttnArgs at{a.N, a.NS, QT, KT, a.split, qimg, kvimg, a.sc, a.msg};
+    AttnArgs at{a.N, a.NS, QT, KT, a.split, qimg, kvimg, a.sc, a.msg,
+                (a.timeline && a.debug_layer == l) ? a.timeline + 512 : nullptr};
     if (a.attn_events) cudaEventRecord(a.attn_events[2 * l], st);
     tc_attention_kernel<FMT><<<a.B * QT, kAttnThreads, kAttnSmemTc, st>>>(at);
     if (a.attn_events) cudaEventRecord(a.attn_events[2 * l + 1], st);

@@ -33,6 +33,7 @@ struct TcForwardArgs {
   float* layer_tap_out;
   int debug_layer;           // layer whose internals are decoded into debug_out
   float* debug_out;          // [5][B*N][128]: feat1, q (scaled by log2e/sqrt(C)), k, v, msg — or nullptr
+  long long* timeline;       // nullptr or [2][16][4][8] clock64 stamps: chain<PCQ> and attention of layer `debug_layer`
   cudaEvent_t* attn_events;  // nullptr or 2 events per layer, recorded around the attention launch
 };
 

@@ -442,6 +442,7 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
       a.debug_layer = io ? io->layer_tap : -1;
       a.debug_out = io ? io->out_layer_debug : nullptr;
       a.attn_events = attn_ev;
+      a.timeline = io ? reinterpret_cast<long long*>(io->out_timeline) : nullptr;
       const int rc = tc_encoder_forward(e->tc, a, st);
       if (rc) return fail(PDSC_ERR_CUDA, "tensor-core encoder launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     }

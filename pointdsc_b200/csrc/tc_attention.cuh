@@ -24,6 +24,7 @@ struct AttnArgs {
   const uint8_t* kvimg;
   const float* sc;
   float* msg;
+  long long* dbg;
 };
 
 constexpr int kAttnThreads = 320;
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
       mbar_wait(q_full, 0);
       mbar_wait(k_full, 0);
       tc_fence_after();
-      issue_gemm(tmem, q_hi, q_lo, 16384, s0 + kAttnK, s0 + kAttnK + 16384, 8192, 128, 64, a.split, 0, FMT);
+      issue_gemm<2, 64>(tmem, q_hi, q_lo, 16384, s0 + kAttnK, s0 + kAttnK + 16384, 8192, a.split, 0, FMT);
       mma_commit(s_full);
       mma_commit(k_empty);
       for (int j = 0; j < T; ++j) {
@@ -115,18 +116,22 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
           if (j + 1 >= 2) mbar_wait(s_empty + 8 * s1, (uint32_t)((u1 - 1) & 1));
           tc_fence_after();
           const uint32_t kb = s0 + kAttnK + s1 * 32768;
-          issue_gemm(tmem + 64 * s1, q_hi, q_lo, 16384, kb, kb + 16384, 8192, 128, 64, a.split, 0, FMT);
+          issue_gemm<2, 64>(tmem + 64 * s1, q_hi, q_lo, 16384, kb, kb + 16384, 8192, a.split, 0, FMT);
           mma_commit(s_full + 8 * s1);
           mma_commit(k_empty + 8 * s1);
         }
         const int s = j & 1, u = j >> 1;
+        PDSC_STAMP(a.dbg, j, 0, 0);
         mbar_wait(p_full, (uint32_t)(j & 1));
+        PDSC_STAMP(a.dbg, j, 0, 1);
         mbar_wait(v_full + 8 * s, (uint32_t)(u & 1));
+        PDSC_STAMP(a.dbg, j, 0, 2);
         tc_fence_after();
         const uint32_t vb = s0 + kAttnV + s * 32768;
-        issue_gemm(tO, p_hi, p_lo, 16384, vb, vb + 16384, 16384, 64, 128, a.split, j > 0 ? 1u : 0u, FMT);
+        issue_gemm<1, 128>(tO, p_hi, p_lo, 16384, vb, vb + 16384, 16384, a.split, j > 0 ? 1u : 0u, FMT);
         mma_commit(p_empty);
         mma_commit(v_empty + 8 * s);
+        PDSC_STAMP(a.dbg, j, 0, 3);
       }
     }
     __syncwarp();
@@ -162,7 +167,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
           sc_nxt[c] = (key < a.N) ? __ldg(scb + (size_t)key * a.NS) : 0.f;
         }
       }
+      if (j + 3 < T && lane < 4 && qt * 128 + q4 * 32 < a.NS) {
+        // pull the tile after next towards L2: one 128-byte line per key row covers this warp's 32 query columns
+        const float* line0 = a.sc + (size_t)b * a.N * a.NS + qt * 128 + q4 * 32;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const int key = j0 + 192 + c + lane;
+          if (key < a.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(line0 + (size_t)key * a.NS));
+        }
+      }
+      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 0);
       mbar_wait(s_full + 8 * s, (uint32_t)(u & 1));
+      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 1);
       tc_fence_after();
       uint32_t raw[32];
       tmem_ld32(tmem + 64 * s + lane_base + 32 * h, raw);
@@ -186,8 +202,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
         }
       }
       // row maximum over both halves
+      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 2);
       mx[((j & 1) * 2 + h) * 128 + r] = hmax;
       softmax_group_sync();
+      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 3);
       const float tmax = fmaxf(hmax, mx[((j & 1) * 2 + (1 - h)) * 128 + r]);
       const bool advance = (j == 0) || (tmax > m_ref + kRescaleThreshold);
       const float new_ref = advance ? tmax : m_ref;
@@ -198,10 +216,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
         rsum += p[c];
       }
       const bool rescale_any = __any_sync(0xffffffffu, advance && j > 0);
+      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 4);
       if (j > 0) {
         mbar_wait(p_empty, (uint32_t)((j - 1) & 1));  // PV_{j-1} done: P smem free, O quiescent
         tc_fence_after();
       }
+      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 5);
       if (rescale_any) {  // this thread rescales its 64-column half of row r of O
         const float scale = (advance && j > 0) ? ex2_approx(m_ref - new_ref) : 1.0f;
 #pragma unroll
@@ -226,9 +246,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
         *reinterpret_cast<uint4*>(Pbuf + off) = hi;
         if (a.split) *reinterpret_cast<uint4*>(Pbuf + 16384 + off) = lo;
       }
+      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 6);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
+      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 7);
     }
     // ---- epilogue: O / l  ->  msg, staged through the (now free) Q region for full-row stores ----
     const int lb = (T & 1) * 2;  // the mx buffer NOT used by tile T-1 (its last readers are behind tile T-1's group sync)

@@ -5,11 +5,12 @@
 //   MSG : msg --Wm0,relu--> --Wm1,relu--> --Wm2--> + feat1 --> feat (fp32 -> HBM)
 // (reference models/PointDSC.py:56-61 PointCN, :21-23/:36-38 projections, :12-20/:43-44 fc_message + residual)
 //
-// Persistent CTAs (one per SM), weights resident in shared memory, 128-row tiles.  Warp roles:
-//   warps 0-3  epilogue: thread <-> tile row <-> TMEM lane; bias / ReLU / residual, hi-lo split, stores
-//   warps 4-7  loaders : prefetch the NEXT tile's fp32 rows into registers (coalesced), convert to the
-//                        swizzled 16-bit A image once the tensor core has released the buffer
-//   warp  8    MMA issuer (one lane) + TMEM allocation
+// Persistent CTAs (one per SM), weights resident in shared memory, 128-row tiles.  Warp roles (544 threads):
+//   warps 0-7   epilogue: two warpgroups; thread (row r, half h) owns TMEM lane r and half of the step's columns;
+//               bias / ReLU / residual, hi-lo split, stores
+//   warps 8-15  loaders : prefetch the NEXT tile's fp32 rows into registers (coalesced, 16 rows per warp), convert
+//               to the swizzled 16-bit A image once the tensor core has released the buffer
+//   warp  16    MMA issuer (one lane) + TMEM allocation
 // Accumulators are double-buffered in TMEM by tile parity (512 columns), so the MMAs of tile t+1 run under the
 // epilogue of tile t.  Global stores are staged through a per-warp swizzled smem buffer so that every store
 // instruction writes full 128-byte lines (thread-per-row stores would touch 32 lines per instruction).
@@ -18,15 +19,15 @@
 
 namespace pdsc {
 
-constexpr int kChainThreads = 288;
-constexpr int kChA = 0;                       // A image: [hi p0 16K][hi p1 16K][lo p0 16K][lo p1 16K]
-constexpr int kChW = 65536;                   // weight images (128 KB for PCQ / KV, 80 KB for MSG)
-constexpr int kChStage = 65536 + 131072;      // PCQ / KV: 4 x 4 KB store staging
-constexpr int kChRes = 65536 + 81920;         // MSG: 64 KB residual tile (also the fp32 store staging)
-constexpr int kChBias = 65536 + 81920 + 65536;  // = kChStage + 16384
-constexpr int kChBars = kChBias + kBiasFloats * 4;
-constexpr int kChainSmem = kChBars + 256 + 1024;
-static_assert(kChStage + 16384 == kChBias, "smem map");
+constexpr int kChainThreads = 544;
+constexpr int kChA = 0;                          // A image: [hi p0 16K][hi p1 16K][lo p0 16K][lo p1 16K]
+constexpr int kChW = 65536;                      // weight images (128 KB for PCQ / KV, 80 KB for MSG)
+constexpr int kChStage = 65536 + 131072;         // PCQ / KV: 8 x 4 KB store staging
+constexpr int kChRes = 65536 + 81920;            // MSG: 64 KB residual tile (also the fp32 store staging)
+constexpr int kChBias = kChStage + 32768;        // 256 floats: this mode's biases
+constexpr int kChBars = kChBias + 1024;
+constexpr int kChainSmem = kChBars + 256;        // 230,656 B
+static_assert(kChRes + 65536 <= kChBias, "smem map");
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -34,11 +35,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void quarter_sync(int q4) { asm volatile("bar.sync %0, 64;" ::"r"(2 + q4) : "memory"); }
 
 template <int MODE, int FMT>
 __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* Abuf = smem + kChA;
   float* bias = reinterpret_cast<float*>(smem + kChBias);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kChBars);
@@ -46,25 +47,32 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
   const uint32_t s0 = smem_u32(smem);
   const uint32_t bar_w = smem_u32(bars + 0), a_ready = smem_u32(bars + 1), a1_ready = smem_u32(bars + 2),
                  a_free = smem_u32(bars + 3), r_ready = smem_u32(bars + 4), r_free = smem_u32(bars + 5);
-  // d_full[step][parity] = bars[6 + step*2 + parity],  d_free[parity] = bars[12 + parity]
+  const uint32_t d_full = smem_u32(bars + 6);   // [step][parity] at + 8 * (step * 2 + parity)
+  const uint32_t d_free = smem_u32(bars + 12);  // [parity]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_base = s0 + kChA, w_base = s0 + kChW;
   constexpr int kSteps = (MODE == kMSG) ? 3 : 2;
+  // this mode's biases, packed: PCQ b1|bq, KV bk|bv, MSG bm0|bm1|bm2
+  constexpr int kBiasSrc = (MODE == kPCQ) ? kB1 : (MODE == kKV) ? kBk : kBm0;
 
   if (tid == 0) {
+    if (s0 & 1023u) {
+      printf("pointdsc_b200: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
     mbar_init(bar_w, 1);
-    mbar_init(a_ready, 128);
-    mbar_init(a1_ready, 128);
+    mbar_init(a_ready, 256);
+    mbar_init(a1_ready, 256);
     mbar_init(a_free, 1);
-    mbar_init(r_ready, 128);
-    mbar_init(r_free, 128);
-    for (int i = 0; i < 6; ++i) mbar_init(smem_u32(bars + 6 + i), 1);
-    mbar_init(smem_u32(bars + 12), 128);
-    mbar_init(smem_u32(bars + 13), 128);
+    mbar_init(r_ready, 256);
+    mbar_init(r_free, 256);
+    for (int i = 0; i < 6; ++i) mbar_init(d_full + 8 * i, 1);
+    mbar_init(d_free, 256);
+    mbar_init(d_free + 8, 256);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), 512);
-  for (int i = tid; i < kBiasFloats; i += kChainThreads) bias[i] = a.bias[i];
+  if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (tid < 256) bias[tid] = a.bias[kBiasSrc + tid];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -76,7 +84,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
   }
   const long long num_tiles = (a.rows + 127) / 128;
 
-  if (warp == 8) {
+  if (warp == 16) {
     // =================================== MMA issuer ===================================
     if (lane == 0) {
       mbar_wait(bar_w, 0);
@@ -85,72 +93,82 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
       for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int par = it & 1, u = it >> 1;
         const uint32_t dcol = tmem + (uint32_t)par * 256u;
+        PDSC_STAMP(a.dbg, it, 0, 0);
         mbar_wait(a_ready, (uint32_t)(it & 1));
-        if (it >= 2) mbar_wait(smem_u32(bars + 12 + par), (uint32_t)((u - 1) & 1));  // epilogue drained D[par]
+        PDSC_STAMP(a.dbg, it, 0, 1);
+        if (it >= 2) mbar_wait(d_free + 8 * par, (uint32_t)((u - 1) & 1));  // epilogue drained D[par]
+        PDSC_STAMP(a.dbg, it, 0, 2);
         tc_fence_after();
         if (MODE == kPCQ || MODE == kKV) {
-          issue_gemm(dcol, a_base, a_base + 32768, 16384, w_base, w_base + 32768, 16384, 128, 128, a.split, 0, FMT);
-          mma_commit(smem_u32(bars + 6 + 0 * 2 + par));
+          issue_gemm<2, 128>(dcol, a_base, a_base + 32768, 16384, w_base, w_base + 32768, 16384, a.split, 0, FMT);
+          mma_commit(d_full + 8 * (0 * 2 + par));
+          PDSC_STAMP(a.dbg, it, 0, 3);
           if (MODE == kPCQ) {
             mbar_wait(a1_ready, a1_uses & 1);
             ++a1_uses;
             tc_fence_after();
           }
-          issue_gemm(dcol + 128, a_base, a_base + 32768, 16384, w_base + 65536, w_base + 65536 + 32768, 16384, 128, 128,
-                     a.split, 0, FMT);
-          mma_commit(smem_u32(bars + 6 + 1 * 2 + par));
+          PDSC_STAMP(a.dbg, it, 0, 4);
+          issue_gemm<2, 128>(dcol + 128, a_base, a_base + 32768, 16384, w_base + 65536, w_base + 65536 + 32768, 16384, a.split,
+                             0, FMT);
+          mma_commit(d_full + 8 * (1 * 2 + par));
           mma_commit(a_free);
+          PDSC_STAMP(a.dbg, it, 0, 5);
         } else {
           // Wm0: 64 x 128 (hi 16K | lo 16K, panel 8K)   Wm1: 64 x 64 (hi 8K | lo 8K)   Wm2: 128 x 64 (hi 16K | lo 16K)
-          issue_gemm(dcol, a_base, a_base + 32768, 16384, w_base, w_base + 16384, 8192, 128, 64, a.split, 0, FMT);
-          mma_commit(smem_u32(bars + 6 + 0 * 2 + par));
+          issue_gemm<2, 64>(dcol, a_base, a_base + 32768, 16384, w_base, w_base + 16384, 8192, a.split, 0, FMT);
+          mma_commit(d_full + 8 * (0 * 2 + par));
           mbar_wait(a1_ready, a1_uses & 1);
           ++a1_uses;
           tc_fence_after();
-          issue_gemm(dcol + 64, a_base, a_base + 32768, 16384, w_base + 32768, w_base + 32768 + 8192, 8192, 64, 64, a.split, 0,
-                     FMT);
-          mma_commit(smem_u32(bars + 6 + 1 * 2 + par));
+          issue_gemm<1, 64>(dcol + 64, a_base, a_base + 32768, 16384, w_base + 32768, w_base + 32768 + 8192, 8192, a.split, 0,
+                            FMT);
+          mma_commit(d_full + 8 * (1 * 2 + par));
           mbar_wait(a1_ready, a1_uses & 1);
           ++a1_uses;
           tc_fence_after();
-          issue_gemm(dcol + 128, a_base, a_base + 32768, 16384, w_base + 49152, w_base + 49152 + 16384, 16384, 64, 128, a.split,
-                     0, FMT);
-          mma_commit(smem_u32(bars + 6 + 2 * 2 + par));
+          issue_gemm<1, 128>(dcol + 128, a_base, a_base + 32768, 16384, w_base + 49152, w_base + 49152 + 16384, 16384, a.split,
+                             0, FMT);
+          mma_commit(d_full + 8 * (2 * 2 + par));
           mma_commit(a_free);
         }
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // =================================== loaders ===================================
-    const int lw = warp - 4;
+  } else if (warp >= 8) {
+    // =================================== loaders: 8 warps x 16 rows ===================================
+    const int lw = warp - 8;
     int it = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const long long row0 = tile * 128 + lw * 32;
-      float4 v[32];
+      const long long row0 = tile * 128 + lw * 16;
+      float4 v[16];
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
+      for (int rr = 0; rr < 16; ++rr) {
         const long long grow = row0 + rr;
         v[rr] = (grow < a.rows) ? __ldg(reinterpret_cast<const float4*>(a.in + grow * kC) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      if (tid == 256) PDSC_STAMP(a.dbg, it, 1, 0);
       if (it > 0) mbar_wait(a_free, (uint32_t)((it - 1) & 1));
+      if (tid == 256) PDSC_STAMP(a.dbg, it, 1, 1);
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
+      for (int rr = 0; rr < 16; ++rr) {
         uint32_t h0, l0, h1, l1;
         split_pair<FMT>(v[rr].x, v[rr].y, h0, l0);
         split_pair<FMT>(v[rr].z, v[rr].w, h1, l1);
-        const uint32_t off = (uint32_t)(lane >> 4) * 16384u + sw128_offset((uint32_t)(lw * 32 + rr), (uint32_t)(lane & 15) * 4u);
+        const uint32_t off = (uint32_t)(lane >> 4) * 16384u + sw128_offset((uint32_t)(lw * 16 + rr), (uint32_t)(lane & 15) * 4u);
         *reinterpret_cast<uint2*>(Abuf + off) = make_uint2(h0, h1);
         if (a.split) *reinterpret_cast<uint2*>(Abuf + 32768 + off) = make_uint2(l0, l1);
       }
+      if (tid == 256) PDSC_STAMP(a.dbg, it, 1, 2);
       fence_proxy_async_smem();
       mbar_arrive(a_ready);
+      if (tid == 256) PDSC_STAMP(a.dbg, it, 1, 3);
       if (MODE == kMSG) {
         // residual tile: global -> smem without registers; 16-byte chunk c of row r lands at chunk (c & ~7) | ((c ^ r) & 7)
         if (it > 0) mbar_wait(r_free, (uint32_t)((it - 1) & 1));
 #pragma unroll 8
-        for (int rr = 0; rr < 32; ++rr) {
-          const int r = lw * 32 + rr;
+        for (int rr = 0; rr < 16; ++rr) {
+          const int r = lw * 16 + rr;
           const long long grow = row0 + rr;
           const uint32_t dst = s0 + kChRes + (uint32_t)r * 512u + (uint32_t)(((lane & ~7) | ((lane ^ r) & 7)) << 4);
           const bool ok = grow < a.rows;
@@ -160,21 +178,24 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
       }
     }
   } else {
-    // =================================== epilogue ===================================
-    const int r = tid;  // row of the tile == TMEM lane
-    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
-    uint8_t* stage = smem + kChStage + warp * 4096;       // PCQ / KV: [32 rows][128 B], 16-byte chunks XOR-swizzled by row
-    uint8_t* resw = smem + kChRes + warp * 32 * 512;      // MSG: this warp's 32 residual rows
-    const int sub = lane >> 3, piece = lane & 7;          // read-out phase: rows sub + 4 i, 16-byte piece of the row
+    // =================================== epilogue: 2 warpgroups ===================================
+    const int q4 = warp & 3, h = warp >> 2;
+    const int r = q4 * 32 + lane;  // row of the tile == TMEM lane
+    const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
+    uint8_t* stage = smem + kChStage + warp * 4096;          // PCQ / KV: [32 rows][128 B], 16-byte chunks XOR-swizzled by row
+    uint8_t* resq = smem + kChRes + q4 * 32 * 512;           // MSG: the 32 residual rows of this lane quarter
+    const int sub = lane >> 3, piece = lane & 7;             // read-out phase: rows sub + 4 i, 16-byte piece of the row
     int it = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int par = it & 1, u = it >> 1;
+      if (tid == 0) PDSC_STAMP(a.dbg, it, 3, 6);
       const uint32_t dcol = tmem + lane_base + (uint32_t)par * 256u;
-      const long long row0 = tile * 128 + warp * 32;      // first global row of this warp
+      const long long row0 = tile * 128 + q4 * 32;          // first global row of this lane quarter
       const long long grow = row0 + lane;
       const bool live = grow < a.rows;
-      const int my_b = live ? (int)(grow / a.N) : 0;
-      const int my_n = live ? (int)(grow % a.N) : 0;
+      const unsigned un = (unsigned)a.N;   // rows < 2^31 (checked on the host): 32-bit divisions
+      const int my_b = live ? (int)((unsigned)grow / un) : 0;
+      const int my_n = live ? (int)((unsigned)grow - (unsigned)my_b * un) : 0;
       // image destinations of the 8 rows this lane stores in the read-out phase (PCQ: Q, KV: K)
       uint8_t* img_row[8];
       uint32_t img_rx[8];
@@ -185,7 +206,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           img_row[i] = nullptr;
           img_rx[i] = 0;
           if (g < a.rows) {
-            const int bb = (int)(g / a.N), nn = (int)(g % a.N);
+            const int bb = (int)((unsigned)g / un), nn = (int)((unsigned)g - (unsigned)bb * un);
             if (MODE == kPCQ) {
               const uint32_t rit = (uint32_t)(nn & 127);
               img_row[i] = a.qimg + ((size_t)bb * a.QT + (nn >> 7)) * 65536 + (rit >> 3) * 1024u + (rit & 7u) * 128u;
@@ -199,22 +220,33 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         }
       }
 
+      if (tid == 0) PDSC_STAMP(a.dbg, it, 3, 7);
       for (int step = 0; step < kSteps; ++step) {
-        mbar_wait(smem_u32(bars + 6 + step * 2 + par), (uint32_t)(u & 1));
+        if (tid == 0) PDSC_STAMP(a.dbg, it, 2, step * 2);
+        mbar_wait(d_full + 8 * (step * 2 + par), (uint32_t)(u & 1));
+        if (tid == 0) PDSC_STAMP(a.dbg, it, 2, step * 2 + 1);
         tc_fence_after();
         if (MODE == kMSG && step == 2) mbar_wait(r_ready, (uint32_t)(it & 1));
         const int ncols = (MODE == kMSG && step < 2) ? 64 : 128;
         const uint32_t dstep = (MODE == kMSG) ? (step == 0 ? 0u : (step == 1 ? 64u : 128u)) : (uint32_t)step * 128u;
-        const float* bvec = bias + ((MODE == kPCQ) ? (step == 0 ? kB1 : kBq)
-                                    : (MODE == kKV) ? (step == 0 ? kBk : kBv)
-                                                    : (step == 0 ? kBm0 : (step == 1 ? kBm1 : kBm2)));
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
+        const float* bvec = bias + ((MODE == kMSG) ? (step == 0 ? 0 : (step == 1 ? 64 : 128)) : step * 128);
+        const int cbeg = h * (ncols / 2), cend = cbeg + ncols / 2;
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+          const bool st1 = (tid == 0 && step == 1 && c0 == cbeg);
+          if (st1) PDSC_STAMP(a.dbg, it, 3, 0);
           uint32_t raw[32];
           tmem_ld32(dcol + dstep + c0, raw);
           tmem_ld_wait();
+          if (st1) PDSC_STAMP(a.dbg, it, 3, 1);
           float x[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(raw[i]) + bvec[c0 + i];
+          for (int i = 0; i < 32; i += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(bvec + c0 + i);
+            x[i] = __uint_as_float(raw[i]) + bv.x;
+            x[i + 1] = __uint_as_float(raw[i + 1]) + bv.y;
+            x[i + 2] = __uint_as_float(raw[i + 2]) + bv.z;
+            x[i + 3] = __uint_as_float(raw[i + 3]) + bv.w;
+          }
           if ((MODE == kPCQ && step == 0) || (MODE == kMSG && step < 2)) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
@@ -225,7 +257,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               const int c = (c0 >> 2) + g;  // 16-byte chunk index within the 512-byte row
-              float4* slot = reinterpret_cast<float4*>(resw + lane * 512 + (((c & ~7) | ((c ^ lane) & 7)) << 4));
+              float4* slot = reinterpret_cast<float4*>(resq + lane * 512 + (((c & ~7) | ((c ^ lane) & 7)) << 4));
               float4 rv = *slot;
               rv.x += x[g * 4]; rv.y += x[g * 4 + 1]; rv.z += x[g * 4 + 2]; rv.w += x[g * 4 + 3];
               *slot = rv;
@@ -261,6 +293,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           }
           if ((MODE == kPCQ && step == 1) || (MODE == kKV && step == 0)) {
             // Q / K image -> HBM: stage [hi 64 B | lo 64 B] per row, then 16-byte pieces to their swizzled homes
+            if (st1) PDSC_STAMP(a.dbg, it, 3, 2);
             __syncwarp();
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -270,6 +303,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
               *reinterpret_cast<uint4*>(stage + lane * 128 + (((4 + g) ^ (lane & 7)) << 4)) = lo;
             }
             __syncwarp();
+            if (st1) PDSC_STAMP(a.dbg, it, 3, 3);
             const bool is_lo = piece >= 4;
             const uint32_t kk = (uint32_t)(c0 + (piece & 3) * 8);
             const uint32_t panel_bytes = (MODE == kPCQ) ? 16384u : 8192u;
@@ -284,16 +318,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
                                             (is_lo ? lo_off : 0u)) = val;
               }
             }
+            if (st1) PDSC_STAMP(a.dbg, it, 3, 4);
           }
           if (MODE == kKV && step == 1 && live) {
             // V^T image: row = channel, column = key; a warp writes 32 consecutive keys of one channel row
             uint8_t* base = a.kvimg + ((size_t)my_b * a.KT + (my_n >> 6)) * 65536 + 32768;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const uint16_t h = to_16<FMT>(x[i]);
+              const uint16_t hv = to_16<FMT>(x[i]);
               const uint32_t off = sw128_offset((uint32_t)(c0 + i), (uint32_t)(my_n & 63));
-              *reinterpret_cast<uint16_t*>(base + off) = h;
-              if (a.split) *reinterpret_cast<uint16_t*>(base + 16384 + off) = to_16<FMT>(x[i] - from_16<FMT>(h));
+              *reinterpret_cast<uint16_t*>(base + off) = hv;
+              if (a.split) *reinterpret_cast<uint16_t*>(base + 16384 + off) = to_16<FMT>(x[i] - from_16<FMT>(hv));
             }
           }
         }
@@ -304,23 +339,25 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         }
       }
       if (MODE == kMSG) {
-        // store the finished fp32 tile: one full 512-byte row per instruction
-        __syncwarp();
+        // store the finished fp32 tile: one full 512-byte row per instruction, 16 rows per warp
+        quarter_sync(q4);  // both column halves of these 32 rows are in place
 #pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
+        for (int i = 0; i < 16; ++i) {
+          const int rr = 16 * h + i;
           const long long g = row0 + rr;
-          const float4 val = *reinterpret_cast<const float4*>(resw + rr * 512 + (((lane & ~7) | ((lane ^ rr) & 7)) << 4));
+          const float4 val = *reinterpret_cast<const float4*>(resq + rr * 512 + (((lane & ~7) | ((lane ^ rr) & 7)) << 4));
           if (g < a.rows) *reinterpret_cast<float4*>(a.out_f32 + g * kC + lane * 4) = val;
         }
         mbar_arrive(r_free);
       }
+      if (tid == 0) PDSC_STAMP(a.dbg, it, 2, 6);
       tc_fence_before();
-      mbar_arrive(smem_u32(bars + 12 + par));  // D[par] drained
+      mbar_arrive(d_free + 8 * par);  // D[par] drained
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace pdsc

@@ -27,23 +27,44 @@ struct ChainArgs {
   const uint8_t* wimg;   // this kernel's weight images (contiguous)
   const float* bias;     // the layer's bias block
   int wbytes;            // bytes of weight images to stage
+  long long* dbg;        // optional timeline: clock64() stamps of CTA 0 (tools/tc_timeline.py)
 };
 
-// issue one GEMM step: D[128 x Nout] (+)= A[128 x K] * W[Nout x K]^T, optionally as three hi/lo products
+// timeline stamp: slot = role * 64 + event (CTA 0 only, first 16 tiles)
+#define PDSC_STAMP(dbg, it, role, ev)                                                       \
+  do {                                                                                       \
+    if ((dbg) && blockIdx.x == 0 && (it) < 16) (dbg)[((it) * 4 + (role)) * 8 + (ev)] = clock64(); \
+  } while (0)
+
+// issue one GEMM step: D[128 x NOUT] (+)= A[128 x 64*KP] * W[NOUT x 64*KP]^T, optionally as three hi/lo products.
+// Fully unrolled; a descriptor differs from its neighbour only in the 14-bit start-address field, so each MMA costs
+// one shift/mask per operand on the issuing thread.
+template <int KP, int NOUT>
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_panel_bytes,
-                                           uint32_t b_hi, uint32_t b_lo, uint32_t b_panel_bytes, int K, int Nout,
-                                           int split, uint32_t accumulate, int fmt) {
-  const uint32_t idesc = idesc_f16kind(128, Nout, fmt);
-  const int terms = split ? 3 : 1;
+                                           uint32_t b_hi, uint32_t b_lo, uint32_t b_panel_bytes, int split,
+                                           uint32_t accumulate, int fmt) {
+  const uint32_t idesc = idesc_f16kind(128, NOUT, fmt);
+  constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
   uint32_t acc = accumulate;
-  for (int t = 0; t < terms; ++t) {
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    if (t > 0 && !split) break;
     const uint32_t a = (t == 2) ? a_lo : a_hi;
     const uint32_t b = (t == 1) ? b_lo : b_hi;
-    for (int p = 0; p < K / 64; ++p) {
+#pragma unroll
+    for (int p = 0; p < KP; ++p) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        mma_bf16(d_tmem, smem_desc_sw128(a + p * a_panel_bytes + ks * 32), smem_desc_sw128(b + p * b_panel_bytes + ks * 32),
-                 idesc, acc);
+        const uint32_t alo = (((a + p * a_panel_bytes + ks * 32) >> 4) & 0x3FFFu) | (1u << 16);
+        const uint32_t blo = (((b + p * b_panel_bytes + ks * 32) >> 4) & 0x3FFFu) | (1u << 16);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %5};\n\t"
+            "mov.b64 db, {%2, %5};\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+            ::"r"(d_tmem), "r"(alo), "r"(blo), "r"(idesc), "r"(acc), "r"(kDescHi)
+            : "memory");
         acc = 1;
       }
     }

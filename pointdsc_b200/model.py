@@ -45,6 +45,7 @@ _TAP_SPECS = {
     "refine_solves": (torch.int32, lambda B, N, S, k, c: (B,)),
     "layer_features": (torch.float32, lambda B, N, S, k, c: (B, N, c)),
     "layer_debug": (torch.float32, lambda B, N, S, k, c: (5, B, N, c)),
+    "timeline": (torch.int64, lambda B, N, S, k, c: (2, 16, 4, 8)),
 }
 _INJECT_DTYPES = {"features": torch.float32, "confidence": torch.float32, "seeds": torch.int32,
                   "knn_idx": torch.int32, "seed_trans": torch.float32}
@@ -153,10 +154,13 @@ class PointDSC(nn.Module):
                 _capi.load().pdsc_destroy(self._engine)
             except Exception:
                 pass
-            self._engine = None
+            object.__setattr__(self, "_engine", None)
 
     def __del__(self):
-        self._release()
+        try:
+            self._release()
+        except Exception:  # interpreter shutdown: torch / ctypes may already be torn down
+            pass
 
     def set_precision(self, precision: str):
         if precision not in _capi.PRECISIONS:

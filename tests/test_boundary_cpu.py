@@ -31,8 +31,8 @@ def test_library_builds_and_exports_every_header_symbol():
 def test_struct_layouts_match_the_header():
     from pointdsc_b200 import _capi
     assert ctypes.sizeof(_capi.Config) == 11 * 4
-    # 5 injection + 14 tap pointers, int32 layer_tap (+4 pad), 2 pointers
-    assert ctypes.sizeof(_capi.StageIO) == 19 * 8 + 8 + 16
+    # 5 injection + 14 tap pointers, int32 layer_tap (+4 pad), 3 pointers
+    assert ctypes.sizeof(_capi.StageIO) == 19 * 8 + 8 + 24
     assert _capi.StageIO.layer_tap.offset == 19 * 8
     assert _capi.StageIO.out_layer_features.offset == 19 * 8 + 8
 
