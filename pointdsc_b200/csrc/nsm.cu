@@ -75,20 +75,78 @@ __global__ void __launch_bounds__(128) knn_select_kernel(const float* __restrict
   }
 }
 
+// Register-resident variant for N <= 32 * EPL: one warp per seed row, lane l holds the distances of points
+// l, l+32, ...  Each of the k+1 rounds takes the lexicographic minimum (distance, index) of what is left:
+// lane-local scan in ascending index order (strict '<' keeps the lowest index among equal distances), a 5-step
+// shuffle argmin, and the owning lane retires its element.  No shared memory, no block barriers.
+template <int EPL>
+__global__ void __launch_bounds__(256) knn_select_warp_kernel(const float* __restrict__ dist, int32_t* __restrict__ knn_idx,
+                                                              int N, int rows, int k) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* d = dist + (size_t)row * N;
+  float v[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    const int j = lane + 32 * i;
+    float x = (j < N) ? d[j] : INFINITY;
+    if (x == 0.0f) x = 0.0f;          // -0 ranks equal to +0
+    v[i] = (x == x) ? x : INFINITY;   // NaN distances are never selected
+  }
+  for (int r = 0; r <= k; ++r) {
+    float bd = INFINITY;
+    int bi = EPL;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const bool better = v[i] < bd;
+      bd = better ? v[i] : bd;
+      bi = better ? i : bi;
+    }
+    int bj = (bi < EPL) ? lane + 32 * bi : 0x7FFFFFFF;
+    float wd = bd;
+    int wj = bj;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, wd, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, wj, o);
+      const bool take = (od < wd) || (od == wd && oj < wj);
+      wd = take ? od : wd;
+      wj = take ? oj : wj;
+    }
+    if (wj == bj && bi < EPL) {
+#pragma unroll
+      for (int i = 0; i < EPL; ++i)
+        if (i == bi) v[i] = INFINITY;
+    }
+    if (r > 0 && lane == 0) knn_idx[(size_t)row * k + (r - 1)] = (wj == 0x7FFFFFFF) ? 0 : wj;
+  }
+}
+
 void launch_knn_select(const float* dist, int32_t* knn_idx, int B, int N, int S, int k, cudaStream_t st) {
   if (S <= 0) return;
+  const int rows = B * S;
+  if (N <= 1024) {
+    knn_select_warp_kernel<32><<<(rows + 7) / 8, 256, 0, st>>>(dist, knn_idx, N, rows, k);
+    return;
+  }
+  if (N <= 2048) {
+    knn_select_warp_kernel<64><<<(rows + 7) / 8, 256, 0, st>>>(dist, knn_idx, N, rows, k);
+    return;
+  }
   const int smem = N * (int)sizeof(unsigned long long);
   static int configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
     configured = 16384 * 8;
   }
-  knn_select_kernel<<<B * S, 128, smem, st>>>(dist, knn_idx, N, S, k);
+  knn_select_kernel<<<rows, 128, smem, st>>>(dist, knn_idx, N, S, k);
 }
 
 // ---- compatibility matrix + power iteration, one CTA per seed ----------------------------------------
-constexpr int kFs = kC + 4;  // padded feature row stride (floats)
-
+// Gathered features live TRANSPOSED in shared memory (Ft[channel][neighbour], neighbour stride kp = k rounded
+// up to 4) so a 4 x 4 block of Gram entries costs two LDS.128 per channel (16 FMA per 2 loads); only blocks on
+// or above the diagonal are computed.  Channels are accumulated in ascending order, one fp32 FMA each.
 __global__ void __launch_bounds__(128) nsm_power_kernel(const float* __restrict__ normed, const float* __restrict__ src,
                                                         const float* __restrict__ tgt,
                                                         const int32_t* __restrict__ knn_idx,
@@ -97,8 +155,9 @@ __global__ void __launch_bounds__(128) nsm_power_kernel(const float* __restrict_
                                                         float sigma2, float sigmad2) {
   extern __shared__ __align__(16) float sm[];
   const int ms = k | 1;                  // odd row stride of M: conflict-free row-per-thread reads
-  float* Fs = sm;                        // [k][kFs]
-  float* M = Fs + (size_t)k * kFs;       // [k][ms]
+  const int kp = (k + 3) & ~3;
+  float* Ft = sm;                        // [kC][kp]
+  float* M = Ft + (size_t)kC * kp;       // [k][ms]
   float* pa = M + (size_t)k * ms;        // [k][3]
   float* pb = pa + k * 3;                // [k][3]
   float* v = pb + k * 3;                 // [k]
@@ -108,44 +167,69 @@ __global__ void __launch_bounds__(128) nsm_power_kernel(const float* __restrict_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t seed_row = (size_t)b * S + s;
 
-  for (int a = tid; a < k; a += 128) {
-    int j = knn_idx[seed_row * k + a];
-    j = min(max(j, 0), N - 1);
-    idx[a] = j;
-    const float* ps = src + ((size_t)b * N + j) * 3;
-    const float* pt = tgt + ((size_t)b * N + j) * 3;
-    pa[a * 3 + 0] = ps[0]; pa[a * 3 + 1] = ps[1]; pa[a * 3 + 2] = ps[2];
-    pb[a * 3 + 0] = pt[0]; pb[a * 3 + 1] = pt[1]; pb[a * 3 + 2] = pt[2];
-    v[a] = 1.0f;
-    M[a * ms + a] = 0.0f;  // total_knn_M[:, i, i] = 0  (PointDSC.py:278)
+  for (int a = tid; a < kp; a += 128) {
+    if (a < k) {
+      int j = knn_idx[seed_row * k + a];
+      j = min(max(j, 0), N - 1);
+      idx[a] = j;
+      const float* ps = src + ((size_t)b * N + j) * 3;
+      const float* pt = tgt + ((size_t)b * N + j) * 3;
+      pa[a * 3 + 0] = ps[0]; pa[a * 3 + 1] = ps[1]; pa[a * 3 + 2] = ps[2];
+      pb[a * 3 + 0] = pt[0]; pb[a * 3 + 1] = pt[1]; pb[a * 3 + 2] = pt[2];
+      v[a] = 1.0f;
+      M[a * ms + a] = 0.0f;  // total_knn_M[:, i, i] = 0  (PointDSC.py:278)
+    }
   }
   __syncthreads();
-  for (int a = warp; a < k; a += 4) {
-    const float4 f = *reinterpret_cast<const float4*>(normed + ((size_t)b * N + idx[a]) * kC + lane * 4);
-    *reinterpret_cast<float4*>(Fs + (size_t)a * kFs + lane * 4) = f;
+  for (int a = warp; a < kp; a += 4) {
+    const float* row = normed + ((size_t)b * N + idx[min(a, k - 1)]) * kC;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + 32 * i;
+      Ft[(size_t)c * kp + a] = (a < k) ? row[c] : 0.0f;
+    }
   }
   __syncthreads();
 
-  // upper triangle of feature-compat * spatial-compat
-  const int npairs = k * (k - 1) / 2;
-  for (int t = tid; t < npairs; t += 128) {
-    int a = 0, rem = t;
-    while (rem >= k - 1 - a) { rem -= k - 1 - a; ++a; }
-    const int c = a + 1 + rem;
-    const float4* fa = reinterpret_cast<const float4*>(Fs + (size_t)a * kFs);
-    const float4* fc = reinterpret_cast<const float4*>(Fs + (size_t)c * kFs);
-    float g = 0.f;
-#pragma unroll 8
-    for (int q = 0; q < kC / 4; ++q) {
-      const float4 x = fa[q], y = fc[q];
-      g = fmaf(x.x, y.x, g); g = fmaf(x.y, y.y, g); g = fmaf(x.z, y.z, g); g = fmaf(x.w, y.w, g);
+  // 4 x 4 blocks (A <= B) of feature-compat * spatial-compat
+  const int nb = kp >> 2;
+  const int nblk = nb * (nb + 1) / 2;
+  for (int t = tid; t < nblk; t += 128) {
+    int A = 0, rem = t;
+    while (rem >= nb - A) { rem -= nb - A; ++A; }
+    const int Bk = A + rem;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const float* fa = Ft + 4 * A;
+    const float* fb = Ft + 4 * Bk;
+#pragma unroll 4
+    for (int c = 0; c < kC; ++c) {
+      const float4 x = *reinterpret_cast<const float4*>(fa + (size_t)c * kp);
+      const float4 y = *reinterpret_cast<const float4*>(fb + (size_t)c * kp);
+      const float xr[4] = {x.x, x.y, x.z, x.w};
+      const float yr[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xr[i], yr[j], acc[i][j]);
     }
-    const float fm = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fsub_rn(1.0f, g), sigma2)), 0.0f);
-    const float la = length3_pow(pa[a * 3] - pa[c * 3], pa[a * 3 + 1] - pa[c * 3 + 1], pa[a * 3 + 2] - pa[c * 3 + 2]);
-    const float lb = length3_pow(pb[a * 3] - pb[c * 3], pb[a * 3 + 1] - pb[c * 3 + 1], pb[a * 3 + 2] - pb[c * 3 + 2]);
-    const float val = __fmul_rn(fm, consistency(__fsub_rn(la, lb), sigmad2));
-    M[a * ms + c] = val;
-    M[c * ms + a] = val;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int a = 4 * A + i, c = 4 * Bk + j;
+        if (a < c && c < k) {
+          const float fm = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fsub_rn(1.0f, acc[i][j]), sigma2)), 0.0f);
+          const float la = length3_pow(pa[a * 3] - pa[c * 3], pa[a * 3 + 1] - pa[c * 3 + 1], pa[a * 3 + 2] - pa[c * 3 + 2]);
+          const float lb = length3_pow(pb[a * 3] - pb[c * 3], pb[a * 3 + 1] - pb[c * 3 + 1], pb[a * 3 + 2] - pb[c * 3 + 2]);
+          const float val = __fmul_rn(fm, consistency(__fsub_rn(la, lb), sigmad2));
+          M[a * ms + c] = val;
+          M[c * ms + a] = val;
+        }
+      }
   }
   __syncthreads();
   if (compat_out) {
@@ -186,7 +270,8 @@ void launch_nsm_power(const float* normed, const float* src, const float* tgt, c
                       float sigma_d, cudaStream_t st) {
   if (S <= 0) return;
   const int ms = k | 1;
-  const int smem = (k * kFs + k * ms + 6 * k + k + 4) * (int)sizeof(float);
+  const int kp = (k + 3) & ~3;
+  const int smem = (kC * kp + k * ms + 6 * k + k + 4) * (int)sizeof(float);
   static int configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaFuncSetAttribute(nsm_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);

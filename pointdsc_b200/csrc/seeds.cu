@@ -8,6 +8,8 @@
 // Ranking contract (SURVEY.md §7 trap 3): keys are compared as fp32 values with +0 == -0, and exact
 // ties are broken by the LOWEST index (a stable descending sort; the reference's argsort is unstable,
 // so any order of tied keys is a valid reference output).
+#include <cmath>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -15,23 +17,41 @@ namespace pdsc {
 
 constexpr int kSeedMaxN = 16384;
 
-__global__ void __launch_bounds__(256) nms_key_kernel(const float* __restrict__ src, const float* __restrict__ conf,
-                                                      float* __restrict__ key, int N, float radius) {
+// Thread <-> row i; candidate points j staged through shared memory as (x, y, z, s) and read as broadcasts.
+// `d2_min` is the smallest fp32 squared length whose correctly rounded square root is >= R (found on the host by
+// stepping floats around R^2): sqrt is monotonic, so  length3(d) >= R  <=>  fma-chain(d) >= d2_min  exactly,
+// and the kernel needs no square root at all.
+constexpr int kNmsTile = 256;
+
+__global__ void __launch_bounds__(kNmsTile) nms_key_kernel(const float* __restrict__ src, const float* __restrict__ conf,
+                                                           float* __restrict__ key, int N, float d2_min) {
+  __shared__ float4 pts[kNmsTile];
   const int b = blockIdx.y;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int i = blockIdx.x * 8 + warp;
-  if (i >= N) return;
+  const int i = blockIdx.x * kNmsTile + threadIdx.x;
   const float* p = src + (size_t)b * N * 3;
   const float* s = conf + (size_t)b * N;
-  const float si = s[i];
-  const float xi = p[(size_t)i * 3], yi = p[(size_t)i * 3 + 1], zi = p[(size_t)i * 3 + 2];
+  const bool live = i < N;
+  const int ic = live ? i : N - 1;
+  const float si = s[ic];
+  const float xi = p[(size_t)ic * 3], yi = p[(size_t)ic * 3 + 1], zi = p[(size_t)ic * 3 + 2];
   bool ok = true;
-  for (int j = lane; j < N; j += 32) {
-    const float d = length3(xi - p[(size_t)j * 3], yi - p[(size_t)j * 3 + 1], zi - p[(size_t)j * 3 + 2]);
-    ok = ok && ((si >= s[j]) || (d >= radius));
+  for (int j0 = 0; j0 < N; j0 += kNmsTile) {
+    __syncthreads();
+    const int j = j0 + threadIdx.x;
+    if (j < N) pts[threadIdx.x] = make_float4(p[(size_t)j * 3], p[(size_t)j * 3 + 1], p[(size_t)j * 3 + 2], s[j]);
+    __syncthreads();
+    const int cnt = min(kNmsTile, N - j0);
+    if (ok) {
+#pragma unroll 4
+      for (int t = 0; t < cnt; ++t) {
+        const float4 q = pts[t];
+        const float dx = xi - q.x, dy = yi - q.y, dz = zi - q.z;
+        const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));  // the argument of length3()'s sqrt
+        ok = ok && ((si >= q.w) || (d2 >= d2_min));
+      }
+    }
   }
-  ok = __all_sync(0xffffffffu, ok);
-  if (lane == 0) key[(size_t)b * N + i] = si * (ok ? 1.0f : 0.0f);
+  if (live) key[(size_t)b * N + i] = si * (ok ? 1.0f : 0.0f);
 }
 
 __device__ __forceinline__ uint32_t orderable(float f) {
@@ -71,8 +91,12 @@ int pick_seeds_max_n() { return kSeedMaxN; }
 
 void launch_pick_seeds(const float* src, const float* conf, int32_t* seeds, float* key_scratch, int B, int N, int S,
                        float radius, cudaStream_t st) {
-  dim3 g1((N + 7) / 8, B);
-  nms_key_kernel<<<g1, 256, 0, st>>>(src, conf, key_scratch, N, radius);
+  // smallest float x with sqrtf(x) >= radius (IEEE sqrt on the host == the device's sqrt.rn)
+  float d2_min = radius * radius;
+  while (std::sqrt(d2_min) >= radius && d2_min > 0.f) d2_min = std::nextafter(d2_min, 0.0f);
+  while (std::sqrt(d2_min) < radius) d2_min = std::nextafter(d2_min, INFINITY);
+  dim3 g1((N + kNmsTile - 1) / kNmsTile, B);
+  nms_key_kernel<<<g1, kNmsTile, 0, st>>>(src, conf, key_scratch, N, d2_min);
   int P = 2;
   while (P < N) P <<= 1;
   const int smem = P * (int)sizeof(unsigned long long);
