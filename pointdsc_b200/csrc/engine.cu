@@ -117,7 +117,10 @@ Workspace carve(const pdsc_engine* e, void* ptr, int B, int N) {
   const int NS = pdsc::round_up(N, 64);
   const int S = pdsc_num_seeds(e, N), k = pdsc_num_neighbours(e, N);
   const int T = e->cfg.num_iterations;
-  w.sc = c.take<float>(R * NS);
+  {
+    const size_t tiled = (size_t)B * ((N + 63) / 64) * ((N + 127) / 128) * 8192;  // tensor-core layout (sc_matrix.cu)
+    w.sc = c.take<float>(R * NS > tiled ? R * NS : tiled);
+  }
   w.feat_a = c.take<float>(R * kC);
   w.feat_b = c.take<float>(R * kC);
   w.msg = c.take<float>(R * kC);
@@ -422,12 +425,18 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
 
   // ---- stages i + ii ------------------------------------------------------------------------------
   if (!inject_feat) {
-    launch_sc_matrix(d_src, d_tgt, w.sc, B, N, NS, e->sigma_spat, st);
+    const bool simt = e->cfg.precision == PDSC_FP32_SIMT;
+    if (simt) launch_sc_matrix(d_src, d_tgt, w.sc, B, N, NS, e->sigma_spat, st);
+    else launch_sc_matrix_tiled(d_src, d_tgt, w.sc, B, N, e->sigma_spat, st);
     mark(1);
-    if (io && io->out_sc)
-      cudaMemcpy2DAsync(io->out_sc, (size_t)N * sizeof(float), w.sc, (size_t)NS * sizeof(float), (size_t)N * sizeof(float),
-                        R, cudaMemcpyDeviceToDevice, st);
-    if (e->cfg.precision == PDSC_FP32_SIMT) {
+    if (io && io->out_sc) {
+      if (simt)
+        cudaMemcpy2DAsync(io->out_sc, (size_t)N * sizeof(float), w.sc, (size_t)NS * sizeof(float), (size_t)N * sizeof(float),
+                          R, cudaMemcpyDeviceToDevice, st);
+      else
+        launch_sc_untile(w.sc, io->out_sc, B, N, st);
+    }
+    if (simt) {
       const int rc = encoder_simt(e, w, B, N, d_corr_pos, io, attn_ev, st);
       if (rc) return rc;
     } else {

@@ -11,6 +11,10 @@ namespace pdsc {
 void launch_sc_matrix(const float* src, const float* tgt, float* sc, int B, int N, int NS, float sigma_d,
                       cudaStream_t st);
 
+// tensor-core path: sc_t[b][kt][qt][64][128] tiles (see sc_matrix.cu); size B * ceil(N/64) * ceil(N/128) * 8192 floats
+void launch_sc_matrix_tiled(const float* src, const float* tgt, float* sc, int B, int N, float sigma_d, cudaStream_t st);
+void launch_sc_untile(const float* sc_t, float* out, int B, int N, cudaStream_t st);
+
 // ---- stage ii, fp32 SIMT path -------------------------------------------------------------------
 // out[b][r][o] = epi( sum_c A[b][r][c] * W[b][o][c] )   A,W K-contiguous; K % 16 == 0.
 //   epi 0: (+bias[o]) (relu) (+res[r][o])     epi 1: 2 - 2*acc  (feature-space distance, common.py:58-61)

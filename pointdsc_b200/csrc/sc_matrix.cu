@@ -55,6 +55,61 @@ void launch_sc_matrix(const float* src, const float* tgt, float* sc, int B, int 
   sc_matrix_kernel<<<grid, 256, 0, st>>>(src, tgt, sc, N, NS, s2);
 }
 
+// ---- tiled layout for the tensor-core attention (tc_attention.cuh) ---------------------------------------
+// sc_t[b][kt][qt][64 keys][128 queries]: every (64-key x 128-query) tile the attention CTA (b, qt) consumes at key
+// step kt is one contiguous 32 KB block, so a softmax thread (query row r) reads its 32 SC values at compile-time
+// offsets from one per-tile base pointer, coalesced over the 128 rows, with no per-element address arithmetic.
+// SC is exactly symmetric in fp32 ((x_i - x_j)^2 == (x_j - x_i)^2), so element (key, q) is computed as SC[q][key].
+// Pad rows / columns (key >= N or q >= N) are written as 0.
+__global__ void __launch_bounds__(256) sc_matrix_tiled_kernel(const float* __restrict__ src, const float* __restrict__ tgt,
+                                                              float* __restrict__ sc, int N, int KT, int QT, float s2) {
+  __shared__ float ks[64][3], kt3[64][3];
+  const int b = blockIdx.y;
+  const int kt = blockIdx.x / QT, qt = blockIdx.x % QT;
+  const float* ps = src + (size_t)b * N * 3;
+  const float* pt = tgt + (size_t)b * N * 3;
+  if (threadIdx.x < 192) {
+    const int r = threadIdx.x / 3, c = threadIdx.x % 3;
+    const int i = min(kt * 64 + r, N - 1);
+    ks[r][c] = ps[(size_t)i * 3 + c];
+    kt3[r][c] = pt[(size_t)i * 3 + c];
+  }
+  __syncthreads();
+  const int ql = threadIdx.x & 127, kh = threadIdx.x >> 7;
+  const int q = qt * 128 + ql;
+  const int qc = min(q, N - 1);
+  const float sx = ps[(size_t)qc * 3], sy = ps[(size_t)qc * 3 + 1], sz = ps[(size_t)qc * 3 + 2];
+  const float tx = pt[(size_t)qc * 3], ty = pt[(size_t)qc * 3 + 1], tz = pt[(size_t)qc * 3 + 2];
+  float* out = sc + ((((size_t)b * KT + kt) * QT + qt) << 13) + (size_t)(kh * 32) * 128 + ql;
+#pragma unroll 4
+  for (int c = 0; c < 32; ++c) {
+    const int r = kh * 32 + c;
+    const float ds = length3(ks[r][0] - sx, ks[r][1] - sy, ks[r][2] - sz);
+    const float dt = length3(kt3[r][0] - tx, kt3[r][1] - ty, kt3[r][2] - tz);
+    const float v = consistency(__fsub_rn(ds, dt), s2);
+    out[c * 128] = (q < N && kt * 64 + r < N) ? v : 0.0f;
+  }
+}
+
+void launch_sc_matrix_tiled(const float* src, const float* tgt, float* sc, int B, int N, float sigma_d, cudaStream_t st) {
+  const float s2 = sigma_d * sigma_d;
+  const int KT = (N + 63) / 64, QT = (N + 127) / 128;
+  sc_matrix_tiled_kernel<<<dim3(KT * QT, B), 256, 0, st>>>(src, tgt, sc, N, KT, QT, s2);
+}
+
+// tiled -> dense [B][N][N] (stage tap only)
+__global__ void sc_untile_kernel(const float* __restrict__ sc_t, float* __restrict__ out, int N, int KT, int QT) {
+  const int b = blockIdx.z, i = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  const float* tile = sc_t + ((((size_t)b * KT + (i >> 6)) * QT + (j >> 7)) << 13);
+  out[((size_t)b * N + i) * N + j] = tile[(i & 63) * 128 + (j & 127)];
+}
+void launch_sc_untile(const float* sc_t, float* out, int B, int N, cudaStream_t st) {
+  const int KT = (N + 63) / 64, QT = (N + 127) / 128;
+  sc_untile_kernel<<<dim3((N + 255) / 256, N, B), 256, 0, st>>>(sc_t, out, N, KT, QT);
+}
+
 __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

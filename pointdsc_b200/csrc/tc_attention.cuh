@@ -39,6 +39,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 __device__ __forceinline__ void softmax_group_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// streaming read-only load: every SC element is used once per CTA, keep it out of L1
+__device__ __forceinline__ float ldg_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int FMT>
 __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs a) {
@@ -141,44 +148,29 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
     const int h = (warp - 2) >> 2;           // which 32-column half of the 64-key tile this thread owns
     const int r = q4 * 32 + lane;            // query row within the tile == TMEM lane
     const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
-    const int qi = qt * 128 + r;
-    const int qic = min(qi, a.N - 1);
-    const float* scb = a.sc + (size_t)b * a.N * a.NS + qic;  // SC is symmetric: column qi, coalesced over r
+    // SC tiles of this CTA: sc_t[b][j][qt][64 keys][128 queries] (sc_matrix.cu); thread (r, h) reads element
+    // (32 h + c, r) of tile j at the compile-time offset c * 512 B from one per-tile pointer, coalesced over r.
+    const size_t tile_stride = (size_t)a.QT << 13;
+    const float* sc_cta = a.sc + ((((size_t)b * a.KT) * a.QT + qt) << 13);
+    const float* sc_ptr = sc_cta + (32 * h) * 128 + r;
+    const float* sc_line = sc_cta + (tid - 64) * 32;   // one 128-byte line of the 32 KB tile per softmax thread (L2 prefetch)
     uint8_t* Pbuf = smem + kAttnP;
     const bool ragged = (a.N & 63) != 0;
+    const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && tid == 64;
     float m_ref = -INFINITY, l_sum = 0.f;
 
-    float sc_nxt[32];
+    float scv[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const int key = 32 * h + c;
-      sc_nxt[c] = (key < a.N) ? __ldg(scb + (size_t)key * a.NS) : 0.f;
-    }
+    for (int c = 0; c < 32; ++c) scv[c] = ldg_stream(sc_ptr + c * 128);
+    if (T > 1) prefetch_l2(sc_line + tile_stride);
+    if (T > 2) prefetch_l2(sc_line + 2 * tile_stride);
     for (int j = 0; j < T; ++j) {
       const int s = j & 1, u = j >> 1;
       const int j0 = j * 64 + 32 * h;
-      float scv[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) scv[c] = sc_nxt[c];
-      if (j + 1 < T) {  // prefetch the next tile's SC column segment under this tile's work
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int key = j0 + 64 + c;
-          sc_nxt[c] = (key < a.N) ? __ldg(scb + (size_t)key * a.NS) : 0.f;
-        }
-      }
-      if (j + 3 < T && lane < 4 && qt * 128 + q4 * 32 < a.NS) {
-        // pull the tile after next towards L2: one 128-byte line per key row covers this warp's 32 query columns
-        const float* line0 = a.sc + (size_t)b * a.N * a.NS + qt * 128 + q4 * 32;
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const int key = j0 + 192 + c + lane;
-          if (key < a.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(line0 + (size_t)key * a.NS));
-        }
-      }
-      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 0);
+      if (j + 3 < T) prefetch_l2(sc_line + (size_t)(j + 3) * tile_stride);
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 0);
       mbar_wait(s_full + 8 * s, (uint32_t)(u & 1));
-      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 1);
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 1);
       tc_fence_after();
       uint32_t raw[32];
       tmem_ld32(tmem + 64 * s + lane_base + 32 * h, raw);
@@ -201,11 +193,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
           hmax = fmaxf(hmax, p[c]);
         }
       }
+      if (j + 1 < T) {  // the SC registers are dead: refill them with the next tile's values under the rest of this tile
+        sc_ptr += tile_stride;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) scv[c] = ldg_stream(sc_ptr + c * 128);
+      }
       // row maximum over both halves
-      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 2);
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 2);
       mx[((j & 1) * 2 + h) * 128 + r] = hmax;
       softmax_group_sync();
-      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 3);
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 3);
       const float tmax = fmaxf(hmax, mx[((j & 1) * 2 + (1 - h)) * 128 + r]);
       const bool advance = (j == 0) || (tmax > m_ref + kRescaleThreshold);
       const float new_ref = advance ? tmax : m_ref;
@@ -216,12 +213,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
         rsum += p[c];
       }
       const bool rescale_any = __any_sync(0xffffffffu, advance && j > 0);
-      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 4);
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 4);
       if (j > 0) {
         mbar_wait(p_empty, (uint32_t)((j - 1) & 1));  // PV_{j-1} done: P smem free, O quiescent
         tc_fence_after();
       }
-      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 5);
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 5);
       if (rescale_any) {  // this thread rescales its 64-column half of row r of O
         const float scale = (advance && j > 0) ? ex2_approx(m_ref - new_ref) : 1.0f;
 #pragma unroll
@@ -246,11 +243,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
         *reinterpret_cast<uint4*>(Pbuf + off) = hi;
         if (a.split) *reinterpret_cast<uint4*>(Pbuf + 16384 + off) = lo;
       }
-      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 6);
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 6);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
-      if (tid == 64) PDSC_STAMP(a.dbg, j, 1, 7);
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 7);
     }
     // ---- epilogue: O / l  ->  msg, staged through the (now free) Q region for full-row stores ----
     const int lb = (T & 1) * 2;  // the mx buffer NOT used by tile T-1 (its last readers are behind tile T-1's group sync)

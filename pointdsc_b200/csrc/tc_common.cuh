@@ -36,6 +36,12 @@ struct ChainArgs {
     if ((dbg) && blockIdx.x == 0 && (it) < 16) (dbg)[((it) * 4 + (role)) * 8 + (ev)] = clock64(); \
   } while (0)
 
+// same, for a caller that has already folded the "timeline on, CTA 0, my thread" test into one predicate
+#define PDSC_STAMP1(dbg, it, role, ev)                                              \
+  do {                                                                              \
+    if ((it) < 16) (dbg)[((it) * 4 + (role)) * 8 + (ev)] = clock64();               \
+  } while (0)
+
 // issue one GEMM step: D[128 x NOUT] (+)= A[128 x 64*KP] * W[NOUT x 64*KP]^T, optionally as three hi/lo products.
 // Fully unrolled; a descriptor differs from its neighbour only in the 14-bit start-address field, so each MMA costs
 // one shift/mask per operand on the issuing thread.

@@ -28,14 +28,16 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the warp is parked by the hardware until the phase completes (or the hint
+// expires) instead of spinning through the issue slots the working warps of the same scheduler need.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(1000000u)
       : "memory");
   return ok != 0;
 }
@@ -43,8 +45,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+  for (uint32_t tries = 1;; ++tries) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((tries & 63u) == 0u && clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
       printf("pointdsc_b200: mbarrier wait timed out (block %d, thread %d, bar 0x%x, parity %u)\n", blockIdx.x,
              threadIdx.x, bar, parity);
       __trap();

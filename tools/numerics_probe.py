@@ -46,6 +46,11 @@ def mm(a, b, fmt):
         ah, bh = rnd(a, f), rnd(b, f)
         al = rnd(a - ah, f)
         return ah @ bh + al @ bh
+    if fmt.endswith("x2b"):
+        f = fmt[:-3]
+        ah, bh = rnd(a, f), rnd(b, f)
+        bl = rnd(b - bh, f)
+        return ah @ bh + ah @ bl
     return rnd(a, fmt) @ rnd(b, fmt)
 
 
@@ -106,6 +111,11 @@ CONFIGS = {
     "fp16x3": dict(qk="fp16x3", pv="fp16x3", lin="fp16x3", scfmt="fp32"),
     "fp16x3+scfp16": dict(qk="fp16x3", pv="fp16x3", lin="fp16x3", scfmt="fp16"),
     "bf16x3": dict(qk="bf16x3", pv="bf16x3", lin="bf16x3", scfmt="fp32"),
+    "pv-x2a": dict(qk="fp16x3", pv="fp16x2a", lin="fp16x3", scfmt="fp32"),
+    "pv-x2b": dict(qk="fp16x3", pv="fp16x2b", lin="fp16x3", scfmt="fp32"),
+    "lin-x2a": dict(qk="fp16x3", pv="fp16x3", lin="fp16x2a", scfmt="fp32"),
+    "lin-x2b": dict(qk="fp16x3", pv="fp16x3", lin="fp16x2b", scfmt="fp32"),
+    "lin-fp16": dict(qk="fp16x3", pv="fp16x3", lin="fp16", scfmt="fp32"),
 }
 
 
