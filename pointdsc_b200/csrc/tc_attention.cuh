@@ -5,14 +5,18 @@
 // SC multiplies the logit (it is not a mask): SC_ij = 0 leaves logit 0, which still takes softmax mass.
 //
 // One CTA = 128 queries of one set, looping over 64-key tiles.  Warp roles (320 threads):
-//   warp 0      loader : bulk async copies (TMA engine) of the ready-made K / V^T operand images, 2-stage ring
-//   warp 1      MMA    : S[j&1] = Q K_j^T (TMEM, double-buffered), O += P_j V_j (TMEM); owns the TMEM allocation
-//   warps 2-9   softmax: two warpgroups; thread (row r, half h) owns 32 of the 64 logits of row r.
-//               logits (log2 domain; Q carries log2e/sqrt(C)) = S * SC, SC read through its symmetry
-//               (SC[j][i], coalesced over the 128 rows); lazily advanced reference maximum (FA4-style): the
-//               exponent offset only moves when the row maximum grew by > 8, so O in TMEM is rescaled rarely;
-//               P = ex2(l - ref) is split hi/lo into the swizzled smem A-operand image of the PV MMA.
-// QK_{j+1} is issued before PV_j, so the tensor core works on the next S tile while the softmax runs.
+//   warp 0      loader : bulk async copies (TMA engine) of the ready-made K / V^T operand images (K ring of 3, V ring of 2)
+//   warp 1      MMA    : S_j = Q K_j^T into one of four TMEM buffers, issued up to three tiles ahead;
+//                        O += P_j V_j with P_j read FROM TENSOR MEMORY (A operand in TMEM); owns the TMEM allocation
+//   warps 2-5   softmax group 0: even key tiles          warps 6-9  softmax group 1: odd key tiles
+//               thread = one query row (TMEM lane) and all 64 logits of the tile, so a tile needs no cross-thread
+//               reduction; the two groups work on consecutive tiles half a period apart, so one group's exponentials
+//               (MUFU) run under the other group's conversions (ALU).  Logits (log2 domain; Q carries log2e/sqrt(C))
+//               = S * SC with SC read from the tiled layout of sc_matrix.cu at compile-time offsets.  The running
+//               reference maximum of a row is shared by the two threads that own it (one per group) through shared
+//               memory, tile by tile; it only advances when the row maximum grew by > 8 (FA4-style lazy rescale), so
+//               O in TMEM is rescaled rarely.  P = ex2(l - ref) is split hi/lo (16-bit) and written over its own S
+//               tile in TMEM: it never touches shared memory.
 #pragma once
 #include "tc_common.cuh"
 
@@ -22,15 +26,17 @@ struct AttnArgs {
   int N, NS, QT, KT, split;
   const uint8_t* qimg;
   const uint8_t* kvimg;
-  const float* sc;
+  const float* sc;    // tiled: [B][KT][QT][64 keys][128 queries]
   float* msg;
   long long* dbg;
 };
 
 constexpr int kAttnThreads = 320;
-constexpr int kAttnQ = 0, kAttnK = 65536, kAttnV = 131072, kAttnP = 196608, kAttnBars = 229376;
-constexpr int kAttnMx = kAttnBars + 256;               // float mx[2][2][128]
-constexpr int kAttnSmemTc = kAttnMx + 2048;            // 231,680 B (limit 232,448)
+constexpr int kAttnKStages = 3, kAttnVStages = 2;
+constexpr int kAttnQ = 0, kAttnK = 65536, kAttnV = kAttnK + kAttnKStages * 32768, kAttnBars = kAttnV + kAttnVStages * 32768;
+constexpr int kAttnRef = kAttnBars + 256;              // float ref[2][128], lsum[2][128]
+constexpr int kAttnSmemTc = kAttnRef + 2048;           // 231,680 B (limit 232,448)
+static_assert(kAttnBars == 229376, "smem map");
 constexpr float kRescaleThreshold = 8.0f;              // log2 units: P < 2^8 before the reference max advances
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -38,7 +44,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void softmax_group_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void softmax_all_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // streaming read-only load: every SC element is used once per CTA, keep it out of L1
 __device__ __forceinline__ float ldg_stream(const float* p) {
   float v;
@@ -47,18 +53,53 @@ __device__ __forceinline__ float ldg_stream(const float* p) {
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// D[128 x NOUT] (+)= A[128 x 64 KP] * B[NOUT x 64 KP]^T with A in TENSOR MEMORY (lane = row, 32-bit column c = K elements
+// 2c | 2c+1; hi image at a_hi, lo image at a_lo) and B K-major SWIZZLE_128B panels (64 K elements each) in shared memory.
+// With A in tensor memory the tensor core only streams B from shared memory: an N = 64 step costs 32 cycles instead of
+// the ~64 it costs when the 4 KB A slice is re-read from shared memory as well.
+template <int KP, int NOUT>
+__device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                              uint32_t b_panel_bytes, int split, uint32_t accumulate, int fmt) {
+  const uint32_t idesc = idesc_f16kind(128, NOUT, fmt);
+  constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+  uint32_t acc = accumulate;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    if (t > 0 && !split) break;
+    const uint32_t at = (t == 2) ? a_lo : a_hi;
+    const uint32_t b = (t == 1) ? b_lo : b_hi;
+#pragma unroll
+    for (int p = 0; p < KP; ++p) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t blo = (((b + p * b_panel_bytes + ks * 32) >> 4) & 0x3FFFu) | (1u << 16);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+            "mov.b64 db, {%2, %5};\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+            ::"r"(d_tmem), "r"(at + (p * 4 + ks) * 8), "r"(blo), "r"(idesc), "r"(acc), "r"(kDescHi)
+            : "memory");
+        acc = 1;
+      }
+    }
+  }
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAttnBars);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  float* mx = reinterpret_cast<float*>(smem + kAttnMx);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);   // bars[24] holds the TMEM base, bars[25] is q_tmem
+  float* ref_s = reinterpret_cast<float*>(smem + kAttnRef);   // [2][128] reference maximum after tile j (slot j & 1)
+  float* lsum_s = ref_s + 256;                                // [2][128] per-group row sums (epilogue)
   const uint32_t s0 = smem_u32(smem);
   const uint32_t q_full = smem_u32(bars + 0);
-  const uint32_t k_full = smem_u32(bars + 1), k_empty = smem_u32(bars + 3);     // [stage] at +8*stage
-  const uint32_t v_full = smem_u32(bars + 5), v_empty = smem_u32(bars + 7);
-  const uint32_t s_full = smem_u32(bars + 9), s_empty = smem_u32(bars + 11);
-  const uint32_t p_full = smem_u32(bars + 13), p_empty = smem_u32(bars + 14);
+  const uint32_t k_full = smem_u32(bars + 1), k_empty = smem_u32(bars + 4);     // [3]
+  const uint32_t v_full = smem_u32(bars + 7), v_empty = smem_u32(bars + 9);     // [2]
+  const uint32_t s_full = smem_u32(bars + 11), p_full = smem_u32(bars + 15);    // [4]
+  const uint32_t pv_done = smem_u32(bars + 19), ref_ready = smem_u32(bars + 21);  // [2]
+  const uint32_t o_done = smem_u32(bars + 23), q_tmem = smem_u32(bars + 25);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / a.QT, qt = blockIdx.x % a.QT;
   const int T = a.KT;
@@ -69,21 +110,23 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
       __trap();
     }
     mbar_init(q_full, 1);
+    mbar_init(o_done, 1);
+    mbar_init(q_tmem, 256);
+    for (int i = 0; i < 3; ++i) { mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 1);
       mbar_init(v_full + 8 * i, 1); mbar_init(v_empty + 8 * i, 1);
-      mbar_init(s_full + 8 * i, 1); mbar_init(s_empty + 8 * i, 256);
+      mbar_init(pv_done + 8 * i, 1); mbar_init(ref_ready + 8 * i, 128);
     }
-    mbar_init(p_full, 256);
-    mbar_init(p_empty, 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(p_full + 8 * i, 128); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 256);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tO = tmem + 128;   // S[0] at +0, S[1] at +64 (64 fp32 columns each), O at +128 (128 columns)
+  const uint32_t tO = tmem + 256;   // S/P buffer i at +64 i (i = tile & 3), O at +256 (128 fp32 columns)
+  const uint32_t tQ = tmem + 384;   // Q: hi image (64 columns = 128 channels) at +384, lo image at +448
 
   if (warp == 0) {
     // ===================================== loader =====================================
@@ -93,195 +136,234 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
       bulk_g2s(s0 + kAttnQ, qsrc, 32768u, q_full);
       if (a.split) bulk_g2s(s0 + kAttnQ + 32768, qsrc + 32768, 32768u, q_full);
       const uint32_t half = a.split ? 32768u : 16384u;
-      for (int j = 0; j < T; ++j) {
-        const int s = j & 1, u = j >> 1;
-        const uint8_t* src = a.kvimg + ((size_t)b * a.KT + j) * 65536;
-        if (j >= 2) mbar_wait(k_empty + 8 * s, (uint32_t)((u - 1) & 1));
-        mbar_expect_tx(k_full + 8 * s, half);
-        bulk_g2s(s0 + kAttnK + s * 32768, src, half, k_full + 8 * s);
-        if (j >= 2) mbar_wait(v_empty + 8 * s, (uint32_t)((u - 1) & 1));
-        mbar_expect_tx(v_full + 8 * s, half);
-        bulk_g2s(s0 + kAttnV + s * 32768, src + 32768, half, v_full + 8 * s);
+      const uint8_t* kv = a.kvimg + (size_t)b * a.KT * 65536;
+      // two independent streams (K three tiles deep, V two): never let a full V ring hold back the next K tile
+      int kj = 0, vj = 0;
+      while (kj < T || vj < T) {
+        bool progress = false;
+        if (kj < T) {
+          const int st = kj % kAttnKStages, use = kj / kAttnKStages;
+          if (use == 0 || mbar_test(k_empty + 8 * st, (uint32_t)((use - 1) & 1))) {
+            mbar_expect_tx(k_full + 8 * st, half);
+            bulk_g2s(s0 + kAttnK + st * 32768, kv + (size_t)kj * 65536, half, k_full + 8 * st);
+            ++kj;
+            progress = true;
+          }
+        }
+        if (vj < T) {
+          const int st = vj & 1, use = vj >> 1;
+          if (use == 0 || mbar_test(v_empty + 8 * st, (uint32_t)((use - 1) & 1))) {
+            mbar_expect_tx(v_full + 8 * st, half);
+            bulk_g2s(s0 + kAttnV + st * 32768, kv + (size_t)vj * 65536 + 32768, half, v_full + 8 * st);
+            ++vj;
+            progress = true;
+          }
+        }
+        if (!progress) __nanosleep(64);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
-    if (lane == 0) {
-      const uint32_t q_hi = s0 + kAttnQ, q_lo = s0 + kAttnQ + 32768;
-      const uint32_t p_hi = s0 + kAttnP, p_lo = s0 + kAttnP + 16384;
-      mbar_wait(q_full, 0);
-      mbar_wait(k_full, 0);
+    // The whole warp runs the control flow (waits included); one elected lane issues the MMAs and commits.
+    const bool leader = elect_one();
+    const bool stamp_mma = leader && a.dbg != nullptr && blockIdx.x == 0;
+    mbar_wait(q_tmem, 0);   // Q (hi | lo images, 64 columns each) is resident in tensor memory
+    tc_fence_after();
+    auto issue_qk = [&](int j) {
+      const int st = j % kAttnKStages, use = j / kAttnKStages;
+      mbar_wait(k_full + 8 * st, (uint32_t)(use & 1));
       tc_fence_after();
-      issue_gemm<2, 64>(tmem, q_hi, q_lo, 16384, s0 + kAttnK, s0 + kAttnK + 16384, 8192, a.split, 0, FMT);
-      mma_commit(s_full);
-      mma_commit(k_empty);
-      for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) {
-          const int s1 = (j + 1) & 1, u1 = (j + 1) >> 1;
-          mbar_wait(k_full + 8 * s1, (uint32_t)(u1 & 1));
-          if (j + 1 >= 2) mbar_wait(s_empty + 8 * s1, (uint32_t)((u1 - 1) & 1));
-          tc_fence_after();
-          const uint32_t kb = s0 + kAttnK + s1 * 32768;
-          issue_gemm<2, 64>(tmem + 64 * s1, q_hi, q_lo, 16384, kb, kb + 16384, 8192, a.split, 0, FMT);
-          mma_commit(s_full + 8 * s1);
-          mma_commit(k_empty + 8 * s1);
-        }
-        const int s = j & 1, u = j >> 1;
-        PDSC_STAMP(a.dbg, j, 0, 0);
-        mbar_wait(p_full, (uint32_t)(j & 1));
-        PDSC_STAMP(a.dbg, j, 0, 1);
-        mbar_wait(v_full + 8 * s, (uint32_t)(u & 1));
-        PDSC_STAMP(a.dbg, j, 0, 2);
-        tc_fence_after();
-        const uint32_t vb = s0 + kAttnV + s * 32768;
-        issue_gemm<1, 128>(tO, p_hi, p_lo, 16384, vb, vb + 16384, 16384, a.split, j > 0 ? 1u : 0u, FMT);
-        mma_commit(p_empty);
-        mma_commit(v_empty + 8 * s);
-        PDSC_STAMP(a.dbg, j, 0, 3);
+      if (leader) {
+        const uint32_t kb = s0 + kAttnK + st * 32768;
+        issue_gemm_ts<2, 64>(tmem + 64 * (j & 3), tQ, tQ + 64, kb, kb + 16384, 8192, a.split, 0, FMT);
+        mma_commit(s_full + 8 * (j & 3));
+        mma_commit(k_empty + 8 * st);
       }
+    };
+    for (int j = 0; j < T && j < 3; ++j) issue_qk(j);
+    for (int j = 0; j < T; ++j) {
+      const int vs = j & 1;
+      if (stamp_mma) PDSC_STAMP1(a.dbg, j, 0, 0);
+      mbar_wait(p_full + 8 * (j & 3), (uint32_t)((j >> 2) & 1));
+      if (stamp_mma) PDSC_STAMP1(a.dbg, j, 0, 1);
+      mbar_wait(v_full + 8 * vs, (uint32_t)((j >> 1) & 1));
+      if (stamp_mma) PDSC_STAMP1(a.dbg, j, 0, 2);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t vb = s0 + kAttnV + vs * 32768;
+        const uint32_t tP = tmem + 64 * (j & 3);   // P_j: hi image in columns [0,32), lo image in [32,64) of its S buffer
+        issue_gemm_ts<1, 128>(tO, tP, tP + 32, vb, vb + 16384, 0, a.split, j > 0 ? 1u : 0u, FMT);
+        mma_commit(pv_done + 8 * vs);
+        mma_commit(v_empty + 8 * vs);
+      }
+      if (stamp_mma) PDSC_STAMP1(a.dbg, j, 0, 3);
+      if (j + 3 < T) issue_qk(j + 3);   // in-order execution: runs after PV_{j-1}, the last reader of that S/P buffer
     }
+    if (leader) mma_commit(o_done);
     __syncwarp();
   } else {
     // ===================================== softmax =====================================
     const int q4 = warp & 3;                 // TMEM lane quarter this warp may access
-    const int h = (warp - 2) >> 2;           // which 32-column half of the 64-key tile this thread owns
+    const int g = (warp - 2) >> 2;           // group: tiles j with (j & 1) == g
     const int r = q4 * 32 + lane;            // query row within the tile == TMEM lane
+    const int gt = (warp - 2 - 4 * g) * 32 + lane;   // thread index within the group
     const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
-    // SC tiles of this CTA: sc_t[b][j][qt][64 keys][128 queries] (sc_matrix.cu); thread (r, h) reads element
-    // (32 h + c, r) of tile j at the compile-time offset c * 512 B from one per-tile pointer, coalesced over r.
+    // SC tiles of this CTA: sc_t[b][j][qt][64 keys][128 queries]; thread r reads element (c, r) of tile j at the
+    // compile-time offset c * 512 B from one per-tile pointer, coalesced over the 128 rows.
     const size_t tile_stride = (size_t)a.QT << 13;
     const float* sc_cta = a.sc + ((((size_t)b * a.KT) * a.QT + qt) << 13);
-    const float* sc_ptr = sc_cta + (32 * h) * 128 + r;
-    const float* sc_line = sc_cta + (tid - 64) * 32;   // one 128-byte line of the 32 KB tile per softmax thread (L2 prefetch)
-    uint8_t* Pbuf = smem + kAttnP;
+    const float* sc_line = sc_cta + gt * 32;   // two 128-byte lines of each 32 KB tile per thread (L2 prefetch)
     const bool ragged = (a.N & 63) != 0;
-    const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && tid == 64;
-    float m_ref = -INFINITY, l_sum = 0.f;
+    const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && gt == 0;
+    float my_ref = -INFINITY, l_sum = 0.f;
 
-    float scv[32];
+    float sc[64];
+    if (g < T) {
+      const float* p0 = sc_cta + (size_t)g * tile_stride + r;
 #pragma unroll
-    for (int c = 0; c < 32; ++c) scv[c] = ldg_stream(sc_ptr + c * 128);
-    if (T > 1) prefetch_l2(sc_line + tile_stride);
-    if (T > 2) prefetch_l2(sc_line + 2 * tile_stride);
-    for (int j = 0; j < T; ++j) {
-      const int s = j & 1, u = j >> 1;
-      const int j0 = j * 64 + 32 * h;
-      if (j + 3 < T) prefetch_l2(sc_line + (size_t)(j + 3) * tile_stride);
-      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 0);
-      mbar_wait(s_full + 8 * s, (uint32_t)(u & 1));
-      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 1);
+      for (int c = 0; c < 64; ++c) sc[c] = ldg_stream(p0 + c * 128);
+    }
+    if (g + 2 < T) { prefetch_l2(sc_line + (size_t)(g + 2) * tile_stride); prefetch_l2(sc_line + (size_t)(g + 2) * tile_stride + 4096); }
+    // Q image: shared memory (landed by bulk copy) -> tensor memory, this thread's row; group 0 moves the hi image,
+    // group 1 the lo image.  Logical 16-byte chunk c of row r sits at physical chunk c ^ (r & 7) of its 128-byte row.
+    mbar_wait(q_full, 0);
+    if (g == 0 || a.split) {
+      const uint8_t* qrow = smem + kAttnQ + g * 32768 + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+      for (int pnl = 0; pnl < 2; ++pnl) {
+        uint32_t qv[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v = *reinterpret_cast<const uint4*>(qrow + pnl * 16384 + ((c ^ (r & 7)) << 4));
+          qv[4 * c] = v.x; qv[4 * c + 1] = v.y; qv[4 * c + 2] = v.z; qv[4 * c + 3] = v.w;
+        }
+        tmem_st32(tQ + lane_base + 64 * g + 32 * pnl, qv);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    mbar_arrive(q_tmem);
+    for (int j = g; j < T; j += 2) {
+      const uint32_t tS = tmem + 64 * (j & 3) + lane_base;
+      if (j + 4 < T) { prefetch_l2(sc_line + (size_t)(j + 4) * tile_stride); prefetch_l2(sc_line + (size_t)(j + 4) * tile_stride + 4096); }
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1 + g, 0);
+      mbar_wait(s_full + 8 * (j & 3), (uint32_t)((j >> 2) & 1));
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1 + g, 1);
       tc_fence_after();
-      uint32_t raw[32];
-      tmem_ld32(tmem + 64 * s + lane_base + 32 * h, raw);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(s_empty + 8 * s);
-
-      float p[32];
-      float hmax = -INFINITY;
+      float l[64];
+      {
+        uint32_t raw[32];
+        tmem_ld32(tS, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) l[c] = __uint_as_float(raw[c]) * sc[c];
+        tmem_ld32(tS + 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) l[32 + c] = __uint_as_float(raw[c]) * sc[32 + c];
+      }
       if (ragged && j == T - 1) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          p[c] = (j0 + c < a.N) ? __uint_as_float(raw[c]) * scv[c] : -INFINITY;
-          hmax = fmaxf(hmax, p[c]);
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          p[c] = __uint_as_float(raw[c]) * scv[c];
-          hmax = fmaxf(hmax, p[c]);
-        }
+        for (int c = 0; c < 64; ++c) l[c] = (j * 64 + c < a.N) ? l[c] : -INFINITY;
       }
-      if (j + 1 < T) {  // the SC registers are dead: refill them with the next tile's values under the rest of this tile
-        sc_ptr += tile_stride;
+      if (j + 2 < T) {  // the SC registers are dead: refill them with this group's next tile under the rest of the work
+        const float* pn = sc_cta + (size_t)(j + 2) * tile_stride + r;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) scv[c] = ldg_stream(sc_ptr + c * 128);
+        for (int c = 0; c < 64; ++c) sc[c] = ldg_stream(pn + c * 128);
       }
-      // row maximum over both halves
-      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 2);
-      mx[((j & 1) * 2 + h) * 128 + r] = hmax;
-      softmax_group_sync();
-      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 3);
-      const float tmax = fmaxf(hmax, mx[((j & 1) * 2 + (1 - h)) * 128 + r]);
-      const bool advance = (j == 0) || (tmax > m_ref + kRescaleThreshold);
-      const float new_ref = advance ? tmax : m_ref;
+      float tmax = l[0];
+#pragma unroll
+      for (int c = 1; c < 64; ++c) tmax = fmaxf(tmax, l[c]);
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1 + g, 2);
+      // running reference maximum of the row, handed from tile to tile between the row's two owner threads
+      float prev_ref = -INFINITY;
+      if (j > 0) {
+        mbar_wait(ref_ready + 8 * ((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));
+        prev_ref = ref_s[((j - 1) & 1) * 128 + r];
+      }
+      const bool advance = (j == 0) || (tmax > prev_ref + kRescaleThreshold);
+      const float new_ref = advance ? tmax : prev_ref;
+      ref_s[(j & 1) * 128 + r] = new_ref;
+      mbar_arrive(ref_ready + 8 * (j & 1));
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1 + g, 3);
+      l_sum *= ex2_approx(my_ref - new_ref);   // the reference may have moved since this thread's previous tile
+      my_ref = new_ref;
       float rsum = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        p[c] = ex2_approx(p[c] - new_ref);
-        rsum += p[c];
+      for (int c = 0; c < 64; ++c) {
+        l[c] = ex2_approx(l[c] - new_ref);
+        rsum += l[c];
       }
-      const bool rescale_any = __any_sync(0xffffffffu, advance && j > 0);
-      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 4);
-      if (j > 0) {
-        mbar_wait(p_empty, (uint32_t)((j - 1) & 1));  // PV_{j-1} done: P smem free, O quiescent
-        tc_fence_after();
-      }
-      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 5);
-      if (rescale_any) {  // this thread rescales its 64-column half of row r of O
-        const float scale = (advance && j > 0) ? ex2_approx(m_ref - new_ref) : 1.0f;
+      l_sum += rsum;
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1 + g, 4);
+      // P (16-bit hi / lo images) over this thread's own S row: column c holds keys 2c | 2c+1
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) split_pair<FMT>(l[32 * hf + 2 * i], l[32 * hf + 2 * i + 1], hi[i], lo[i]);
+        tmem_st16(tS + 16 * hf, hi);
+        if (a.split) tmem_st16(tS + 32 + 16 * hf, lo);
+      }
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1 + g, 5);
+      // rare: the reference advanced, O (accumulated under the old reference) must be rescaled before PV_j
+      if (__any_sync(0xffffffffu, advance && j > 0)) {
+        mbar_wait(pv_done + 8 * ((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));   // PV_{j-1} complete: O quiescent
+        tc_fence_after();
+        const float scale = (advance && j > 0) ? ex2_approx(prev_ref - new_ref) : 1.0f;
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t o[32];
-          tmem_ld32(tO + lane_base + 64 * h + c0, o);
+          tmem_ld32(tO + lane_base + c0, o);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * scale);
-          tmem_st32(tO + lane_base + 64 * h + c0, o);
+          tmem_st32(tO + lane_base + c0, o);
         }
-        tmem_st_wait();
-        l_sum *= scale;
       }
-      m_ref = new_ref;
-      l_sum += rsum;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 hi, lo;
-        split8<FMT>(p + g * 8, hi, lo);
-        const uint32_t off = sw128_offset((uint32_t)r, (uint32_t)(32 * h + g * 8));
-        *reinterpret_cast<uint4*>(Pbuf + off) = hi;
-        if (a.split) *reinterpret_cast<uint4*>(Pbuf + 16384 + off) = lo;
-      }
-      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 6);
-      fence_proxy_async_smem();
+      tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
-      if (stamp) PDSC_STAMP1(a.dbg, j, 1, 7);
+      mbar_arrive(p_full + 8 * (j & 3));
+      if (stamp) PDSC_STAMP1(a.dbg, j, 1 + g, 6);
     }
     // ---- epilogue: O / l  ->  msg, staged through the (now free) Q region for full-row stores ----
-    const int lb = (T & 1) * 2;  // the mx buffer NOT used by tile T-1 (its last readers are behind tile T-1's group sync)
-    mx[(lb + h) * 128 + r] = l_sum;
-    mbar_wait(p_empty, (uint32_t)((T - 1) & 1));
-    tc_fence_after();
-    softmax_group_sync();
-    const float inv_l = 1.0f / (l_sum + mx[(lb + 1 - h) * 128 + r]);
+    {
+      const int jl = T - 1;
+      mbar_wait(ref_ready + 8 * (jl & 1), (uint32_t)((jl >> 1) & 1));
+      const float final_ref = ref_s[(jl & 1) * 128 + r];
+      lsum_s[g * 128 + r] = l_sum * ex2_approx(my_ref - final_ref);
+      mbar_wait(o_done, 0);   // last PV complete (and with it every earlier MMA)
+      tc_fence_after();
+    }
+    softmax_all_sync();
+    const float inv_l = 1.0f / (lsum_s[r] + lsum_s[128 + r]);
     uint8_t* ostage = smem + kAttnQ;  // [128 rows][512 B], 16-byte chunk c of row r at (c & ~7) | ((c ^ r) & 7)
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
+    for (int c0 = 0; c0 < 64; c0 += 32) {   // group g converts columns [64 g, 64 g + 64) of every row
       uint32_t o[32];
-      tmem_ld32(tO + lane_base + 64 * h + c0, o);
+      tmem_ld32(tO + lane_base + 64 * g + c0, o);
       tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const int c = 16 * h + (c0 >> 2) + g;
+      for (int q = 0; q < 8; ++q) {
+        const int c = 16 * g + (c0 >> 2) + q;
         *reinterpret_cast<float4*>(ostage + r * 512 + (((c & ~7) | ((c ^ r) & 7)) << 4)) =
-            make_float4(__uint_as_float(o[g * 4]) * inv_l, __uint_as_float(o[g * 4 + 1]) * inv_l,
-                        __uint_as_float(o[g * 4 + 2]) * inv_l, __uint_as_float(o[g * 4 + 3]) * inv_l);
+            make_float4(__uint_as_float(o[q * 4]) * inv_l, __uint_as_float(o[q * 4 + 1]) * inv_l,
+                        __uint_as_float(o[q * 4 + 2]) * inv_l, __uint_as_float(o[q * 4 + 3]) * inv_l);
       }
     }
     tc_fence_before();
-    softmax_group_sync();
+    softmax_all_sync();
     float* dst = a.msg + ((size_t)b * a.N + qt * 128) * kC;
 #pragma unroll 4
     for (int i = 0; i < 16; ++i) {
-      const int rr = q4 * 32 + 16 * h + i;
+      const int rr = q4 * 32 + 16 * g + i;
       const float4 val = *reinterpret_cast<const float4*>(ostage + rr * 512 + (((lane & ~7) | ((lane ^ rr) & 7)) << 4));
       if (qt * 128 + rr < a.N) *reinterpret_cast<float4*>(dst + (size_t)rr * kC + lane * 4) = val;
     }
   }
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace pdsc

@@ -86,47 +86,58 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
 
   if (warp == 16) {
     // =================================== MMA issuer ===================================
-    if (lane == 0) {
-      mbar_wait(bar_w, 0);
-      int it = 0;
-      uint32_t a1_uses = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int par = it & 1, u = it >> 1;
-        const uint32_t dcol = tmem + (uint32_t)par * 256u;
-        PDSC_STAMP(a.dbg, it, 0, 0);
-        mbar_wait(a_ready, (uint32_t)(it & 1));
-        PDSC_STAMP(a.dbg, it, 0, 1);
-        if (it >= 2) mbar_wait(d_free + 8 * par, (uint32_t)((u - 1) & 1));  // epilogue drained D[par]
-        PDSC_STAMP(a.dbg, it, 0, 2);
-        tc_fence_after();
-        if (MODE == kPCQ || MODE == kKV) {
+    // The whole warp runs the control flow (waits included); one elected lane issues the MMAs and commits.
+    const bool leader = elect_one();
+    const bool stamp_mma = leader && a.dbg != nullptr && blockIdx.x == 0;
+    mbar_wait(bar_w, 0);
+    int it = 0;
+    uint32_t a1_uses = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int par = it & 1, u = it >> 1;
+      const uint32_t dcol = tmem + (uint32_t)par * 256u;
+      if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 0);
+      mbar_wait(a_ready, (uint32_t)(it & 1));
+      if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 1);
+      if (it >= 2) mbar_wait(d_free + 8 * par, (uint32_t)((u - 1) & 1));  // epilogue drained D[par]
+      if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 2);
+      tc_fence_after();
+      if (MODE == kPCQ || MODE == kKV) {
+        if (leader) {
           issue_gemm<2, 128>(dcol, a_base, a_base + 32768, 16384, w_base, w_base + 32768, 16384, a.split, 0, FMT);
           mma_commit(d_full + 8 * (0 * 2 + par));
-          PDSC_STAMP(a.dbg, it, 0, 3);
-          if (MODE == kPCQ) {
-            mbar_wait(a1_ready, a1_uses & 1);
-            ++a1_uses;
-            tc_fence_after();
-          }
-          PDSC_STAMP(a.dbg, it, 0, 4);
+        }
+        if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 3);
+        if (MODE == kPCQ) {
+          mbar_wait(a1_ready, a1_uses & 1);
+          ++a1_uses;
+          tc_fence_after();
+        }
+        if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 4);
+        if (leader) {
           issue_gemm<2, 128>(dcol + 128, a_base, a_base + 32768, 16384, w_base + 65536, w_base + 65536 + 32768, 16384, a.split,
                              0, FMT);
           mma_commit(d_full + 8 * (1 * 2 + par));
           mma_commit(a_free);
-          PDSC_STAMP(a.dbg, it, 0, 5);
-        } else {
-          // Wm0: 64 x 128 (hi 16K | lo 16K, panel 8K)   Wm1: 64 x 64 (hi 8K | lo 8K)   Wm2: 128 x 64 (hi 16K | lo 16K)
+        }
+        if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 5);
+      } else {
+        // Wm0: 64 x 128 (hi 16K | lo 16K, panel 8K)   Wm1: 64 x 64 (hi 8K | lo 8K)   Wm2: 128 x 64 (hi 16K | lo 16K)
+        if (leader) {
           issue_gemm<2, 64>(dcol, a_base, a_base + 32768, 16384, w_base, w_base + 16384, 8192, a.split, 0, FMT);
           mma_commit(d_full + 8 * (0 * 2 + par));
-          mbar_wait(a1_ready, a1_uses & 1);
-          ++a1_uses;
-          tc_fence_after();
+        }
+        mbar_wait(a1_ready, a1_uses & 1);
+        ++a1_uses;
+        tc_fence_after();
+        if (leader) {
           issue_gemm<1, 64>(dcol + 64, a_base, a_base + 32768, 16384, w_base + 32768, w_base + 32768 + 8192, 8192, a.split, 0,
                             FMT);
           mma_commit(d_full + 8 * (1 * 2 + par));
-          mbar_wait(a1_ready, a1_uses & 1);
-          ++a1_uses;
-          tc_fence_after();
+        }
+        mbar_wait(a1_ready, a1_uses & 1);
+        ++a1_uses;
+        tc_fence_after();
+        if (leader) {
           issue_gemm<1, 128>(dcol + 128, a_base, a_base + 32768, 16384, w_base + 49152, w_base + 49152 + 16384, 16384, a.split,
                              0, FMT);
           mma_commit(d_full + 8 * (2 * 2 + par));
