@@ -1,25 +1,31 @@
 // tc_chain: fused row-tile GEMM chains of the encoder's 1x1 convolutions on tcgen05 (included by encoder_tc.cu).
 //
-//   PCQ : feat  --W1,relu--> feat1 (fp32 -> HBM, and 16-bit image -> smem) --Wq--> Q image (HBM)
+//   PCQ : feat  --W1,relu--> feat1 (fp32 -> HBM) --Wq--> Q image (HBM)
 //   KV  : feat1 --Wk--> K image (HBM) ;  feat1 --Wv--> V^T image (HBM)
 //   MSG : msg --Wm0,relu--> --Wm1,relu--> --Wm2--> + feat1 --> feat (fp32 -> HBM)
 // (reference models/PointDSC.py:56-61 PointCN, :21-23/:36-38 projections, :12-20/:43-44 fc_message + residual)
 //
-// Persistent CTAs (one per SM), weights resident in shared memory, 128-row tiles.  Warp roles (544 threads):
+// Persistent CTAs (one per SM), weights resident in shared memory, 128-row tiles.  Warp roles (512 threads, so that the
+// register file divides into 128 registers per thread):
 //   warps 0-7   epilogue: two warpgroups; thread (row r, half h) owns TMEM lane r and half of the step's columns;
 //               bias / ReLU / residual, hi-lo split, stores
-//   warps 8-15  loaders : prefetch the NEXT tile's fp32 rows into registers (coalesced, 16 rows per warp), convert
+//   warps 8-14  loaders : prefetch the NEXT tile's fp32 rows into registers (coalesced, rows lw, lw+7, ...), convert
 //               to the swizzled 16-bit A image once the tensor core has released the buffer
-//   warp  16    MMA issuer (one lane) + TMEM allocation
-// Accumulators are double-buffered in TMEM by tile parity (512 columns), so the MMAs of tile t+1 run under the
-// epilogue of tile t.  Global stores are staged through a per-warp swizzled smem buffer so that every store
-// instruction writes full 128-byte lines (thread-per-row stores would touch 32 lines per instruction).
+//   warp  15    MMA issuer (whole warp runs the control flow, one elected lane issues) + TMEM allocation
+// Chained steps never go back through shared memory: the epilogue writes the next step's A operand (16-bit hi | lo
+// images) over the accumulator columns it has just read, and the next MMA takes A FROM TENSOR MEMORY.  Chunk q (K
+// elements 32 q .. 32 q + 31) of such an operand sits at columns 32 q .. 32 q + 31 of the producing accumulator as
+// [hi: 16 columns | lo: 16 columns].  The shared-memory A buffer is therefore released as soon as the tile's first
+// MMA has consumed it, and the loaders convert tile t+1 under the epilogue of tile t.
+// Accumulators are double-buffered in TMEM by tile parity (2 x 256 columns).  Global stores are staged through a
+// per-warp swizzled smem buffer so that every store instruction writes full 64/128-byte segments.
 #pragma once
 #include "tc_common.cuh"
 
 namespace pdsc {
 
-constexpr int kChainThreads = 544;
+constexpr int kChainThreads = 512;
+constexpr int kChLoaderWarps = 7, kChLoaderRows = 19;   // rows lw + 7 i, i < 19 (the last one only for lw < 2)
 constexpr int kChA = 0;                          // A image: [hi p0 16K][hi p1 16K][lo p0 16K][lo p1 16K]
 constexpr int kChW = 65536;                      // weight images (128 KB for PCQ / KV, 80 KB for MSG)
 constexpr int kChStage = 65536 + 131072;         // PCQ / KV: 8 x 4 KB store staging
@@ -36,6 +42,50 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void quarter_sync(int q4) { asm volatile("bar.sync %0, 64;" ::"r"(2 + q4) : "memory"); }
+
+// D[128 x NOUT] (+)= A[128 x 32 KCH] * B[NOUT x 32 KCH]^T, A in tensor memory in the chunked in-place layout described
+// above (chunk q at a_base + 32 q), B K-major SWIZZLE_128B panels of 64 K elements in shared memory.
+template <int KCH, int NOUT>
+__device__ __forceinline__ void issue_gemm_tchunk(uint32_t d_tmem, uint32_t a_base, uint32_t b_hi, uint32_t b_lo,
+                                                  uint32_t b_panel_bytes, int split, int fmt) {
+  const uint32_t idesc = idesc_f16kind(128, NOUT, fmt);
+  constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+  uint32_t acc = 0;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    if (t > 0 && !split) break;
+    const uint32_t b = (t == 1) ? b_lo : b_hi;
+#pragma unroll
+    for (int q = 0; q < KCH; ++q) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int k0 = 32 * q + 16 * s;
+        const uint32_t acol = a_base + 32 * q + (t == 2 ? 16 : 0) + 8 * s;
+        const uint32_t blo = (((b + (k0 >> 6) * b_panel_bytes + ((k0 & 63) >> 4) * 32) >> 4) & 0x3FFFu) | (1u << 16);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+            "mov.b64 db, {%2, %5};\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+            ::"r"(d_tmem), "r"(acol), "r"(blo), "r"(idesc), "r"(acc), "r"(kDescHi)
+            : "memory");
+        acc = 1;
+      }
+    }
+  }
+}
+
+// (set, index within the set) of the row `rr` rows after a row known to be (b0, n0); rows < 2^31
+__device__ __forceinline__ void locate_row(int b0, int n0, int rr, int N, int& bb, int& nn) {
+  nn = n0 + rr;
+  bb = b0;
+  if (N >= 64) {            // at most one wrap within a 32-row quarter
+    if (nn >= N) { nn -= N; ++bb; }
+  } else {
+    bb += nn / N;
+    nn = nn % N;
+  }
+}
 
 template <int MODE, int FMT>
 __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a) {
@@ -61,17 +111,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
       __trap();
     }
     mbar_init(bar_w, 1);
-    mbar_init(a_ready, 256);
+    mbar_init(a_ready, kChLoaderWarps * 32);
     mbar_init(a1_ready, 256);
     mbar_init(a_free, 1);
-    mbar_init(r_ready, 256);
+    mbar_init(r_ready, kChLoaderWarps * 32);
     mbar_init(r_free, 256);
     for (int i = 0; i < 6; ++i) mbar_init(d_full + 8 * i, 1);
     mbar_init(d_free, 256);
     mbar_init(d_free + 8, 256);
     fence_barrier_init();
   }
-  if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 15) tmem_alloc(smem_u32(tmem_slot), 512);
   if (tid < 256) bias[tid] = a.bias[kBiasSrc + tid];
   tc_fence_before();
   __syncthreads();
@@ -84,9 +134,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
   }
   const long long num_tiles = (a.rows + 127) / 128;
 
-  if (warp == 16) {
+  if (warp == 15) {
     // =================================== MMA issuer ===================================
-    // The whole warp runs the control flow (waits included); one elected lane issues the MMAs and commits.
     const bool leader = elect_one();
     const bool stamp_mma = leader && a.dbg != nullptr && blockIdx.x == 0;
     mbar_wait(bar_w, 0);
@@ -101,89 +150,101 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
       if (it >= 2) mbar_wait(d_free + 8 * par, (uint32_t)((u - 1) & 1));  // epilogue drained D[par]
       if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 2);
       tc_fence_after();
-      if (MODE == kPCQ || MODE == kKV) {
+      if (MODE == kPCQ) {
         if (leader) {
           issue_gemm<2, 128>(dcol, a_base, a_base + 32768, 16384, w_base, w_base + 32768, 16384, a.split, 0, FMT);
           mma_commit(d_full + 8 * (0 * 2 + par));
+          mma_commit(a_free);   // the smem A image is dead: step 1 reads feat1 from tensor memory
         }
         if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 3);
-        if (MODE == kPCQ) {
-          mbar_wait(a1_ready, a1_uses & 1);
-          ++a1_uses;
-          tc_fence_after();
-        }
+        mbar_wait(a1_ready, a1_uses & 1);
+        ++a1_uses;
+        tc_fence_after();
         if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 4);
         if (leader) {
+          issue_gemm_tchunk<4, 128>(dcol + 128, dcol, w_base + 65536, w_base + 65536 + 32768, 16384, a.split, FMT);
+          mma_commit(d_full + 8 * (1 * 2 + par));
+        }
+        if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 5);
+      } else if (MODE == kKV) {
+        if (leader) {
+          issue_gemm<2, 128>(dcol, a_base, a_base + 32768, 16384, w_base, w_base + 32768, 16384, a.split, 0, FMT);
+          mma_commit(d_full + 8 * (0 * 2 + par));
           issue_gemm<2, 128>(dcol + 128, a_base, a_base + 32768, 16384, w_base + 65536, w_base + 65536 + 32768, 16384, a.split,
                              0, FMT);
           mma_commit(d_full + 8 * (1 * 2 + par));
           mma_commit(a_free);
         }
-        if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 5);
       } else {
         // Wm0: 64 x 128 (hi 16K | lo 16K, panel 8K)   Wm1: 64 x 64 (hi 8K | lo 8K)   Wm2: 128 x 64 (hi 16K | lo 16K)
         if (leader) {
           issue_gemm<2, 64>(dcol, a_base, a_base + 32768, 16384, w_base, w_base + 16384, 8192, a.split, 0, FMT);
           mma_commit(d_full + 8 * (0 * 2 + par));
+          mma_commit(a_free);
         }
         mbar_wait(a1_ready, a1_uses & 1);
         ++a1_uses;
         tc_fence_after();
         if (leader) {
-          issue_gemm<1, 64>(dcol + 64, a_base, a_base + 32768, 16384, w_base + 32768, w_base + 32768 + 8192, 8192, a.split, 0,
-                            FMT);
+          issue_gemm_tchunk<2, 64>(dcol + 64, dcol, w_base + 32768, w_base + 32768 + 8192, 8192, a.split, FMT);
           mma_commit(d_full + 8 * (1 * 2 + par));
         }
         mbar_wait(a1_ready, a1_uses & 1);
         ++a1_uses;
         tc_fence_after();
         if (leader) {
-          issue_gemm<1, 128>(dcol + 128, a_base, a_base + 32768, 16384, w_base + 49152, w_base + 49152 + 16384, 16384, a.split,
-                             0, FMT);
+          issue_gemm_tchunk<2, 128>(dcol + 128, dcol + 64, w_base + 49152, w_base + 49152 + 16384, 16384, a.split, FMT);
           mma_commit(d_full + 8 * (2 * 2 + par));
-          mma_commit(a_free);
         }
       }
     }
     __syncwarp();
   } else if (warp >= 8) {
-    // =================================== loaders: 8 warps x 16 rows ===================================
+    // =================================== loaders: 7 warps, rows lw + 7 i ===================================
     const int lw = warp - 8;
+    const bool stamp_ld = a.dbg != nullptr && blockIdx.x == 0 && tid == 256;
     int it = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const long long row0 = tile * 128 + lw * 16;
-      float4 v[16];
+      const long long row0 = tile * 128;
+      float4 v[kChLoaderRows];
 #pragma unroll
-      for (int rr = 0; rr < 16; ++rr) {
+      for (int i = 0; i < kChLoaderRows; ++i) {
+        const int rr = lw + kChLoaderWarps * i;
         const long long grow = row0 + rr;
-        v[rr] = (grow < a.rows) ? __ldg(reinterpret_cast<const float4*>(a.in + grow * kC) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = (rr < 128 && grow < a.rows) ? __ldg(reinterpret_cast<const float4*>(a.in + grow * kC) + lane)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (tid == 256) PDSC_STAMP(a.dbg, it, 1, 0);
+      if (stamp_ld) PDSC_STAMP1(a.dbg, it, 1, 0);
       if (it > 0) mbar_wait(a_free, (uint32_t)((it - 1) & 1));
-      if (tid == 256) PDSC_STAMP(a.dbg, it, 1, 1);
+      if (stamp_ld) PDSC_STAMP1(a.dbg, it, 1, 1);
 #pragma unroll
-      for (int rr = 0; rr < 16; ++rr) {
-        uint32_t h0, l0, h1, l1;
-        split_pair<FMT>(v[rr].x, v[rr].y, h0, l0);
-        split_pair<FMT>(v[rr].z, v[rr].w, h1, l1);
-        const uint32_t off = (uint32_t)(lane >> 4) * 16384u + sw128_offset((uint32_t)(lw * 16 + rr), (uint32_t)(lane & 15) * 4u);
-        *reinterpret_cast<uint2*>(Abuf + off) = make_uint2(h0, h1);
-        if (a.split) *reinterpret_cast<uint2*>(Abuf + 32768 + off) = make_uint2(l0, l1);
+      for (int i = 0; i < kChLoaderRows; ++i) {
+        const int rr = lw + kChLoaderWarps * i;
+        if (rr < 128) {
+          uint32_t h0, l0, h1, l1;
+          split_pair<FMT>(v[i].x, v[i].y, h0, l0);
+          split_pair<FMT>(v[i].z, v[i].w, h1, l1);
+          const uint32_t off = (uint32_t)(lane >> 4) * 16384u + sw128_offset((uint32_t)rr, (uint32_t)(lane & 15) * 4u);
+          *reinterpret_cast<uint2*>(Abuf + off) = make_uint2(h0, h1);
+          if (a.split) *reinterpret_cast<uint2*>(Abuf + 32768 + off) = make_uint2(l0, l1);
+        }
       }
-      if (tid == 256) PDSC_STAMP(a.dbg, it, 1, 2);
+      if (stamp_ld) PDSC_STAMP1(a.dbg, it, 1, 2);
       fence_proxy_async_smem();
       mbar_arrive(a_ready);
-      if (tid == 256) PDSC_STAMP(a.dbg, it, 1, 3);
+      if (stamp_ld) PDSC_STAMP1(a.dbg, it, 1, 3);
       if (MODE == kMSG) {
         // residual tile: global -> smem without registers; 16-byte chunk c of row r lands at chunk (c & ~7) | ((c ^ r) & 7)
         if (it > 0) mbar_wait(r_free, (uint32_t)((it - 1) & 1));
-#pragma unroll 8
-        for (int rr = 0; rr < 16; ++rr) {
-          const int r = lw * 16 + rr;
-          const long long grow = row0 + rr;
-          const uint32_t dst = s0 + kChRes + (uint32_t)r * 512u + (uint32_t)(((lane & ~7) | ((lane ^ r) & 7)) << 4);
-          const bool ok = grow < a.rows;
-          cp_async16(dst, ok ? (const void*)(a.res + grow * kC + lane * 4) : (const void*)a.res, ok ? 16u : 0u);
+#pragma unroll
+        for (int i = 0; i < kChLoaderRows; ++i) {
+          const int r = lw + kChLoaderWarps * i;
+          if (r < 128) {
+            const long long grow = row0 + r;
+            const uint32_t dst = s0 + kChRes + (uint32_t)r * 512u + (uint32_t)(((lane & ~7) | ((lane ^ r) & 7)) << 4);
+            const bool ok = grow < a.rows;
+            cp_async16(dst, ok ? (const void*)(a.res + grow * kC + lane * 4) : (const void*)a.res, ok ? 16u : 0u);
+          }
         }
         cp_async_arrive_noinc(r_ready);
       }
@@ -191,33 +252,37 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
   } else {
     // =================================== epilogue: 2 warpgroups ===================================
     const int q4 = warp & 3, h = warp >> 2;
-    const int r = q4 * 32 + lane;  // row of the tile == TMEM lane
     const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
     uint8_t* stage = smem + kChStage + warp * 4096;          // PCQ / KV: [32 rows][128 B], 16-byte chunks XOR-swizzled by row
     uint8_t* resq = smem + kChRes + q4 * 32 * 512;           // MSG: the 32 residual rows of this lane quarter
     const int sub = lane >> 3, piece = lane & 7;             // read-out phase: rows sub + 4 i, 16-byte piece of the row
+    const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    uint32_t a1_arrivals = 0;
     int it = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int par = it & 1, u = it >> 1;
-      if (tid == 0) PDSC_STAMP(a.dbg, it, 3, 6);
+      if (stamp) PDSC_STAMP1(a.dbg, it, 3, 6);
       const uint32_t dcol = tmem + lane_base + (uint32_t)par * 256u;
       const long long row0 = tile * 128 + q4 * 32;          // first global row of this lane quarter
       const long long grow = row0 + lane;
       const bool live = grow < a.rows;
-      const unsigned un = (unsigned)a.N;   // rows < 2^31 (checked on the host): 32-bit divisions
-      const int my_b = live ? (int)((unsigned)grow / un) : 0;
-      const int my_n = live ? (int)((unsigned)grow - (unsigned)my_b * un) : 0;
+      // (set, index) of the quarter's first row: one division per tile, the 32 rows follow by comparison
+      const int b0 = (int)((unsigned)row0 / (unsigned)a.N);
+      const int n0 = (int)((unsigned)row0 - (unsigned)b0 * (unsigned)a.N);
+      int my_b, my_n;
+      locate_row(b0, n0, lane, a.N, my_b, my_n);
       // image destinations of the 8 rows this lane stores in the read-out phase (PCQ: Q, KV: K)
       uint8_t* img_row[8];
       uint32_t img_rx[8];
       if (MODE == kPCQ || MODE == kKV) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const long long g = row0 + sub + 4 * i;
+          const int rr = sub + 4 * i;
           img_row[i] = nullptr;
           img_rx[i] = 0;
-          if (g < a.rows) {
-            const int bb = (int)((unsigned)g / un), nn = (int)((unsigned)g - (unsigned)bb * un);
+          if (row0 + rr < a.rows) {
+            int bb, nn;
+            locate_row(b0, n0, rr, a.N, bb, nn);
             if (MODE == kPCQ) {
               const uint32_t rit = (uint32_t)(nn & 127);
               img_row[i] = a.qimg + ((size_t)bb * a.QT + (nn >> 7)) * 65536 + (rit >> 3) * 1024u + (rit & 7u) * 128u;
@@ -231,24 +296,25 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         }
       }
 
-      if (tid == 0) PDSC_STAMP(a.dbg, it, 3, 7);
+      if (stamp) PDSC_STAMP1(a.dbg, it, 3, 7);
       for (int step = 0; step < kSteps; ++step) {
-        if (tid == 0) PDSC_STAMP(a.dbg, it, 2, step * 2);
+        if (stamp) PDSC_STAMP1(a.dbg, it, 2, step * 2);
         mbar_wait(d_full + 8 * (step * 2 + par), (uint32_t)(u & 1));
-        if (tid == 0) PDSC_STAMP(a.dbg, it, 2, step * 2 + 1);
+        if (stamp) PDSC_STAMP1(a.dbg, it, 2, step * 2 + 1);
         tc_fence_after();
         if (MODE == kMSG && step == 2) mbar_wait(r_ready, (uint32_t)(it & 1));
         const int ncols = (MODE == kMSG && step < 2) ? 64 : 128;
         const uint32_t dstep = (MODE == kMSG) ? (step == 0 ? 0u : (step == 1 ? 64u : 128u)) : (uint32_t)step * 128u;
         const float* bvec = bias + ((MODE == kMSG) ? (step == 0 ? 0 : (step == 1 ? 64 : 128)) : step * 128);
         const int cbeg = h * (ncols / 2), cend = cbeg + ncols / 2;
+        const bool chained = (MODE == kPCQ && step == 0) || (MODE == kMSG && step < 2);   // feeds the next MMA
         for (int c0 = cbeg; c0 < cend; c0 += 32) {
-          const bool st1 = (tid == 0 && step == 1 && c0 == cbeg);
-          if (st1) PDSC_STAMP(a.dbg, it, 3, 0);
+          const bool st1 = stamp && step == 1 && c0 == cbeg;
+          if (st1) PDSC_STAMP1(a.dbg, it, 3, 0);
           uint32_t raw[32];
           tmem_ld32(dcol + dstep + c0, raw);
           tmem_ld_wait();
-          if (st1) PDSC_STAMP(a.dbg, it, 3, 1);
+          if (st1) PDSC_STAMP1(a.dbg, it, 3, 1);
           float x[32];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
@@ -258,9 +324,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
             x[i + 2] = __uint_as_float(raw[i + 2]) + bv.z;
             x[i + 3] = __uint_as_float(raw[i + 3]) + bv.w;
           }
-          if ((MODE == kPCQ && step == 0) || (MODE == kMSG && step < 2)) {
+          if (chained) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
+            // next step's A operand, in place over the columns just read: [hi 16 | lo 16]
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split_pair<FMT>(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
+            tmem_st16(dcol + dstep + c0, hi);
+            if (a.split) tmem_st16(dcol + dstep + c0 + 16, lo);
           }
 
           if (MODE == kMSG && step == 2) {
@@ -290,21 +362,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
               if (g < a.rows) *reinterpret_cast<float4*>(a.out_f32 + g * kC + c0 + piece * 4) = val;
             }
           }
-          if ((MODE == kPCQ && step == 0) || (MODE == kMSG && step < 2)) {
-            // next step's A operand: 16-bit hi/lo image in smem
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 hi, lo;
-              split8<FMT>(x + g * 8, hi, lo);
-              const uint32_t kk = (uint32_t)(c0 + g * 8);
-              const uint32_t off = (kk >> 6) * 16384u + sw128_offset((uint32_t)r, kk & 63u);
-              *reinterpret_cast<uint4*>(Abuf + off) = hi;
-              if (a.split) *reinterpret_cast<uint4*>(Abuf + 32768 + off) = lo;
-            }
-          }
           if ((MODE == kPCQ && step == 1) || (MODE == kKV && step == 0)) {
             // Q / K image -> HBM: stage [hi 64 B | lo 64 B] per row, then 16-byte pieces to their swizzled homes
-            if (st1) PDSC_STAMP(a.dbg, it, 3, 2);
+            if (st1) PDSC_STAMP1(a.dbg, it, 3, 2);
             __syncwarp();
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -314,7 +374,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
               *reinterpret_cast<uint4*>(stage + lane * 128 + (((4 + g) ^ (lane & 7)) << 4)) = lo;
             }
             __syncwarp();
-            if (st1) PDSC_STAMP(a.dbg, it, 3, 3);
+            if (st1) PDSC_STAMP1(a.dbg, it, 3, 3);
             const bool is_lo = piece >= 4;
             const uint32_t kk = (uint32_t)(c0 + (piece & 3) * 8);
             const uint32_t panel_bytes = (MODE == kPCQ) ? 16384u : 8192u;
@@ -329,7 +389,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
                                             (is_lo ? lo_off : 0u)) = val;
               }
             }
-            if (st1) PDSC_STAMP(a.dbg, it, 3, 4);
+            if (st1) PDSC_STAMP1(a.dbg, it, 3, 4);
           }
           if (MODE == kKV && step == 1 && live) {
             // V^T image: row = channel, column = key; a warp writes 32 consecutive keys of one channel row
@@ -343,10 +403,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
             }
           }
         }
-        if ((MODE == kPCQ && step == 0) || (MODE == kMSG && step < 2)) {
-          fence_proxy_async_smem();  // A image written through the generic proxy, read by the tensor core
+        if (chained) {
+          tmem_st_wait();        // A operand written through tcgen05.st, read by the tensor core
           tc_fence_before();
           mbar_arrive(a1_ready);
+          ++a1_arrivals;
         }
       }
       if (MODE == kMSG) {
@@ -361,14 +422,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         }
         mbar_arrive(r_free);
       }
-      if (tid == 0) PDSC_STAMP(a.dbg, it, 2, 6);
+      if (stamp) PDSC_STAMP1(a.dbg, it, 2, 6);
       tc_fence_before();
       mbar_arrive(d_free + 8 * par);  // D[par] drained
     }
+    (void)a1_arrivals;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) tmem_dealloc(tmem, 512);
+  if (warp == 15) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace pdsc
