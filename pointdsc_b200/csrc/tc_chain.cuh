@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
       if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 0);
       mbar_wait(a_ready, (uint32_t)(it & 1));
       if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 1);
-      if (it >= 2) mbar_wait(d_free + 8 * par, (uint32_t)((u - 1) & 1));  // epilogue drained D[par]
+      // PCQ: D0[par] is known drained (the a1_ready wait of tile t-2 covered it); D1[par] is checked before step 1
+      if (MODE != kPCQ && it >= 2) mbar_wait(d_free + 8 * par, (uint32_t)((u - 1) & 1));  // epilogue drained D[par]
       if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 2);
       tc_fence_after();
       if (MODE == kPCQ) {
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 3);
         mbar_wait(a1_ready, a1_uses & 1);
         ++a1_uses;
+        if (it >= 2) mbar_wait(d_free + 8 * par, (uint32_t)((u - 1) & 1));  // E1(t-2) drained D1[par]
         tc_fence_after();
         if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 4);
         if (leader) {
@@ -257,9 +259,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
     uint8_t* resq = smem + kChRes + q4 * 32 * 512;           // MSG: the 32 residual rows of this lane quarter
     const int sub = lane >> 3, piece = lane & 7;             // read-out phase: rows sub + 4 i, 16-byte piece of the row
     const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-    uint32_t a1_arrivals = 0;
-    int it = 0;
-    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    // one epilogue step of one tile (all per-tile addressing is derived here, so steps of different tiles can interleave)
+    auto run_step = [&](const long long tile, const int it, const int step) {
       const int par = it & 1, u = it >> 1;
       if (stamp) PDSC_STAMP1(a.dbg, it, 3, 6);
       const uint32_t dcol = tmem + lane_base + (uint32_t)par * 256u;
@@ -297,7 +298,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
       }
 
       if (stamp) PDSC_STAMP1(a.dbg, it, 3, 7);
-      for (int step = 0; step < kSteps; ++step) {
         if (stamp) PDSC_STAMP1(a.dbg, it, 2, step * 2);
         mbar_wait(d_full + 8 * (step * 2 + par), (uint32_t)(u & 1));
         if (stamp) PDSC_STAMP1(a.dbg, it, 2, step * 2 + 1);
@@ -308,6 +308,49 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         const float* bvec = bias + ((MODE == kMSG) ? (step == 0 ? 0 : (step == 1 ? 64 : 128)) : step * 128);
         const int cbeg = h * (ncols / 2), cend = cbeg + ncols / 2;
         const bool chained = (MODE == kPCQ && step == 0) || (MODE == kMSG && step < 2);   // feeds the next MMA
+        if ((MODE == kPCQ && step == 1) || (MODE == kKV && step == 0)) {
+          // Q / K image -> HBM.  This thread's 64 columns are exactly one 128-byte panel row (hi) and one (lo): stage
+          // the warp's 32 rows x 128 B, then every store instruction writes four full 128-byte lines.
+          if (stamp && step == 1) PDSC_STAMP1(a.dbg, it, 3, 0);
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            uint32_t raw[32];
+            tmem_ld32(dcol + dstep + cbeg + 32 * cc, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(bvec + cbeg + 32 * cc + i);
+              split_pair<FMT>(__uint_as_float(raw[i]) + bv.x, __uint_as_float(raw[i + 1]) + bv.y, hi[16 * cc + (i >> 1)],
+                              lo[16 * cc + (i >> 1)]);
+              split_pair<FMT>(__uint_as_float(raw[i + 2]) + bv.z, __uint_as_float(raw[i + 3]) + bv.w,
+                              hi[16 * cc + (i >> 1) + 1], lo[16 * cc + (i >> 1) + 1]);
+            }
+          }
+          if (stamp && step == 1) PDSC_STAMP1(a.dbg, it, 3, 1);
+          const uint32_t panel_off = (uint32_t)h * ((MODE == kPCQ) ? 16384u : 8192u);
+          const uint32_t lo_off = (MODE == kPCQ) ? 32768u : 16384u;
+#pragma unroll
+          for (int part = 0; part < 2; ++part) {
+            if (part == 1 && !a.split) break;
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const uint32_t* src = part ? lo : hi;
+              *reinterpret_cast<uint4*>(stage + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+                  make_uint4(src[4 * g], src[4 * g + 1], src[4 * g + 2], src[4 * g + 3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = sub + 4 * i;
+              const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((piece ^ (rr & 7)) << 4));
+              if (img_row[i])
+                *reinterpret_cast<uint4*>(img_row[i] + panel_off + (((uint32_t)piece ^ img_rx[i]) << 4) + (part ? lo_off : 0u)) = val;
+            }
+          }
+          if (stamp && step == 1) PDSC_STAMP1(a.dbg, it, 3, 4);
+        } else
         for (int c0 = cbeg; c0 < cend; c0 += 32) {
           const bool st1 = stamp && step == 1 && c0 == cbeg;
           if (st1) PDSC_STAMP1(a.dbg, it, 3, 0);
@@ -362,35 +405,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
               if (g < a.rows) *reinterpret_cast<float4*>(a.out_f32 + g * kC + c0 + piece * 4) = val;
             }
           }
-          if ((MODE == kPCQ && step == 1) || (MODE == kKV && step == 0)) {
-            // Q / K image -> HBM: stage [hi 64 B | lo 64 B] per row, then 16-byte pieces to their swizzled homes
-            if (st1) PDSC_STAMP1(a.dbg, it, 3, 2);
-            __syncwarp();
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint4 hi, lo;
-              split8<FMT>(x + g * 8, hi, lo);
-              *reinterpret_cast<uint4*>(stage + lane * 128 + ((g ^ (lane & 7)) << 4)) = hi;
-              *reinterpret_cast<uint4*>(stage + lane * 128 + (((4 + g) ^ (lane & 7)) << 4)) = lo;
-            }
-            __syncwarp();
-            if (st1) PDSC_STAMP1(a.dbg, it, 3, 3);
-            const bool is_lo = piece >= 4;
-            const uint32_t kk = (uint32_t)(c0 + (piece & 3) * 8);
-            const uint32_t panel_bytes = (MODE == kPCQ) ? 16384u : 8192u;
-            const uint32_t lo_off = (MODE == kPCQ) ? 32768u : 16384u;
-            if (!is_lo || a.split) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int rr = sub + 4 * i;
-                const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((piece ^ (rr & 7)) << 4));
-                if (img_row[i])
-                  *reinterpret_cast<uint4*>(img_row[i] + (kk >> 6) * panel_bytes + ((((kk & 63u) >> 3) ^ img_rx[i]) << 4) +
-                                            (is_lo ? lo_off : 0u)) = val;
-              }
-            }
-            if (st1) PDSC_STAMP1(a.dbg, it, 3, 4);
-          }
           if (MODE == kKV && step == 1 && live) {
             // V^T image: row = channel, column = key; a warp writes 32 consecutive keys of one channel row
             uint8_t* base = a.kvimg + ((size_t)my_b * a.KT + (my_n >> 6)) * 65536 + 32768;
@@ -407,26 +421,51 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           tmem_st_wait();        // A operand written through tcgen05.st, read by the tensor core
           tc_fence_before();
           mbar_arrive(a1_ready);
-          ++a1_arrivals;
         }
+      
+    };
+    if (MODE == kPCQ) {
+      // Software-pipelined order  E0(t), E1(t-1), E0(t+1), E1(t), ...: the step-1 MMA of tile t (which needs E0(t)'s
+      // output) runs under E1(t-1), so the epilogue warps never sit waiting for the tensor core.
+      long long prev = -1;
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        run_step(tile, it, 0);
+        if (it > 0) {
+          run_step(prev, it - 1, 1);
+          tc_fence_before();
+          mbar_arrive(d_free + 8 * ((it - 1) & 1));   // D1[par] drained
+        }
+        prev = tile;
       }
-      if (MODE == kMSG) {
-        // store the finished fp32 tile: one full 512-byte row per instruction, 16 rows per warp
-        quarter_sync(q4);  // both column halves of these 32 rows are in place
+      if (it > 0) {
+        run_step(prev, it - 1, 1);
+        tc_fence_before();
+        mbar_arrive(d_free + 8 * ((it - 1) & 1));
+      }
+    } else {
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int par = it & 1;
+        const long long row0 = tile * 128 + q4 * 32;
+#pragma unroll
+        for (int step = 0; step < kSteps; ++step) run_step(tile, it, step);
+        if (MODE == kMSG) {
+          // store the finished fp32 tile: one full 512-byte row per instruction, 16 rows per warp
+          quarter_sync(q4);  // both column halves of these 32 rows are in place
 #pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int rr = 16 * h + i;
-          const long long g = row0 + rr;
-          const float4 val = *reinterpret_cast<const float4*>(resq + rr * 512 + (((lane & ~7) | ((lane ^ rr) & 7)) << 4));
-          if (g < a.rows) *reinterpret_cast<float4*>(a.out_f32 + g * kC + lane * 4) = val;
+          for (int i = 0; i < 16; ++i) {
+            const int rr = 16 * h + i;
+            const long long g = row0 + rr;
+            const float4 val = *reinterpret_cast<const float4*>(resq + rr * 512 + (((lane & ~7) | ((lane ^ rr) & 7)) << 4));
+            if (g < a.rows) *reinterpret_cast<float4*>(a.out_f32 + g * kC + lane * 4) = val;
+          }
+          mbar_arrive(r_free);
         }
-        mbar_arrive(r_free);
+        tc_fence_before();
+        mbar_arrive(d_free + 8 * par);  // D[par] drained
       }
-      if (stamp) PDSC_STAMP1(a.dbg, it, 2, 6);
-      tc_fence_before();
-      mbar_arrive(d_free + 8 * par);  // D[par] drained
     }
-    (void)a1_arrivals;
   }
   tc_fence_before();
   __syncthreads();
