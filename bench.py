@@ -63,14 +63,16 @@ def load_snapshot(dataset):
     return {k: torch.from_numpy(z[k]) for k in z.files}
 
 
-def make_inputs(args, rank):
-    from pointdsc_b200.synth import make_batch
-    ratios = [0.5, 0.3, 0.2, 0.4]
+def make_inputs(args, rank, world=1):
+    """This rank's shard of the global batch (B sets per GPU, weak scaling): global set g has seed g and an inlier
+    ratio cycling through 0.5 / 0.3 / 0.2 / 0.4, so any sharding of the same global batch sees the same sets."""
     import torch
-    per = (args.batch + 3) // 4
-    parts = [make_batch(range(rank * 100000 + i * per, rank * 100000 + (i + 1) * per), args.n, args.dataset, r)
-             for i, r in enumerate(ratios)]
-    return {k: torch.cat([p[k] for p in parts], 0)[:args.batch].contiguous() for k in parts[0]}
+    from pointdsc_b200.shard import shard_bounds
+    from pointdsc_b200.synth import make_pair
+    ratios = [0.5, 0.3, 0.2, 0.4]
+    lo, hi = shard_bounds(args.batch * world, rank, world)
+    pairs = [make_pair(g, args.n, args.dataset, ratios[g % 4]) for g in range(lo, hi)]
+    return {k: torch.stack([p[k] for p in pairs], 0).contiguous() for k in pairs[0]}
 
 
 class ClockSampler:
@@ -117,6 +119,30 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def pick_cpu_threads(args, sets):
+    """torch's CPU ops on small tensors slow down badly when oversubscribed (128 threads: 26 s per N=1000 forward,
+    8 threads: 0.17 s), so "all the host threads it can use" is found by timing one forward per candidate count
+    (bounded: a candidate that takes > 4x the best so far ends the search) and keeping the fastest."""
+    import torch
+    from oracle import pointdsc_oracle as O
+    sd = load_snapshot(args.dataset)
+    cfg = O.default_config(args.dataset)
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
+    best, best_t = cands[0], None
+    for c in cands:
+        torch.set_num_threads(c)
+        O.forward_testing(sd, cfg, sets["corr_pos"][0], sets["src_keypts"][0], sets["tgt_keypts"][0])  # warm this pool size
+        t0 = time.perf_counter()
+        O.forward_testing(sd, cfg, sets["corr_pos"][0], sets["src_keypts"][0], sets["tgt_keypts"][0])
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+        elif dt > 4 * best_t:
+            break
+    return best
+
+
 def cpu_oracle_rate(args, sets, budget_s, threads):
     """sets/s of the CPU oracle on a bounded sample of the same workload."""
     import torch
@@ -140,11 +166,16 @@ def run_reference(args, rank, world):
         return
     import torch
     from oracle import pointdsc_oracle as O
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
     sd = load_snapshot(args.dataset)
     cfg = O.default_config(args.dataset)
-    per_step = 2
+    probe = make_inputs(argparse.Namespace(**{**vars(args), "batch": 4}), 0)
+    threads = pick_cpu_threads(args, probe)
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    O.forward_testing(sd, cfg, probe["corr_pos"][1], probe["src_keypts"][1], probe["tgt_keypts"][1])
+    one = max(time.perf_counter() - t0, 1e-3)
+    # a step = a bounded sample of the batch, sized so that steps + warmup stay within ~2 minutes
+    per_step = int(max(1, min(args.batch, 120.0 / (one * (args.steps + args.warmup)))))
     need = per_step * (args.steps + args.warmup)
     small = argparse.Namespace(**{**vars(args), "batch": min(args.batch, need)})
     sets = make_inputs(small, 0)
@@ -161,7 +192,8 @@ def run_reference(args, rank, world):
         step(args.warmup + i)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    sample = f"{per_step} sets per step (loop of bs=1 testing forwards) x {args.steps} steps of the N={args.n} workload"
+    sample = (f"{per_step} sets per step (loop of bs=1 testing forwards) x {args.steps} steps of the N={args.n} workload, "
+              f"{threads} host threads (fastest of the candidate counts on {os.cpu_count()} cores)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -186,7 +218,7 @@ def run_engine(args, rank, world, local_rank):
     res = model.load_state_dict(load_snapshot(args.dataset), strict=False)
     assert res.missing_keys == [], res
     model = model.to(dev).eval()
-    host = make_inputs(args, rank)
+    host = make_inputs(args, rank, world)
     pinned = {k: host[k].pin_memory() for k in ("corr_pos", "src_keypts", "tgt_keypts")}
     d = {k: host[k].to(dev) for k in ("corr_pos", "src_keypts", "tgt_keypts")}
     B, N = args.batch, args.n
@@ -196,12 +228,11 @@ def run_engine(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from pointdsc_b200.shard import gather_counters, output_checksum
+    from pointdsc_b200.shard import max_over_ranks as _max_over_ranks
+
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0])
+        return _max_over_ranks(x, dev)
 
     # ---- device-resident throughput ----------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -243,8 +274,12 @@ def run_engine(args, rank, world, local_rank):
     h2d = sum(pinned[k].numel() * 4 for k in pinned)
     d2h = ho["final_trans"].numel() * 4 + ho["final_labels"].numel() * 4
 
+    counters = output_checksum(out["final_trans"].cpu(), out["final_labels"].cpu())
+    counters["registered"] = registered
+    per_rank = gather_counters(counters)     # NCCL is used for timing / counters only: there is no data-path collective
     if rank != 0:
         return
+    registered = sum(c["registered"] * c["sets"] for c in per_rank) / max(1.0, sum(c["sets"] for c in per_rank))
     # ---- roofline of the dominant kernel --------------------------------------------------------------------
     peaks = {}
     try:
@@ -276,11 +311,11 @@ def run_engine(args, rank, world, local_rank):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = pick_cpu_threads(args, host)
         rate, done, dt = cpu_oracle_rate(args, host, args.cpu_seconds, threads)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"first {done} sets of the step's batch, loop of bs=1 testing forwards, {dt:.1f} s on {threads} host threads "
-                         f"(torch {torch.__version__} CPU fp32)"}
+                         f"(fastest of the candidate thread counts on {os.cpu_count()} cores; torch {torch.__version__} CPU fp32)"}
     launches = model.launches_per_forward(B, N) * args.steps
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -290,7 +325,8 @@ def run_engine(args, rank, world, local_rank):
         "data": "synthetic", "config": config_of(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "stages": stages,
-        "registered_fraction": registered}))
+        "registered_fraction": registered,
+        "rank_checksums": [{k: c[k] for k in ("sets", "trans_abs", "inliers")} for c in per_rank]}))
     if world > 1:
         dist.destroy_process_group()
 
