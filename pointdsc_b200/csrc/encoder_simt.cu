@@ -82,21 +82,56 @@ void launch_linear_simt(const LinearArgs& a, cudaStream_t st) {
   linear_simt_kernel<<<grid, 256, 0, st>>>(a);
 }
 
-// layer0: Conv1d(in_dim -> 128), in_dim = 6 (PointDSC.py:54, :73)
-__global__ void layer0_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
-                              float* __restrict__ out, long long rows, int in_dim) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long r = idx / kC;
-  const int o = (int)(idx % kC);
-  if (r >= rows) return;
-  float acc = 0.f;
-  for (int c = 0; c < in_dim; ++c) acc = fmaf(x[r * in_dim + c], W[o * in_dim + c], acc);
-  out[r * kC + o] = acc + bias[o];
+// layer0: Conv1d(in_dim -> 128), in_dim = 6 (PointDSC.py:54, :73).  HBM-write bound (512 B per row out, 24 B in): one
+// warp per row per pass, lane = four output channels (weights and bias live in registers across the grid-stride loop),
+// one 16-byte store per lane so every warp store is a full 512-byte row.  FMA order: ascending input channel, bias last.
+constexpr int kL0MaxIn = 8;
+__global__ void __launch_bounds__(256) layer0_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                     const float* __restrict__ bias, float* __restrict__ out,
+                                                     long long rows, int in_dim) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * 8;
+  if (in_dim <= kL0MaxIn) {
+    float w[4][kL0MaxIn];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int c = 0; c < kL0MaxIn; ++c) w[o][c] = (c < in_dim) ? W[(lane * 4 + o) * in_dim + c] : 0.f;
+    const float4 bv = *reinterpret_cast<const float4*>(bias + lane * 4);
+    for (long long r = warp; r < rows; r += nwarps) {
+      float xin[kL0MaxIn];
+#pragma unroll
+      for (int c = 0; c < kL0MaxIn; ++c) xin[c] = (c < in_dim) ? __ldg(x + r * in_dim + c) : 0.f;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < kL0MaxIn; ++c) {
+        if (c < in_dim) {
+#pragma unroll
+          for (int o = 0; o < 4; ++o) acc[o] = fmaf(xin[c], w[o][c], acc[o]);
+        }
+      }
+      *reinterpret_cast<float4*>(out + r * kC + lane * 4) = make_float4(acc[0] + bv.x, acc[1] + bv.y, acc[2] + bv.z, acc[3] + bv.w);
+    }
+  } else {
+    for (long long r = warp; r < rows; r += nwarps) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int c = 0; c < in_dim; ++c) {
+        const float xv = __ldg(x + r * in_dim + c);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o] = fmaf(xv, W[(lane * 4 + o) * in_dim + c], acc[o]);
+      }
+#pragma unroll
+      for (int o = 0; o < 4; ++o) out[r * kC + lane * 4 + o] = acc[o] + bias[lane * 4 + o];
+    }
+  }
 }
 void launch_layer0(const float* corr_pos, const float* W, const float* bias, float* out, long long rows, int in_dim,
                    cudaStream_t st) {
-  const long long total = rows * kC;
-  layer0_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(corr_pos, W, bias, out, rows, in_dim);
+  long long blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  layer0_kernel<<<(unsigned)blocks, 256, 0, st>>>(corr_pos, W, bias, out, rows, in_dim);
 }
 
 // -------------------------------------------------------------------------------------------------

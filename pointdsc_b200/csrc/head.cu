@@ -9,48 +9,121 @@
 
 namespace pdsc {
 
-__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ feat, HeadWeights w,
-                                                   float* __restrict__ normed, float* __restrict__ conf,
-                                                   long long rows, int want_conf) {
-  __shared__ float w0t[kC * 32];   // [c][o]
-  __shared__ float w2t[32 * 32];   // [c][o]
-  __shared__ float frow[8][kC];
+// Lane = one correspondence (row), 32 rows per warp pass.  The warp stages its 32 rows transposed in shared memory
+// ([channel][row], stride 33: conflict-free both ways); every lane then runs the whole MLP of its own row with the 32
+// hidden accumulators in registers while the weights arrive as warp-wide BROADCAST 16-byte loads — 32 FMAs per 8 weight
+// loads + 1 activation load, instead of 1 FMA per 2 loads in a channel-per-lane scheme.  Accumulation order is the
+// reference's: bias first, then ascending input channel, one fp32 FMA each.
+constexpr int kHeadWarps = 4;
+constexpr int kHeadStride = 33;
+
+__global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(const float* __restrict__ feat, HeadWeights w,
+                                                                float* __restrict__ normed, float* __restrict__ conf,
+                                                                long long rows, int want_conf) {
+  extern __shared__ __align__(16) float hsm[];
+  float* w0t = hsm;                    // [c][o]  128 x 32
+  float* w2t = w0t + kC * 32;          // [c][o]   32 x 32
+  float* b0s = w2t + 32 * 32;
+  float* b2s = b0s + 32;
+  float* w4s = b2s + 32;
+  float* tiles = w4s + 32;             // [warp][kC * kHeadStride]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (want_conf) {
-    for (int i = tid; i < kC * 32; i += 256) w0t[i] = w.w0t[i];
-    for (int i = tid; i < 32 * 32; i += 256) w2t[i] = w.w2t[i];
+    for (int i = tid; i < kC * 32; i += kHeadWarps * 32) w0t[i] = w.w0t[i];
+    for (int i = tid; i < 32 * 32; i += kHeadWarps * 32) w2t[i] = w.w2t[i];
+    if (tid < 32) { b0s[tid] = w.b0[tid]; b2s[tid] = w.b2[tid]; w4s[tid] = w.w4[tid]; }
   }
   __syncthreads();
-  const float b0 = want_conf ? w.b0[lane] : 0.f, b2 = want_conf ? w.b2[lane] : 0.f;
-  const float w4 = want_conf ? w.w4[lane] : 0.f, b4 = want_conf ? w.b4[0] : 0.f;
-  for (long long r = (long long)blockIdx.x * 8 + warp; r < rows; r += (long long)gridDim.x * 8) {
-    const float4 f = *reinterpret_cast<const float4*>(feat + r * kC + lane * 4);
-    const float ss = warp_sum(f.x * f.x + f.y * f.y + f.z * f.z + f.w * f.w);
-    const float den = fmaxf(sqrtf(ss), 1e-12f);
-    *reinterpret_cast<float4*>(normed + r * kC + lane * 4) = make_float4(f.x / den, f.y / den, f.z / den, f.w / den);
-    if (!want_conf) continue;
+  const float b4 = want_conf ? w.b4[0] : 0.f;
+  float* T = tiles + (size_t)warp * kC * kHeadStride;
+  const long long ntiles = (rows + 31) / 32;
+  for (long long t = (long long)blockIdx.x * kHeadWarps + warp; t < ntiles; t += (long long)gridDim.x * kHeadWarps) {
+    const long long r0 = t * 32;
+    // stage: row i, channels 4 lane .. 4 lane + 3  ->  T[c][i]
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + i < rows) f = *reinterpret_cast<const float4*>(feat + (r0 + i) * kC + lane * 4);
+      T[(lane * 4 + 0) * kHeadStride + i] = f.x;
+      T[(lane * 4 + 1) * kHeadStride + i] = f.y;
+      T[(lane * 4 + 2) * kHeadStride + i] = f.z;
+      T[(lane * 4 + 3) * kHeadStride + i] = f.w;
+    }
     __syncwarp();
-    *reinterpret_cast<float4*>(&frow[warp][lane * 4]) = f;
-    __syncwarp();
-    float h1 = b0;
-#pragma unroll 8
-    for (int c = 0; c < kC; ++c) h1 = fmaf(frow[warp][c], w0t[c * 32 + lane], h1);
-    h1 = fmaxf(h1, 0.f);
-    float h2 = b2;
+    // this lane's row: squared norm (+ hidden layer 1 when the confidence is wanted)
+    float ss = 0.f;
+    float h1[32];
+    if (want_conf) {
 #pragma unroll
-    for (int c = 0; c < 32; ++c) h2 = fmaf(__shfl_sync(0xffffffffu, h1, c), w2t[c * 32 + lane], h2);
-    h2 = fmaxf(h2, 0.f);
-    const float o = warp_sum(h2 * w4);
-    if (lane == 0) conf[r] = o + b4;
+      for (int o = 0; o < 32; ++o) h1[o] = b0s[o];
+#pragma unroll 2
+      for (int c = 0; c < kC; ++c) {
+        const float f = T[c * kHeadStride + lane];
+        ss = fmaf(f, f, ss);
+#pragma unroll
+        for (int o4 = 0; o4 < 8; ++o4) {
+          const float4 wv = *reinterpret_cast<const float4*>(w0t + c * 32 + o4 * 4);
+          h1[o4 * 4 + 0] = fmaf(f, wv.x, h1[o4 * 4 + 0]);
+          h1[o4 * 4 + 1] = fmaf(f, wv.y, h1[o4 * 4 + 1]);
+          h1[o4 * 4 + 2] = fmaf(f, wv.z, h1[o4 * 4 + 2]);
+          h1[o4 * 4 + 3] = fmaf(f, wv.w, h1[o4 * 4 + 3]);
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int c = 0; c < kC; ++c) {
+        const float f = T[c * kHeadStride + lane];
+        ss = fmaf(f, f, ss);
+      }
+    }
+    const float den = fmaxf(sqrtf(ss), 1e-12f);   // F.normalize: x / max(||x||, eps)
+    if (want_conf) {
+      float h2[32];
+#pragma unroll
+      for (int o = 0; o < 32; ++o) h2[o] = b2s[o];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float a = fmaxf(h1[c], 0.f);
+#pragma unroll
+        for (int o4 = 0; o4 < 8; ++o4) {
+          const float4 wv = *reinterpret_cast<const float4*>(w2t + c * 32 + o4 * 4);
+          h2[o4 * 4 + 0] = fmaf(a, wv.x, h2[o4 * 4 + 0]);
+          h2[o4 * 4 + 1] = fmaf(a, wv.y, h2[o4 * 4 + 1]);
+          h2[o4 * 4 + 2] = fmaf(a, wv.z, h2[o4 * 4 + 2]);
+          h2[o4 * 4 + 3] = fmaf(a, wv.w, h2[o4 * 4 + 3]);
+        }
+      }
+      float o = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) o = fmaf(fmaxf(h2[c], 0.f), w4s[c], o);
+      if (r0 + lane < rows) conf[r0 + lane] = o + b4;
+    }
+    // normalised rows out, one full 512-byte row per store instruction
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+      const float d = __shfl_sync(0xffffffffu, den, i);
+      if (r0 + i < rows) {
+        const float4 f = make_float4(T[(lane * 4 + 0) * kHeadStride + i] / d, T[(lane * 4 + 1) * kHeadStride + i] / d,
+                                     T[(lane * 4 + 2) * kHeadStride + i] / d, T[(lane * 4 + 3) * kHeadStride + i] / d);
+        *reinterpret_cast<float4*>(normed + (r0 + i) * kC + lane * 4) = f;
+      }
+    }
+    __syncwarp();
   }
 }
 
 void launch_head(const float* feat, const HeadWeights& w, float* normed, float* conf, long long rows, int want_conf,
                  cudaStream_t st) {
-  long long blocks = (rows + 7) / 8;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  long long blocks = ((rows + 31) / 32 + kHeadWarps - 1) / kHeadWarps;
+  if (blocks > 148 * 2) blocks = 148 * 2;
   if (blocks < 1) blocks = 1;
-  head_kernel<<<(unsigned)blocks, 256, 0, st>>>(feat, w, normed, conf, rows, want_conf);
+  constexpr int kSmem = (kC * 32 + 32 * 32 + 96 + kHeadWarps * kC * kHeadStride) * (int)sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    configured = true;
+  }
+  head_kernel<<<(unsigned)blocks, kHeadWarps * 32, kSmem, st>>>(feat, w, normed, conf, rows, want_conf);
 }
 
 }  // namespace pdsc

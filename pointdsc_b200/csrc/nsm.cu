@@ -143,21 +143,29 @@ void launch_knn_select(const float* dist, int32_t* knn_idx, int B, int N, int S,
   knn_select_kernel<<<rows, 128, smem, st>>>(dist, knn_idx, N, S, k);
 }
 
-// ---- compatibility matrix + power iteration, one CTA per seed ----------------------------------------
-// Gathered features live TRANSPOSED in shared memory (Ft[channel][neighbour], neighbour stride kp = k rounded
-// up to 4) so a 4 x 4 block of Gram entries costs two LDS.128 per channel (16 FMA per 2 loads); only blocks on
-// or above the diagonal are computed.  Channels are accumulated in ascending order, one fp32 FMA each.
-__global__ void __launch_bounds__(128) nsm_power_kernel(const float* __restrict__ normed, const float* __restrict__ src,
-                                                        const float* __restrict__ tgt,
-                                                        const int32_t* __restrict__ knn_idx,
-                                                        float* __restrict__ iterates, uint32_t* __restrict__ conv_mask,
-                                                        float* __restrict__ compat_out, int N, int S, int k, int iters,
-                                                        float sigma2, float sigmad2) {
+// ---- compatibility matrix + power iteration, one 64-thread CTA per seed -------------------------------
+// The k gathered feature rows stay ROW-major in shared memory (F[a][c], 512 B per row) with the 16-byte chunk index of a
+// row XOR-swizzled by (a >> 2) & 7, so both the gather (one 16-byte store per lane, a full row per warp instruction) and
+// the Gram loop (4 x 4 register blocks: 8 LDS.128 per 64 FMAs, rows of different blocks in different banks) are
+// conflict free.  Only blocks on or above the diagonal are computed (55 of them for k = 40: 86 % of the 64 threads busy).
+// Channels are accumulated in ascending order, one fp32 FMA each.
+constexpr int kNsmThreads = 64;
+
+__device__ __forceinline__ const float4* nsm_chunk(const float* F, int row, int chunk) {
+  return reinterpret_cast<const float4*>(F + (size_t)row * kC + ((chunk ^ ((row >> 2) & 7)) << 2));
+}
+
+__global__ void __launch_bounds__(kNsmThreads) nsm_power_kernel(const float* __restrict__ normed, const float* __restrict__ src,
+                                                                const float* __restrict__ tgt,
+                                                                const int32_t* __restrict__ knn_idx,
+                                                                float* __restrict__ iterates, uint32_t* __restrict__ conv_mask,
+                                                                float* __restrict__ compat_out, int N, int S, int k, int iters,
+                                                                float sigma2, float sigmad2) {
   extern __shared__ __align__(16) float sm[];
   const int ms = k | 1;                  // odd row stride of M: conflict-free row-per-thread reads
   const int kp = (k + 3) & ~3;
-  float* Ft = sm;                        // [kC][kp]
-  float* M = Ft + (size_t)kC * kp;       // [k][ms]
+  float* F = sm;                         // [kp][kC], chunk-swizzled
+  float* M = F + (size_t)kp * kC;        // [k][ms]
   float* pa = M + (size_t)k * ms;        // [k][3]
   float* pb = pa + k * 3;                // [k][3]
   float* v = pb + k * 3;                 // [k]
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(128) nsm_power_kernel(const float* __restrict_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t seed_row = (size_t)b * S + s;
 
-  for (int a = tid; a < kp; a += 128) {
+  for (int a = tid; a < kp; a += kNsmThreads) {
     if (a < k) {
       int j = knn_idx[seed_row * k + a];
       j = min(max(j, 0), N - 1);
@@ -180,13 +188,25 @@ __global__ void __launch_bounds__(128) nsm_power_kernel(const float* __restrict_
       M[a * ms + a] = 0.0f;  // total_knn_M[:, i, i] = 0  (PointDSC.py:278)
     }
   }
+  if (tid < 4) red[tid] = 0.f;
   __syncthreads();
-  for (int a = warp; a < kp; a += 4) {
-    const float* row = normed + ((size_t)b * N + idx[min(a, k - 1)]) * kC;
+  // gather: warp w takes rows w, w+2, ...; all of a warp's loads are issued before the first store
+  {
+    constexpr int kMaxRowsPerWarp = (kMaxK + 3) / 2 / 4 * 4 + 4;
+    (void)kMaxRowsPerWarp;
+    for (int a0 = warp; a0 < kp; a0 += 2 * 8) {
+      float4 buf[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = lane + 32 * i;
-      Ft[(size_t)c * kp + a] = (a < k) ? row[c] : 0.0f;
+      for (int u = 0; u < 8; ++u) {
+        const int a = a0 + 2 * u;
+        buf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a < k) buf[u] = __ldg(reinterpret_cast<const float4*>(normed + ((size_t)b * N + idx[a]) * kC) + lane);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int a = a0 + 2 * u;
+        if (a < kp) *reinterpret_cast<float4*>(F + (size_t)a * kC + ((lane ^ ((a >> 2) & 7)) << 2)) = buf[u];
+      }
     }
   }
   __syncthreads();
@@ -194,7 +214,7 @@ __global__ void __launch_bounds__(128) nsm_power_kernel(const float* __restrict_
   // 4 x 4 blocks (A <= B) of feature-compat * spatial-compat
   const int nb = kp >> 2;
   const int nblk = nb * (nb + 1) / 2;
-  for (int t = tid; t < nblk; t += 128) {
+  for (int t = tid; t < nblk; t += kNsmThreads) {
     int A = 0, rem = t;
     while (rem >= nb - A) { rem -= nb - A; ++A; }
     const int Bk = A + rem;
@@ -203,18 +223,23 @@ __global__ void __launch_bounds__(128) nsm_power_kernel(const float* __restrict_
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    const float* fa = Ft + 4 * A;
-    const float* fb = Ft + 4 * Bk;
-#pragma unroll 4
-    for (int c = 0; c < kC; ++c) {
-      const float4 x = *reinterpret_cast<const float4*>(fa + (size_t)c * kp);
-      const float4 y = *reinterpret_cast<const float4*>(fb + (size_t)c * kp);
-      const float xr[4] = {x.x, x.y, x.z, x.w};
-      const float yr[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll 2
+    for (int cc = 0; cc < kC / 4; ++cc) {
+      float4 x[4], y[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        x[i] = *nsm_chunk(F, 4 * A + i, cc);
+        y[i] = *nsm_chunk(F, 4 * Bk + i, cc);
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xr[i], yr[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] = fmaf(x[i].x, y[j].x, acc[i][j]);
+          acc[i][j] = fmaf(x[i].y, y[j].y, acc[i][j]);
+          acc[i][j] = fmaf(x[i].z, y[j].z, acc[i][j]);
+          acc[i][j] = fmaf(x[i].w, y[j].w, acc[i][j]);
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -234,30 +259,42 @@ __global__ void __launch_bounds__(128) nsm_power_kernel(const float* __restrict_
   __syncthreads();
   if (compat_out) {
     float* dst = compat_out + seed_row * k * k;
-    for (int t = tid; t < k * k; t += 128) dst[t] = M[(t / k) * ms + (t % k)];
+    for (int t = tid; t < k * k; t += kNsmThreads) dst[t] = M[(t / k) * ms + (t % k)];
   }
 
-  // power iteration from the all-ones vector; record every iterate and a convergence bit per iteration
+  // power iteration from the all-ones vector; record every iterate and a convergence bit per iteration.
+  // Thread `a` owns row a (and row a + 64 when k > 64); the squared norm is summed per warp, then warp 0 + warp 1.
   uint32_t mask = 0u;
   float* it_out = iterates + seed_row * (size_t)iters * k;
   for (int t = 0; t < iters; ++t) {
-    float u = 0.f, vold = 0.f;
+    float u0 = 0.f, u1 = 0.f, vold0 = 0.f, vold1 = 0.f;
     if (tid < k) {
       const float* mr = M + tid * ms;
-      for (int c = 0; c < k; ++c) u = fmaf(mr[c], v[c], u);
-      vold = v[tid];
+      for (int c = 0; c < k; ++c) u0 = fmaf(mr[c], v[c], u0);
+      vold0 = v[tid];
     }
-    const float ss = warp_sum(tid < k ? u * u : 0.f);
-    if (lane == 0) red[warp] = ss;
+    if (tid + kNsmThreads < k) {
+      const float* mr = M + (tid + kNsmThreads) * ms;
+      for (int c = 0; c < k; ++c) u1 = fmaf(mr[c], v[c], u1);
+      vold1 = v[tid + kNsmThreads];
+    }
+    const float ssa = warp_sum(tid < k ? u0 * u0 : 0.f);
+    const float ssb = warp_sum(tid + kNsmThreads < k ? u1 * u1 : 0.f);
+    if (lane == 0) { red[warp] = ssa; red[2 + warp] = ssb; }
     __syncthreads();
     const float nrm = sqrtf(red[0] + red[1] + red[2] + red[3]) + 1e-6f;
-    const float vnew = u / nrm;
+    const float vnew0 = u0 / nrm, vnew1 = u1 / nrm;
     // torch.allclose(new, last): |new - last| <= atol + rtol * |last|, atol 1e-8, rtol 1e-5
-    const int ok = (tid >= k) || (fabsf(vnew - vold) <= 1e-8f + 1e-5f * fabsf(vold));
-    const int all_ok = __syncthreads_and(ok);
+    const int ok0 = (tid >= k) || (fabsf(vnew0 - vold0) <= 1e-8f + 1e-5f * fabsf(vold0));
+    const int ok1 = (tid + kNsmThreads >= k) || (fabsf(vnew1 - vold1) <= 1e-8f + 1e-5f * fabsf(vold1));
+    const int all_ok = __syncthreads_and(ok0 && ok1);
     if (tid < k) {
-      v[tid] = vnew;
-      it_out[(size_t)t * k + tid] = vnew;
+      v[tid] = vnew0;
+      it_out[(size_t)t * k + tid] = vnew0;
+    }
+    if (tid + kNsmThreads < k) {
+      v[tid + kNsmThreads] = vnew1;
+      it_out[(size_t)t * k + tid + kNsmThreads] = vnew1;
     }
     if (all_ok) mask |= (1u << t);
     __syncthreads();
@@ -277,8 +314,8 @@ void launch_nsm_power(const float* normed, const float* src, const float* tgt, c
     cudaFuncSetAttribute(nsm_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     configured = 160 * 1024;
   }
-  nsm_power_kernel<<<dim3(S, B), 128, smem, st>>>(normed, src, tgt, knn_idx, iterates, conv_mask, compat_out, N, S, k,
-                                                   iters, sigma * sigma, sigma_d * sigma_d);
+  nsm_power_kernel<<<dim3(S, B), kNsmThreads, smem, st>>>(normed, src, tgt, knn_idx, iterates, conv_mask, compat_out, N, S, k,
+                                                          iters, sigma * sigma, sigma_d * sigma_d);
 }
 
 }  // namespace pdsc

@@ -61,40 +61,68 @@ void launch_sc_matrix(const float* src, const float* tgt, float* sc, int B, int 
 // offsets from one per-tile base pointer, coalesced over the 128 rows, with no per-element address arithmetic.
 // SC is exactly symmetric in fp32 ((x_i - x_j)^2 == (x_j - x_i)^2), so element (key, q) is computed as SC[q][key].
 // Pad rows / columns (key >= N or q >= N) are written as 0.
+// One CTA = one 128 x 128 super-block (A <= Bq) of one set: it evaluates V[i][j] = SC[128 A + i][128 Bq + j] ONCE and
+// writes it in both orientations — keys in A / queries in Bq directly (coalesced over j), and keys in Bq / queries
+// in A through a shared-memory transpose (coalesced over i) — so the 2 IEEE square roots + 1 IEEE division per element
+// that make this kernel issue-bound are paid for only ~(QT+1)/(2 QT) of the matrix.
+constexpr int kScTStride = 129;   // smem transpose tile [32 i][128 j], odd stride: conflict-free both ways
+
 __global__ void __launch_bounds__(256) sc_matrix_tiled_kernel(const float* __restrict__ src, const float* __restrict__ tgt,
                                                               float* __restrict__ sc, int N, int KT, int QT, float s2) {
-  __shared__ float ks[64][3], kt3[64][3];
+  __shared__ float is[128][3], it3[128][3];
+  __shared__ float tr[32 * kScTStride];
   const int b = blockIdx.y;
-  const int kt = blockIdx.x / QT, qt = blockIdx.x % QT;
+  // blockIdx.x enumerates the pairs A <= Bq
+  int A = 0, rem = blockIdx.x;
+  while (rem >= QT - A) { rem -= QT - A; ++A; }
+  const int Bq = A + rem;
   const float* ps = src + (size_t)b * N * 3;
   const float* pt = tgt + (size_t)b * N * 3;
-  if (threadIdx.x < 192) {
-    const int r = threadIdx.x / 3, c = threadIdx.x % 3;
-    const int i = min(kt * 64 + r, N - 1);
-    ks[r][c] = ps[(size_t)i * 3 + c];
-    kt3[r][c] = pt[(size_t)i * 3 + c];
+  for (int t = threadIdx.x; t < 384; t += 256) {
+    const int r = t / 3, c = t % 3;
+    const int i = min(A * 128 + r, N - 1);
+    is[r][c] = ps[(size_t)i * 3 + c];
+    it3[r][c] = pt[(size_t)i * 3 + c];
   }
   __syncthreads();
-  const int ql = threadIdx.x & 127, kh = threadIdx.x >> 7;
-  const int q = qt * 128 + ql;
-  const int qc = min(q, N - 1);
-  const float sx = ps[(size_t)qc * 3], sy = ps[(size_t)qc * 3 + 1], sz = ps[(size_t)qc * 3 + 2];
-  const float tx = pt[(size_t)qc * 3], ty = pt[(size_t)qc * 3 + 1], tz = pt[(size_t)qc * 3 + 2];
-  float* out = sc + ((((size_t)b * KT + kt) * QT + qt) << 13) + (size_t)(kh * 32) * 128 + ql;
+  const int jl = threadIdx.x & 127, half = threadIdx.x >> 7;
+  const int j = Bq * 128 + jl;
+  const int jc = min(j, N - 1);
+  const float sx = ps[(size_t)jc * 3], sy = ps[(size_t)jc * 3 + 1], sz = ps[(size_t)jc * 3 + 2];
+  const float tx = pt[(size_t)jc * 3], ty = pt[(size_t)jc * 3 + 1], tz = pt[(size_t)jc * 3 + 2];
+  const size_t set_base = (size_t)b * KT * QT;
+  const int ti = threadIdx.x & 31, tg = threadIdx.x >> 5;   // transposed write-out: lane = i within the chunk, 16 j per warp
+  for (int ic = 0; ic < 4; ++ic) {             // 32-row chunks of the A range
+    // orientation 1: key = 128 A + i, query = j   ->  tile (kt = 2 A + (i >> 6), qt = Bq), element [(i & 63)][jl]
 #pragma unroll 4
-  for (int c = 0; c < 32; ++c) {
-    const int r = kh * 32 + c;
-    const float ds = length3(ks[r][0] - sx, ks[r][1] - sy, ks[r][2] - sz);
-    const float dt = length3(kt3[r][0] - tx, kt3[r][1] - ty, kt3[r][2] - tz);
-    const float v = consistency(__fsub_rn(ds, dt), s2);
-    out[c * 128] = (q < N && kt * 64 + r < N) ? v : 0.0f;
+    for (int ii = 0; ii < 16; ++ii) {
+      const int il = ic * 32 + half * 16 + ii;           // row within the super-block
+      const int i = A * 128 + il;
+      const float ds = length3(is[il][0] - sx, is[il][1] - sy, is[il][2] - sz);
+      const float dt = length3(it3[il][0] - tx, it3[il][1] - ty, it3[il][2] - tz);
+      const float v = (i < N && j < N) ? consistency(__fsub_rn(ds, dt), s2) : 0.0f;
+      const int kt = 2 * A + (il >> 6);
+      if (kt < KT) sc[((set_base + (size_t)kt * QT + Bq) << 13) + (il & 63) * 128 + jl] = v;
+      tr[(half * 16 + ii) * kScTStride + jl] = v;
+    }
+    if (A != Bq) {
+      __syncthreads();
+      // orientation 2: key = 128 Bq + j, query = 128 A + i  ->  tile (kt = 2 Bq + (j >> 6), qt = A), element [(j & 63)][i]
+#pragma unroll 4
+      for (int jj = 0; jj < 16; ++jj) {
+        const int jl2 = tg * 16 + jj;
+        const int kt = 2 * Bq + (jl2 >> 6);
+        if (kt < KT) sc[((set_base + (size_t)kt * QT + A) << 13) + (jl2 & 63) * 128 + ic * 32 + ti] = tr[ti * kScTStride + jl2];
+      }
+      __syncthreads();
+    }
   }
 }
 
 void launch_sc_matrix_tiled(const float* src, const float* tgt, float* sc, int B, int N, float sigma_d, cudaStream_t st) {
   const float s2 = sigma_d * sigma_d;
   const int KT = (N + 63) / 64, QT = (N + 127) / 128;
-  sc_matrix_tiled_kernel<<<dim3(KT * QT, B), 256, 0, st>>>(src, tgt, sc, N, KT, QT, s2);
+  sc_matrix_tiled_kernel<<<dim3(QT * (QT + 1) / 2, B), 256, 0, st>>>(src, tgt, sc, N, KT, QT, s2);
 }
 
 // tiled -> dense [B][N][N] (stage tap only)
