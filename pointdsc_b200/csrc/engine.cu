@@ -385,8 +385,8 @@ int32_t pdsc_launches_per_forward(const pdsc_engine* e, int32_t B, int32_t N) {
   if (!e) return 0;
   const int L = e->cfg.num_layers;
   const int enc = (e->cfg.precision == PDSC_FP32_SIMT) ? (1 + 8 * L) : pdsc::tc_launches(L);
-  // sc, encoder, head, nms, sort, gather, dist gemm, knn select, 2 fills, nsm, hypotheses, refine
-  return 1 + enc + 1 + 2 + 3 + 2 + 3;
+  // sc, encoder, head, nms, sort, (gather +) dist gemm, knn select, 2 fills, nsm, hypotheses, refine
+  return 1 + enc + 1 + 2 + ((e->cfg.precision == PDSC_FP32_SIMT) ? 3 : 2) + 2 + 3;
 }
 
 int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, const float* d_src, const float* d_tgt,
@@ -486,14 +486,18 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
     if (io && io->in_knn_idx) {
       PDSC_CUDA(cudaMemcpyAsync(w.knn, io->in_knn_idx, (size_t)B * S * k * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     } else {
-      launch_gather_rows(w.normed, w.seeds, w.seedfeat, B, N, S, st);
-      LinearArgs a{};
-      a.A = w.seedfeat; a.strideA = (long long)S * kC; a.lda = kC;
-      a.W = w.normed; a.strideW = (long long)N * kC; a.ldw = kC;
-      a.bias = nullptr; a.res = nullptr; a.ldres = 0;
-      a.out = w.dist; a.strideO = (long long)S * N; a.ldo = N;
-      a.M = S; a.K = kC; a.Nout = N; a.relu = 0; a.epi = 1; a.batch = B;
-      launch_linear_simt(a, st);
+      if (e->cfg.precision == PDSC_FP32_SIMT) {
+        launch_gather_rows(w.normed, w.seeds, w.seedfeat, B, N, S, st);
+        LinearArgs a{};
+        a.A = w.seedfeat; a.strideA = (long long)S * kC; a.lda = kC;
+        a.W = w.normed; a.strideW = (long long)N * kC; a.ldw = kC;
+        a.bias = nullptr; a.res = nullptr; a.ldres = 0;
+        a.out = w.dist; a.strideO = (long long)S * N; a.ldo = N;
+        a.M = S; a.K = kC; a.Nout = N; a.relu = 0; a.epi = 1; a.batch = B;
+        launch_linear_simt(a, st);
+      } else {
+        launch_knn_dist_tc(w.normed, w.seeds, w.dist, B, N, S, st);
+      }
       launch_knn_select(w.dist, w.knn, B, N, S, k, st);
     }
     if (io) copy_tap(io->out_knn_idx, w.knn, (size_t)B * S * k * sizeof(int32_t), st);

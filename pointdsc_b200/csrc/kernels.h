@@ -50,6 +50,8 @@ int pick_seeds_max_n();
 
 // ---- a7: seed-row kNN ----------------------------------------------------------------------------
 void launch_gather_rows(const float* normed, const int32_t* seeds, float* out, int B, int N, int S, cudaStream_t st);
+// tensor-core seed-row distances (knn_tc.cu): dist[b][s][j] = 2 - 2 <normed[b][seeds[b][s]], normed[b][j]>, fp16 hi/lo split
+void launch_knn_dist_tc(const float* normed, const int32_t* seeds, float* dist, int B, int N, int S, cudaStream_t st);
 void launch_knn_select(const float* dist, int32_t* knn_idx, int B, int N, int S, int k, cudaStream_t st);
 
 // ---- a8 + a9: compatibility + power iteration -----------------------------------------------------

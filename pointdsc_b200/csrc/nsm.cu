@@ -268,14 +268,24 @@ __global__ void __launch_bounds__(kNsmThreads) nsm_power_kernel(const float* __r
   float* it_out = iterates + seed_row * (size_t)iters * k;
   for (int t = 0; t < iters; ++t) {
     float u0 = 0.f, u1 = 0.f, vold0 = 0.f, vold1 = 0.f;
+    // M is symmetric: row a is read as column a (M[c][a]), so consecutive threads read consecutive words.  The loads
+    // of eight steps are issued together; the FMAs stay one dependent chain in ascending c (the reference order).
     if (tid < k) {
-      const float* mr = M + tid * ms;
-      for (int c = 0; c < k; ++c) u0 = fmaf(mr[c], v[c], u0);
+      const float* mc = M + tid;
+      int c = 0;
+      for (; c + 8 <= k; c += 8) {
+        float m8[8], v8[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { m8[q] = mc[(c + q) * ms]; v8[q] = v[c + q]; }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) u0 = fmaf(m8[q], v8[q], u0);
+      }
+      for (; c < k; ++c) u0 = fmaf(mc[c * ms], v[c], u0);
       vold0 = v[tid];
     }
     if (tid + kNsmThreads < k) {
-      const float* mr = M + (tid + kNsmThreads) * ms;
-      for (int c = 0; c < k; ++c) u1 = fmaf(mr[c], v[c], u1);
+      const float* mc = M + tid + kNsmThreads;
+      for (int c = 0; c < k; ++c) u1 = fmaf(mc[c * ms], v[c], u1);
       vold1 = v[tid + kNsmThreads];
     }
     const float ssa = warp_sum(tid < k ? u0 * u0 : 0.f);

@@ -69,7 +69,7 @@ constexpr int kScTStride = 129;   // smem transpose tile [32 i][128 j], odd stri
 
 __global__ void __launch_bounds__(256) sc_matrix_tiled_kernel(const float* __restrict__ src, const float* __restrict__ tgt,
                                                               float* __restrict__ sc, int N, int KT, int QT, float s2) {
-  __shared__ float is[128][3], it3[128][3];
+  __shared__ float4 is4[128], it4[128];   // the A range's points (x, y, z, -), read as broadcast 16-byte loads
   __shared__ float tr[32 * kScTStride];
   const int b = blockIdx.y;
   // blockIdx.x enumerates the pairs A <= Bq
@@ -78,11 +78,10 @@ __global__ void __launch_bounds__(256) sc_matrix_tiled_kernel(const float* __res
   const int Bq = A + rem;
   const float* ps = src + (size_t)b * N * 3;
   const float* pt = tgt + (size_t)b * N * 3;
-  for (int t = threadIdx.x; t < 384; t += 256) {
-    const int r = t / 3, c = t % 3;
-    const int i = min(A * 128 + r, N - 1);
-    is[r][c] = ps[(size_t)i * 3 + c];
-    it3[r][c] = pt[(size_t)i * 3 + c];
+  if (threadIdx.x < 128) {
+    const int i = min(A * 128 + (int)threadIdx.x, N - 1);
+    is4[threadIdx.x] = make_float4(ps[(size_t)i * 3], ps[(size_t)i * 3 + 1], ps[(size_t)i * 3 + 2], 0.f);
+    it4[threadIdx.x] = make_float4(pt[(size_t)i * 3], pt[(size_t)i * 3 + 1], pt[(size_t)i * 3 + 2], 0.f);
   }
   __syncthreads();
   const int jl = threadIdx.x & 127, half = threadIdx.x >> 7;
@@ -93,26 +92,37 @@ __global__ void __launch_bounds__(256) sc_matrix_tiled_kernel(const float* __res
   const size_t set_base = (size_t)b * KT * QT;
   const int ti = threadIdx.x & 31, tg = threadIdx.x >> 5;   // transposed write-out: lane = i within the chunk, 16 j per warp
   for (int ic = 0; ic < 4; ++ic) {             // 32-row chunks of the A range
-    // orientation 1: key = 128 A + i, query = j   ->  tile (kt = 2 A + (i >> 6), qt = Bq), element [(i & 63)][jl]
-#pragma unroll 4
+    // orientation 1: key = 128 A + i, query = j   ->  tile (kt = 2 A + (ic >> 1), qt = Bq), element [(i & 63)][jl]
+    const int kt1 = 2 * A + (ic >> 1);
+    const int il0 = ic * 32 + half * 16;
+    float* out1 = sc + ((set_base + (size_t)min(kt1, KT - 1) * QT + Bq) << 13) + (il0 & 63) * 128 + jl;
+    float* trw = tr + (half * 16) * kScTStride + jl;
+    const bool col_ok = j < N;
+    const int i_lim = N - A * 128 - il0;       // rows ii < i_lim are real correspondences
+    float vals[16];
+#pragma unroll
     for (int ii = 0; ii < 16; ++ii) {
-      const int il = ic * 32 + half * 16 + ii;           // row within the super-block
-      const int i = A * 128 + il;
-      const float ds = length3(is[il][0] - sx, is[il][1] - sy, is[il][2] - sz);
-      const float dt = length3(it3[il][0] - tx, it3[il][1] - ty, it3[il][2] - tz);
-      const float v = (i < N && j < N) ? consistency(__fsub_rn(ds, dt), s2) : 0.0f;
-      const int kt = 2 * A + (il >> 6);
-      if (kt < KT) sc[((set_base + (size_t)kt * QT + Bq) << 13) + (il & 63) * 128 + jl] = v;
-      tr[(half * 16 + ii) * kScTStride + jl] = v;
+      const float4 p = is4[il0 + ii], q = it4[il0 + ii];
+      const float ds = length3(p.x - sx, p.y - sy, p.z - sz);
+      const float dt = length3(q.x - tx, q.y - ty, q.z - tz);
+      const float v = consistency(__fsub_rn(ds, dt), s2);
+      vals[ii] = (col_ok && ii < i_lim) ? v : 0.0f;
+    }
+    if (kt1 < KT) {
+#pragma unroll
+      for (int ii = 0; ii < 16; ++ii) out1[ii * 128] = vals[ii];
     }
     if (A != Bq) {
+#pragma unroll
+      for (int ii = 0; ii < 16; ++ii) trw[ii * kScTStride] = vals[ii];
       __syncthreads();
       // orientation 2: key = 128 Bq + j, query = 128 A + i  ->  tile (kt = 2 Bq + (j >> 6), qt = A), element [(j & 63)][i]
-#pragma unroll 4
-      for (int jj = 0; jj < 16; ++jj) {
-        const int jl2 = tg * 16 + jj;
-        const int kt = 2 * Bq + (jl2 >> 6);
-        if (kt < KT) sc[((set_base + (size_t)kt * QT + A) << 13) + (jl2 & 63) * 128 + ic * 32 + ti] = tr[ti * kScTStride + jl2];
+      const int kt2 = 2 * Bq + (tg >> 2);      // the warp's 16 j share one key tile
+      if (kt2 < KT) {
+        float* out2 = sc + ((set_base + (size_t)kt2 * QT + A) << 13) + ((tg & 3) * 16) * 128 + ic * 32 + ti;
+        const float* trr = tr + ti * kScTStride + tg * 16;
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) out2[jj * 128] = trr[jj];
       }
       __syncthreads();
     }

@@ -32,11 +32,16 @@ struct AttnArgs {
 };
 
 constexpr int kAttnThreads = 320;
-constexpr int kAttnKStages = 3, kAttnVStages = 2;
-constexpr int kAttnQ = 0, kAttnK = 65536, kAttnV = kAttnK + kAttnKStages * 32768, kAttnBars = kAttnV + kAttnVStages * 32768;
+// K is staged per PAIR of 64-key tiles so that S = Q K^T runs as N = 128 MMAs (an N = 64 MMA is bound by the delivery of
+// its 4 KB A slice, ~48 cycles instead of 32): stage = [hi p0 | hi p1 | lo p0 | lo p1], each panel 128 rows x 128 B with
+// the first tile of the pair in rows 0-63 and the second in rows 64-127.  The Q image lands in K stage 1 first (it is
+// moved to tensor memory before the second pair is needed); the output tile is staged in K stage 0 at the end.
+constexpr int kAttnKStages = 2, kAttnVStages = 2;
+constexpr int kAttnK = 0, kAttnQ = 65536, kAttnV = kAttnKStages * 65536, kAttnBars = kAttnV + kAttnVStages * 32768;
+constexpr int kAttnOut = 0;
 constexpr int kAttnRef = kAttnBars + 256;              // float ref[2][128], lsum[2][128]
-constexpr int kAttnSmemTc = kAttnRef + 2048;           // 231,680 B (limit 232,448)
-static_assert(kAttnBars == 229376, "smem map");
+constexpr int kAttnSmemTc = kAttnRef + 2048;           // 198,912 B
+static_assert(kAttnBars == 196608, "smem map");
 constexpr float kRescaleThreshold = 8.0f;              // log2 units: P < 2^8 before the reference max advances
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -95,9 +100,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
   float* lsum_s = ref_s + 256;                                // [2][128] per-group row sums (epilogue)
   const uint32_t s0 = smem_u32(smem);
   const uint32_t q_full = smem_u32(bars + 0);
-  const uint32_t k_full = smem_u32(bars + 1), k_empty = smem_u32(bars + 4);     // [3]
+  const uint32_t k_full = smem_u32(bars + 1), k_empty = smem_u32(bars + 4);     // [2] (per pair of key tiles)
   const uint32_t v_full = smem_u32(bars + 7), v_empty = smem_u32(bars + 9);     // [2]
-  const uint32_t s_full = smem_u32(bars + 11), p_full = smem_u32(bars + 15);    // [4]
+  const uint32_t s_full = smem_u32(bars + 11), p_full = smem_u32(bars + 15);    // s_full [2] per pair, p_full [4] per tile
   const uint32_t pv_done = smem_u32(bars + 19), ref_ready = smem_u32(bars + 21);  // [2]
   const uint32_t o_done = smem_u32(bars + 23), q_tmem = smem_u32(bars + 25);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -112,12 +117,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
     mbar_init(q_full, 1);
     mbar_init(o_done, 1);
     mbar_init(q_tmem, 256);
-    for (int i = 0; i < 3; ++i) { mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) {
+      mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 1);
       mbar_init(v_full + 8 * i, 1); mbar_init(v_empty + 8 * i, 1);
       mbar_init(pv_done + 8 * i, 1); mbar_init(ref_ready + 8 * i, 128);
     }
-    for (int i = 0; i < 4; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(p_full + 8 * i, 128); }
+    for (int i = 0; i < 4; ++i) { mbar_init(s_full + 8 * i, 1); mbar_init(p_full + 8 * i, 128); }   // s_full: [0..1] used
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -135,24 +140,37 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
       mbar_expect_tx(q_full, a.split ? 65536u : 32768u);
       bulk_g2s(s0 + kAttnQ, qsrc, 32768u, q_full);
       if (a.split) bulk_g2s(s0 + kAttnQ + 32768, qsrc + 32768, 32768u, q_full);
-      const uint32_t half = a.split ? 32768u : 16384u;
       const uint8_t* kv = a.kvimg + (size_t)b * a.KT * 65536;
-      // two independent streams (K three tiles deep, V two): never let a full V ring hold back the next K tile
-      int kj = 0, vj = 0;
-      while (kj < T || vj < T) {
+      const int TP = (T + 1) >> 1;
+      // two independent streams (K by pairs, two pairs deep; V by tiles, two deep): a full V ring never holds back K
+      int kp = 0, vj = 0;
+      while (kp < TP || vj < T) {
         bool progress = false;
-        if (kj < T) {
-          const int st = kj % kAttnKStages, use = kj / kAttnKStages;
-          if (use == 0 || mbar_test(k_empty + 8 * st, (uint32_t)((use - 1) & 1))) {
-            mbar_expect_tx(k_full + 8 * st, half);
-            bulk_g2s(s0 + kAttnK + st * 32768, kv + (size_t)kj * 65536, half, k_full + 8 * st);
-            ++kj;
+        if (kp < TP) {
+          const int st = kp & 1, use = kp >> 1;
+          // stage 1 holds the Q image until the softmax threads have moved it to tensor memory
+          const bool free = (use == 0) ? (st == 0 || mbar_test(q_tmem, 0)) : mbar_test(k_empty + 8 * st, (uint32_t)((use - 1) & 1));
+          if (free) {
+            const int ntiles = (2 * kp + 1 < T) ? 2 : 1;
+            mbar_expect_tx(k_full + 8 * st, (a.split ? 32768u : 16384u) * ntiles);
+            for (int hh = 0; hh < ntiles; ++hh) {
+              const uint8_t* src = kv + (size_t)(2 * kp + hh) * 65536;
+              const uint32_t dst = s0 + kAttnK + st * 65536 + hh * 8192;
+              bulk_g2s(dst, src, 8192u, k_full + 8 * st);                          // hi, channels 0-63
+              bulk_g2s(dst + 16384, src + 8192, 8192u, k_full + 8 * st);           // hi, channels 64-127
+              if (a.split) {
+                bulk_g2s(dst + 32768, src + 16384, 8192u, k_full + 8 * st);        // lo
+                bulk_g2s(dst + 49152, src + 24576, 8192u, k_full + 8 * st);
+              }
+            }
+            ++kp;
             progress = true;
           }
         }
         if (vj < T) {
           const int st = vj & 1, use = vj >> 1;
           if (use == 0 || mbar_test(v_empty + 8 * st, (uint32_t)((use - 1) & 1))) {
+            const uint32_t half = a.split ? 32768u : 16384u;
             mbar_expect_tx(v_full + 8 * st, half);
             bulk_g2s(s0 + kAttnV + st * 32768, kv + (size_t)vj * 65536 + 32768, half, v_full + 8 * st);
             ++vj;
@@ -170,18 +188,19 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
     const bool stamp_mma = leader && a.dbg != nullptr && blockIdx.x == 0;
     mbar_wait(q_tmem, 0);   // Q (hi | lo images, 64 columns each) is resident in tensor memory
     tc_fence_after();
-    auto issue_qk = [&](int j) {
-      const int st = j % kAttnKStages, use = j / kAttnKStages;
+    auto issue_qk_pair = [&](int p) {   // S tiles 2p, 2p+1 (columns 128 (p & 1) ...) = Q K^T over 128 keys
+      const int st = p & 1, use = p >> 1;
       mbar_wait(k_full + 8 * st, (uint32_t)(use & 1));
       tc_fence_after();
       if (leader) {
-        const uint32_t kb = s0 + kAttnK + st * 32768;
-        issue_gemm_ts<2, 64>(tmem + 64 * (j & 3), tQ, tQ + 64, kb, kb + 16384, 8192, a.split, 0, FMT);
-        mma_commit(s_full + 8 * (j & 3));
+        const uint32_t kb = s0 + kAttnK + st * 65536;
+        issue_gemm_ts<2, 128>(tmem + 128 * st, tQ, tQ + 64, kb, kb + 32768, 16384, a.split, 0, FMT);
+        mma_commit(s_full + 8 * st);
         mma_commit(k_empty + 8 * st);
       }
     };
-    for (int j = 0; j < T && j < 3; ++j) issue_qk(j);
+    const int TP = (T + 1) >> 1;
+    for (int p = 0; p < TP && p < 2; ++p) issue_qk_pair(p);
     for (int j = 0; j < T; ++j) {
       const int vs = j & 1;
       if (stamp_mma) PDSC_STAMP1(a.dbg, j, 0, 0);
@@ -192,13 +211,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
       tc_fence_after();
       if (leader) {
         const uint32_t vb = s0 + kAttnV + vs * 32768;
-        const uint32_t tP = tmem + 64 * (j & 3);   // P_j: hi image in columns [0,32), lo image in [32,64) of its S buffer
+        const uint32_t tP = tmem + 64 * (j & 3);   // P_j: hi image in columns [0,32), lo image in [32,64) of its S tile
         issue_gemm_ts<1, 128>(tO, tP, tP + 32, vb, vb + 16384, 0, a.split, j > 0 ? 1u : 0u, FMT);
         mma_commit(pv_done + 8 * vs);
         mma_commit(v_empty + 8 * vs);
       }
       if (stamp_mma) PDSC_STAMP1(a.dbg, j, 0, 3);
-      if (j + 3 < T) issue_qk(j + 3);   // in-order execution: runs after PV_{j-1}, the last reader of that S/P buffer
+      // after PV of the second tile of pair p, pair p + 2 may overwrite that S/P buffer (in-order execution)
+      if ((j & 1) && (j >> 1) + 2 < TP) issue_qk_pair((j >> 1) + 2);
     }
     if (leader) mma_commit(o_done);
     __syncwarp();
@@ -248,7 +268,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
       const uint32_t tS = tmem + 64 * (j & 3) + lane_base;
       if (j + 4 < T) { prefetch_l2(sc_line + (size_t)(j + 4) * tile_stride); prefetch_l2(sc_line + (size_t)(j + 4) * tile_stride + 4096); }
       if (stamp) PDSC_STAMP1(a.dbg, j, 1 + g, 0);
-      mbar_wait(s_full + 8 * (j & 3), (uint32_t)((j >> 2) & 1));
+      mbar_wait(s_full + 8 * ((j >> 1) & 1), (uint32_t)((j >> 2) & 1));
       if (stamp) PDSC_STAMP1(a.dbg, j, 1 + g, 1);
       tc_fence_after();
       float l[64];
@@ -338,7 +358,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
     }
     softmax_all_sync();
     const float inv_l = 1.0f / (lsum_s[r] + lsum_s[128 + r]);
-    uint8_t* ostage = smem + kAttnQ;  // [128 rows][512 B], 16-byte chunk c of row r at (c & ~7) | ((c ^ r) & 7)
+    uint8_t* ostage = smem + kAttnOut;  // [128 rows][512 B], 16-byte chunk c of row r at (c & ~7) | ((c ^ r) & 7)
 #pragma unroll
     for (int c0 = 0; c0 < 64; c0 += 32) {   // group g converts columns [64 g, 64 g + 64) of every row
       uint32_t o[32];

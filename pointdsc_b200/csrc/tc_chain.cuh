@@ -41,6 +41,15 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+// explicit global-space 16-byte store: through a pointer the compiler cannot prove global (an element of a local
+// pointer array, a select with nullptr) it emits generic ST.E, which is markedly slower than STG
+__device__ __forceinline__ void st_global_v4(void* p, const uint4& v) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_u16(void* p, uint16_t v) {
+  asm volatile("st.global.b16 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "h"(v) : "memory");
+}
 __device__ __forceinline__ void quarter_sync(int q4) { asm volatile("bar.sync %0, 64;" ::"r"(2 + q4) : "memory"); }
 
 // D[128 x NOUT] (+)= A[128 x 32 KCH] * B[NOUT x 32 KCH]^T, A in tensor memory in the chunked in-place layout described
@@ -345,19 +354,17 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
             for (int i = 0; i < 8; ++i) {
               const int rr = sub + 4 * i;
               const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((piece ^ (rr & 7)) << 4));
-              if (img_row[i])
-                *reinterpret_cast<uint4*>(img_row[i] + panel_off + (((uint32_t)piece ^ img_rx[i]) << 4) + (part ? lo_off : 0u)) = val;
+              if (img_row[i]) st_global_v4(img_row[i] + panel_off + (((uint32_t)piece ^ img_rx[i]) << 4) + (part ? lo_off : 0u), val);
             }
           }
           if (stamp && step == 1) PDSC_STAMP1(a.dbg, it, 3, 4);
         } else
         for (int c0 = cbeg; c0 < cend; c0 += 32) {
-          const bool st1 = stamp && step == 1 && c0 == cbeg;
-          if (st1) PDSC_STAMP1(a.dbg, it, 3, 0);
+          const bool st0 = stamp && step == 0 && c0 == cbeg;   // timeline: loader slots 4-7 carry the step-0 epilogue detail
+          if (st0) PDSC_STAMP1(a.dbg, it, 1, 4);
           uint32_t raw[32];
           tmem_ld32(dcol + dstep + c0, raw);
           tmem_ld_wait();
-          if (st1) PDSC_STAMP1(a.dbg, it, 3, 1);
           float x[32];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
@@ -376,6 +383,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
             for (int i = 0; i < 16; ++i) split_pair<FMT>(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
             tmem_st16(dcol + dstep + c0, hi);
             if (a.split) tmem_st16(dcol + dstep + c0 + 16, lo);
+            if (st0) PDSC_STAMP1(a.dbg, it, 1, 5);
           }
 
           if (MODE == kMSG && step == 2) {
@@ -404,6 +412,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
               const float4 val = *reinterpret_cast<const float4*>(stage + rr * 128 + ((piece ^ (rr & 7)) << 4));
               if (g < a.rows) *reinterpret_cast<float4*>(a.out_f32 + g * kC + c0 + piece * 4) = val;
             }
+            if (st0) PDSC_STAMP1(a.dbg, it, 1, 6);
           }
           if (MODE == kKV && step == 1 && live) {
             // V^T image: row = channel, column = key; a warp writes 32 consecutive keys of one channel row
@@ -412,8 +421,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
             for (int i = 0; i < 32; ++i) {
               const uint16_t hv = to_16<FMT>(x[i]);
               const uint32_t off = sw128_offset((uint32_t)(c0 + i), (uint32_t)(my_n & 63));
-              *reinterpret_cast<uint16_t*>(base + off) = hv;
-              if (a.split) *reinterpret_cast<uint16_t*>(base + 16384 + off) = to_16<FMT>(x[i] - from_16<FMT>(hv));
+              st_global_u16(base + off, hv);
+              if (a.split) st_global_u16(base + 16384 + off, to_16<FMT>(x[i] - from_16<FMT>(hv)));
             }
           }
         }
@@ -421,8 +430,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           tmem_st_wait();        // A operand written through tcgen05.st, read by the tensor core
           tc_fence_before();
           mbar_arrive(a1_ready);
+          if (stamp && step == 0) PDSC_STAMP1(a.dbg, it, 1, 7);
         }
-      
     };
     if (MODE == kPCQ) {
       // Software-pipelined order  E0(t), E1(t-1), E0(t+1), E1(t), ...: the step-1 MMA of tile t (which needs E0(t)'s
