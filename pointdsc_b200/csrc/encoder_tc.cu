@@ -11,15 +11,15 @@
 //
 // Operand images.  Every MMA operand is a K-major bf16 "panel": rows x 64 elements = rows x 128 B in the
 // canonical SWIZZLE_128B layout (8-row atoms of 1024 B; 16-byte chunk c of row r stored at chunk c ^ (r & 7)).
-// A 128-channel operand is two panels; "hi" panels come first, "lo" panels second.  Producers write Q / K / V^T
+// A 128-channel operand is two panels; "hi" panels come first, "lo" panels second.  Producers write Q / K / V
 // straight into this image layout in HBM, so a consumer stages a whole operand tile with ONE bulk async copy
 // (cp.async.bulk -> TMA engine, mbarrier complete_tx) and no tensor map.  Per set b:
 //     Qimg[b][qt]   qt = 128-query tile : [Qhi 32K][Qlo 32K]                       (Q pre-scaled by log2e/sqrt(C))
-//     KVimg[b][kt]  kt = 64-key tile    : [Khi 16K][Klo 16K][V^Thi 16K][V^Tlo 16K]
+//     KVimg[b][kt]  kt = 64-key tile    : [Khi 16K][Klo 16K][Vhi 16K][Vlo 16K]   (V in the K format, read MN-major)
 //
 // Kernels per layer (all warp-specialised, one CTA per SM, mbarrier pipelines):
 //   tc_chain<PCQ>   feat  -> PointCN -> feat1 (fp32, HBM) -> Q image                 weights resident in smem
-//   tc_chain<KV>    feat1 -> K image, V^T image
+//   tc_chain<KV>    feat1 -> K image, V image (K format)
 //   tc_attention    flash-style: S = Q K^T into TMEM, SC-weighted online softmax by 128 row-owner threads,
 //                   P (bf16 hi/lo) through smem, O += P V in TMEM; lazy rescale; msg (fp32, HBM)
 //   tc_chain<MSG>   msg -> fc_message chain -> + feat1 -> feat (fp32, HBM)
@@ -123,15 +123,14 @@ __global__ void tc_clear_pads_kernel(uint8_t* kvimg, int N, int KT) {
   if (first_pad == 0) return;
   uint8_t* base = kvimg + ((size_t)b * KT + (KT - 1)) * 65536;
   const int pads = 64 - first_pad;
-  // K rows n in [first_pad, 64): both panels, hi and lo;  V^T columns likewise for all 128 channel rows
+  // K rows n in [first_pad, 64): both panels, hi and lo;  V rows likewise
   for (int t = threadIdx.x; t < pads * 128; t += blockDim.x) {
     const uint32_t n = (uint32_t)(first_pad + t / 128), c = (uint32_t)(t % 128);
     const uint32_t koff = (c >> 6) * 8192u + sw128_offset(n, c & 63u);
     *reinterpret_cast<uint16_t*>(base + koff) = 0;
     *reinterpret_cast<uint16_t*>(base + 16384 + koff) = 0;
-    const uint32_t voff = sw128_offset(c, n);
-    *reinterpret_cast<uint16_t*>(base + 32768 + voff) = 0;
-    *reinterpret_cast<uint16_t*>(base + 49152 + voff) = 0;
+    *reinterpret_cast<uint16_t*>(base + 32768 + koff) = 0;   // V has the K format (rows = keys)
+    *reinterpret_cast<uint16_t*>(base + 49152 + koff) = 0;
   }
 }
 
@@ -151,8 +150,7 @@ __global__ void tc_decode_kernel(const uint8_t* qimg, const uint8_t* kvimg, floa
   const uint8_t* kb = kvimg + ((size_t)b * KT + (n >> 6)) * 65536;
   const uint32_t ko = (c >> 6) * 8192u + sw128_offset((uint32_t)(n & 63), c & 63u);
   k[idx] = rd(kb + ko) + (split ? rd(kb + 16384 + ko) : 0.f);
-  const uint32_t vo = sw128_offset(c, (uint32_t)(n & 63));
-  v[idx] = rd(kb + 32768 + vo) + (split ? rd(kb + 49152 + vo) : 0.f);
+  v[idx] = rd(kb + 32768 + ko) + (split ? rd(kb + 49152 + ko) : 0.f);
 }
 
 // =========================================================================================================

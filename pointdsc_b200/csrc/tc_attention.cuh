@@ -5,7 +5,7 @@
 // SC multiplies the logit (it is not a mask): SC_ij = 0 leaves logit 0, which still takes softmax mass.
 //
 // One CTA = 128 queries of one set, looping over 64-key tiles.  Warp roles (320 threads):
-//   warp 0      loader : bulk async copies (TMA engine) of the ready-made K / V^T operand images (K ring of 3, V ring of 2)
+//   warp 0      loader : bulk async copies (TMA engine) of the ready-made K / V operand images (K by pairs of tiles, ring of 2; V ring of 2)
 //   warp 1      MMA    : S_j = Q K_j^T into one of four TMEM buffers, issued up to three tiles ahead;
 //                        O += P_j V_j with P_j read FROM TENSOR MEMORY (A operand in TMEM); owns the TMEM allocation
 //   warps 2-5   softmax group 0: even key tiles          warps 6-9  softmax group 1: odd key tiles
@@ -91,6 +91,34 @@ __device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_hi, ui
   }
 }
 
+// O[128 x 128] (+)= P[128 x 64] * V[64 x 128] with P in tensor memory and V (rows = keys, the K image format: two 64-channel
+// panels of 64 rows x 128 B) read as an MN-MAJOR B operand: idesc bit 16, LBO = 8192 B between the two 64-channel atoms,
+// SBO = 1024 B between 8-key groups, 2048 B per K = 16 step (pinned by tools/mn_major_probe.cu).
+__device__ __forceinline__ void issue_pv_mn(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t v_hi, uint32_t v_lo, int split,
+                                            uint32_t accumulate, int fmt) {
+  const uint32_t idesc = idesc_f16kind(128, 128, fmt) | (1u << 16);
+  constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);  // SBO = 1024 B, version 1, SWIZZLE_128B
+  uint32_t acc = accumulate;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    if (t > 0 && !split) break;
+    const uint32_t at = (t == 2) ? a_lo : a_hi;
+    const uint32_t b = (t == 1) ? v_lo : v_hi;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t blo = (((b + ks * 2048) >> 4) & 0x3FFFu) | ((8192u >> 4) << 16);
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+          "mov.b64 db, {%2, %5};\n\t"
+          "setp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+          ::"r"(d_tmem), "r"(at + ks * 8), "r"(blo), "r"(idesc), "r"(acc), "r"(kDescHi)
+          : "memory");
+      acc = 1;
+    }
+  }
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -108,6 +136,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / a.QT, qt = blockIdx.x % a.QT;
   const int T = a.KT;
+  const bool life = a.dbg != nullptr && (blockIdx.x == 0 || blockIdx.x == 1000) && tid == 64;   // row 0: block 0, row 1: block 1000   // CTA lifetime stamps: role 3 of tile row 0 / 1
+  if (life) PDSC_STAMP1(a.dbg, (blockIdx.x ? 1 : 0), 3, 0);
 
   if (tid == 0) {
     if (s0 & 1023u) {
@@ -130,6 +160,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (life) PDSC_STAMP1(a.dbg, (blockIdx.x ? 1 : 0), 3, 1);
   const uint32_t tO = tmem + 256;   // S/P buffer i at +64 i (i = tile & 3), O at +256 (128 fp32 columns)
   const uint32_t tQ = tmem + 384;   // Q: hi image (64 columns = 128 channels) at +384, lo image at +448
 
@@ -212,7 +243,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
       if (leader) {
         const uint32_t vb = s0 + kAttnV + vs * 32768;
         const uint32_t tP = tmem + 64 * (j & 3);   // P_j: hi image in columns [0,32), lo image in [32,64) of its S tile
-        issue_gemm_ts<1, 128>(tO, tP, tP + 32, vb, vb + 16384, 0, a.split, j > 0 ? 1u : 0u, FMT);
+        issue_pv_mn(tO, tP, tP + 32, vb, vb + 16384, a.split, j > 0 ? 1u : 0u, FMT);
         mma_commit(pv_done + 8 * vs);
         mma_commit(v_empty + 8 * vs);
       }
@@ -264,6 +295,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
     }
     tc_fence_before();
     mbar_arrive(q_tmem);
+    if (life) PDSC_STAMP1(a.dbg, (blockIdx.x ? 1 : 0), 3, 2);
     for (int j = g; j < T; j += 2) {
       const uint32_t tS = tmem + 64 * (j & 3) + lane_base;
       if (j + 4 < T) { prefetch_l2(sc_line + (size_t)(j + 4) * tile_stride); prefetch_l2(sc_line + (size_t)(j + 4) * tile_stride + 4096); }
@@ -353,8 +385,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
       mbar_wait(ref_ready + 8 * (jl & 1), (uint32_t)((jl >> 1) & 1));
       const float final_ref = ref_s[(jl & 1) * 128 + r];
       lsum_s[g * 128 + r] = l_sum * ex2_approx(my_ref - final_ref);
+      if (life) PDSC_STAMP1(a.dbg, (blockIdx.x ? 1 : 0), 3, 3);
       mbar_wait(o_done, 0);   // last PV complete (and with it every earlier MMA)
       tc_fence_after();
+      if (life) PDSC_STAMP1(a.dbg, (blockIdx.x ? 1 : 0), 3, 4);
     }
     softmax_all_sync();
     const float inv_l = 1.0f / (lsum_s[r] + lsum_s[128 + r]);
@@ -381,8 +415,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
       const float4 val = *reinterpret_cast<const float4*>(ostage + rr * 512 + (((lane & ~7) | ((lane ^ rr) & 7)) << 4));
       if (qt * 128 + rr < a.N) *reinterpret_cast<float4*>(dst + (size_t)rr * kC + lane * 4) = val;
     }
+    if (life) PDSC_STAMP1(a.dbg, (blockIdx.x ? 1 : 0), 3, 5);
   }
   __syncthreads();
+  if (life) PDSC_STAMP1(a.dbg, (blockIdx.x ? 1 : 0), 3, 6);
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 

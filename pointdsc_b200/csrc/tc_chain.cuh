@@ -1,7 +1,7 @@
 // tc_chain: fused row-tile GEMM chains of the encoder's 1x1 convolutions on tcgen05 (included by encoder_tc.cu).
 //
 //   PCQ : feat  --W1,relu--> feat1 (fp32 -> HBM) --Wq--> Q image (HBM)
-//   KV  : feat1 --Wk--> K image (HBM) ;  feat1 --Wv--> V^T image (HBM)
+//   KV  : feat1 --Wk--> K image (HBM) ;  feat1 --Wv--> V image (HBM, same row-major format as K)
 //   MSG : msg --Wm0,relu--> --Wm1,relu--> --Wm2--> + feat1 --> feat (fp32 -> HBM)
 // (reference models/PointDSC.py:56-61 PointCN, :21-23/:36-38 projections, :12-20/:43-44 fc_message + residual)
 //
@@ -274,8 +274,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
       if (stamp) PDSC_STAMP1(a.dbg, it, 3, 6);
       const uint32_t dcol = tmem + lane_base + (uint32_t)par * 256u;
       const long long row0 = tile * 128 + q4 * 32;          // first global row of this lane quarter
-      const long long grow = row0 + lane;
-      const bool live = grow < a.rows;
       // (set, index) of the quarter's first row: one division per tile, the 32 rows follow by comparison
       const int b0 = (int)((unsigned)row0 / (unsigned)a.N);
       const int n0 = (int)((unsigned)row0 - (unsigned)b0 * (unsigned)a.N);
@@ -317,8 +315,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         const float* bvec = bias + ((MODE == kMSG) ? (step == 0 ? 0 : (step == 1 ? 64 : 128)) : step * 128);
         const int cbeg = h * (ncols / 2), cend = cbeg + ncols / 2;
         const bool chained = (MODE == kPCQ && step == 0) || (MODE == kMSG && step < 2);   // feeds the next MMA
-        if ((MODE == kPCQ && step == 1) || (MODE == kKV && step == 0)) {
-          // Q / K image -> HBM.  This thread's 64 columns are exactly one 128-byte panel row (hi) and one (lo): stage
+        if ((MODE == kPCQ && step == 1) || MODE == kKV) {
+          // Q / K / V image -> HBM (V has the K format: rows = keys; the PV MMA reads it as an MN-major B operand).  This thread's 64 columns are exactly one 128-byte panel row (hi) and one (lo): stage
           // the warp's 32 rows x 128 B, then every store instruction writes four full 128-byte lines.
           if (stamp && step == 1) PDSC_STAMP1(a.dbg, it, 3, 0);
           uint32_t hi[32], lo[32];
@@ -337,7 +335,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
             }
           }
           if (stamp && step == 1) PDSC_STAMP1(a.dbg, it, 3, 1);
-          const uint32_t panel_off = (uint32_t)h * ((MODE == kPCQ) ? 16384u : 8192u);
+          const uint32_t panel_off = (uint32_t)h * ((MODE == kPCQ) ? 16384u : 8192u) + ((MODE == kKV && step == 1) ? 32768u : 0u);
           const uint32_t lo_off = (MODE == kPCQ) ? 32768u : 16384u;
 #pragma unroll
           for (int part = 0; part < 2; ++part) {
@@ -365,6 +363,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           uint32_t raw[32];
           tmem_ld32(dcol + dstep + c0, raw);
           tmem_ld_wait();
+          if (st0) PDSC_STAMP1(a.dbg, it, 3, 2);
           float x[32];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
@@ -381,6 +380,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) split_pair<FMT>(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
+            if (st0) PDSC_STAMP1(a.dbg, it, 3, 3);
             tmem_st16(dcol + dstep + c0, hi);
             if (a.split) tmem_st16(dcol + dstep + c0 + 16, lo);
             if (st0) PDSC_STAMP1(a.dbg, it, 1, 5);
@@ -413,17 +413,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
               if (g < a.rows) *reinterpret_cast<float4*>(a.out_f32 + g * kC + c0 + piece * 4) = val;
             }
             if (st0) PDSC_STAMP1(a.dbg, it, 1, 6);
-          }
-          if (MODE == kKV && step == 1 && live) {
-            // V^T image: row = channel, column = key; a warp writes 32 consecutive keys of one channel row
-            uint8_t* base = a.kvimg + ((size_t)my_b * a.KT + (my_n >> 6)) * 65536 + 32768;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const uint16_t hv = to_16<FMT>(x[i]);
-              const uint32_t off = sw128_offset((uint32_t)(c0 + i), (uint32_t)(my_n & 63));
-              st_global_u16(base + off, hv);
-              if (a.split) st_global_u16(base + 16384 + off, to_16<FMT>(x[i] - from_16<FMT>(hv)));
-            }
           }
         }
         if (chained) {

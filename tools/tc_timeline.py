@@ -15,10 +15,10 @@ cp, s, t = (base[k].repeat(rep, 1, 1)[:a.b].cuda() for k in ("corr_pos", "src_ke
 m.run(cp, s, t)
 out = m.run(cp, s, t, taps=["timeline"], layer_tap=3)
 tl = out["timeline"].cpu().numpy()
-for k, name, roles in ((0, "chain<PCQ>", ["mma", "loader", "epilogue", "epi-detail"]), (1, "attention", ["mma", "softmax-g0", "softmax-g1"])):
+for k, name, roles in ((0, "chain<PCQ>", ["mma", "loader", "epilogue", "epi-detail"]), (1, "attention", ["mma", "softmax-g0", "softmax-g1", "life"])):
     d = tl[k]; t0 = d[d > 0].min()
     print(f"== {name}: cycles since first stamp; rows = tile/iteration, per role events")
-    for it in range(10):
+    for it in range(16):
         line = f"it{it:2d}"
         for ri, rn in enumerate(roles):
             ev = d[it, ri]; line += f" | {rn}:" + " ".join(f"{int(x - t0):7d}" if x > 0 else "      -" for x in ev)
