@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -35,6 +36,7 @@
 #include "encoder_tc.h"
 #include "kernels.h"
 #include "tc_attention.cuh"
+#include "tc_attention_p.cuh"
 #include "tc_chain.cuh"
 #include "tc_common.cuh"
 #include "tc_ptx.cuh"
@@ -157,6 +159,7 @@ __global__ void tc_decode_kernel(const uint8_t* qimg, const uint8_t* kvimg, floa
 // host orchestration
 // =========================================================================================================
 static int g_num_sms = 0;
+static int g_attn_persistent = 1;   // PDSC_ATTN_PERSISTENT=0 selects the one-CTA-per-item kernel (developer switch)
 
 template <int FMT>
 static cudaError_t tc_configure_fmt() {
@@ -165,6 +168,7 @@ static cudaError_t tc_configure_fmt() {
   if ((e = cudaFuncSetAttribute(tc_chain_kernel<kKV, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem))) return e;
   if ((e = cudaFuncSetAttribute(tc_chain_kernel<kMSG, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem))) return e;
   if ((e = cudaFuncSetAttribute(tc_attention_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTc))) return e;
+  if ((e = cudaFuncSetAttribute(tc_attention_persistent_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnPSmem))) return e;
   return cudaSuccess;
 }
 
@@ -175,6 +179,7 @@ static cudaError_t tc_configure() {
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   if ((e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+  if (const char* env = getenv("PDSC_ATTN_PERSISTENT")) g_attn_persistent = atoi(env) != 0;
   if ((e = tc_configure_fmt<kFmtF16>()) != cudaSuccess) return e;
   if ((e = tc_configure_fmt<kFmtBF16>()) != cudaSuccess) return e;
   done = true;
@@ -209,9 +214,14 @@ static int tc_encoder_forward_fmt(const TcWeights& w, const TcForwardArgs& a, cu
     tc_chain_kernel<kKV, FMT><<<grid, kChainThreads, kChainSmem, st>>>(c);
     // attention
     AttnArgs at{a.N, a.NS, QT, KT, a.split, qimg, kvimg, a.sc, a.msg,
-                (a.timeline && a.debug_layer == l) ? a.timeline + 512 : nullptr};
+                (a.timeline && a.debug_layer == l) ? a.timeline + 512 : nullptr, a.B * QT};
     if (a.attn_events) cudaEventRecord(a.attn_events[2 * l], st);
-    tc_attention_kernel<FMT><<<a.B * QT, kAttnThreads, kAttnSmemTc, st>>>(at);
+    if (g_attn_persistent) {
+      const int items = a.B * QT;
+      tc_attention_persistent_kernel<FMT><<<items < g_num_sms ? items : g_num_sms, kAttnThreads, kAttnPSmem, st>>>(at);
+    } else {
+      tc_attention_kernel<FMT><<<a.B * QT, kAttnThreads, kAttnSmemTc, st>>>(at);
+    }
     if (a.attn_events) cudaEventRecord(a.attn_events[2 * l + 1], st);
     if (a.debug_out && a.debug_layer == l) {
       const size_t plane = (size_t)rows * kC;

@@ -29,6 +29,7 @@ struct AttnArgs {
   const float* sc;    // tiled: [B][KT][QT][64 keys][128 queries]
   float* msg;
   long long* dbg;
+  int items;          // B * QT work items (persistent kernel)
 };
 
 constexpr int kAttnThreads = 320;

@@ -1,0 +1,390 @@
+// tc_attention (persistent): SC-weighted flash attention on tcgen05, one CTA per SM looping over (set, 128-query tile)
+// work items (included by encoder_tc.cu only).
+//
+// Reference: models/PointDSC.py:39-42
+//     P = softmax_j( SC_ij * (q_i . k_j) / sqrt(C) ),   msg_i = sum_j P_ij v_j          (heads = 1, C = 128)
+// SC multiplies the logit (it is not a mask): SC_ij = 0 leaves logit 0, which still takes softmax mass.
+//
+// The per-item machinery is that of tc_attention.cuh (Q and P as A operands in tensor memory, S = Q K^T as N = 128 MMAs over
+// pairs of 64-key tiles, two softmax groups on alternate key tiles with the running row maximum handed over through
+// shared memory, lazy rescale of O).  What is new is that NOTHING is torn down between items: barriers keep their phase
+// (running use counts), the K / V rings and the S / P buffers keep rotating, and
+//   * the loader streams the next item's K / V tiles and its Q image (through a 32 KB staging buffer, hi then lo half)
+//     while the current item is still being computed;
+//   * the softmax groups move the next Q into tensor memory right after their last tile of the current item (the Q
+//     columns are free once the item's last QK pair has completed);
+//   * the MMA warp issues the next item's first two QK pairs directly behind the current item's last PV, so the tensor
+//     core works on them while the softmax groups drain O (registers -> global, no shared-memory staging).
+// Per-item fixed cost drops from ~14 k cycles (TMEM allocation, barrier set-up, cold Q / K / SC loads, output drain,
+// CTA launch) to the ~2 k-cycle output drain.
+#pragma once
+#include "tc_attention.cuh"
+
+namespace pdsc {
+
+constexpr int kAttnPK = 0;                                   // K: 2 pair stages x 64 KB
+constexpr int kAttnPV = 131072;                              // V: 2 tile stages x 32 KB
+constexpr int kAttnPQ = 196608;                              // Q staging: one 32 KB half image
+constexpr int kAttnPBars = 229376;
+constexpr int kAttnPRef = kAttnPBars + 256;                  // float ref[2][128], lsum[2][128]
+constexpr int kAttnPSmem = kAttnPRef + 2048;                 // 231,680 B (limit 232,448)
+
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory"); }
+
+template <int FMT>
+__global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kernel(AttnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAttnPBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  float* ref_s = reinterpret_cast<float*>(smem + kAttnPRef);  // [2][128] reference maximum after tile j (slot j & 1)
+  float* lsum_s = ref_s + 256;                                // [2][128] per-group row sums (epilogue)
+  const uint32_t s0 = smem_u32(smem);
+  const uint32_t k_full = smem_u32(bars + 0), k_empty = smem_u32(bars + 2);      // [2] per pair stage
+  const uint32_t v_full = smem_u32(bars + 4), v_empty = smem_u32(bars + 6);      // [2] per tile stage
+  const uint32_t s_full = smem_u32(bars + 8);                                    // [2] per S pair buffer
+  const uint32_t p_full = smem_u32(bars + 10);                                   // [4] per S/P tile buffer
+  const uint32_t pv_done = smem_u32(bars + 14), ref_ready = smem_u32(bars + 16); // [2]
+  const uint32_t qh_full = smem_u32(bars + 18), ql_full = smem_u32(bars + 19);   // staging holds the hi / lo half image
+  const uint32_t qh_used = smem_u32(bars + 20), ql_used = smem_u32(bars + 21);   // ... and has been moved to TMEM
+  const uint32_t q_tmem = smem_u32(bars + 22), o_done = smem_u32(bars + 23), o_free = smem_u32(bars + 24);
+  const uint32_t stage_free = smem_u32(bars + 25);   // the item's output has left the staging buffer
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = a.KT, TP = (a.KT + 1) >> 1;
+  const int TE = (T + 1) >> 1, TO = T >> 1;                   // tiles per item with even / odd index
+  const int my_items = (a.items > (int)blockIdx.x) ? (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (tid == 0) {
+    if (s0 & 1023u) {
+      printf("pointdsc_b200: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 1);
+      mbar_init(v_full + 8 * i, 1); mbar_init(v_empty + 8 * i, 1);
+      mbar_init(s_full + 8 * i, 1);
+      mbar_init(pv_done + 8 * i, 1); mbar_init(ref_ready + 8 * i, 128);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(p_full + 8 * i, 128);
+    mbar_init(qh_full, 1); mbar_init(ql_full, 1);
+    mbar_init(qh_used, 128); mbar_init(ql_used, 128);
+    mbar_init(q_tmem, 256); mbar_init(o_done, 1); mbar_init(o_free, 256); mbar_init(stage_free, 256);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tO = tmem + 256;   // S/P tile buffer i at +64 i, O at +256 (128 fp32 columns)
+  const uint32_t tQ = tmem + 384;   // Q: hi image (64 columns = 128 channels) at +384, lo image at +448
+
+  if (warp == 0) {
+    // ===================================== loader =====================================
+    if (lane == 0) {
+      // three independent streams over this CTA's items, each gated only by its own ring / staging slot
+      int ki = 0, kp = 0, gk = 0;        // K: item ordinal, pair within the item, global pair count
+      int vi = 0, vj = 0, gv = 0;        // V: item ordinal, tile within the item, global tile count
+      int qi = 0, qh = 0;                // Q: item ordinal, half (0 = hi, 1 = lo)
+      const int qhalves = a.split ? 2 : 1;
+      while (ki < my_items || vi < my_items || qi < my_items) {
+        bool progress = false;
+        if (ki < my_items) {
+          const int st = gk & 1, use = gk >> 1;
+          if (use == 0 || mbar_test(k_empty + 8 * st, (uint32_t)((use - 1) & 1))) {
+            const int item = blockIdx.x + ki * gridDim.x;
+            const uint8_t* kv = a.kvimg + (size_t)(item / a.QT) * a.KT * 65536;
+            const int ntiles = (2 * kp + 1 < T) ? 2 : 1;
+            mbar_expect_tx(k_full + 8 * st, (a.split ? 32768u : 16384u) * ntiles);
+            for (int hh = 0; hh < ntiles; ++hh) {
+              const uint8_t* src = kv + (size_t)(2 * kp + hh) * 65536;
+              const uint32_t dst = s0 + kAttnPK + st * 65536 + hh * 8192;
+              bulk_g2s(dst, src, 8192u, k_full + 8 * st);                          // hi, channels 0-63
+              bulk_g2s(dst + 16384, src + 8192, 8192u, k_full + 8 * st);           // hi, channels 64-127
+              if (a.split) {
+                bulk_g2s(dst + 32768, src + 16384, 8192u, k_full + 8 * st);        // lo
+                bulk_g2s(dst + 49152, src + 24576, 8192u, k_full + 8 * st);
+              }
+            }
+            ++gk;
+            if (++kp == TP) { kp = 0; ++ki; }
+            progress = true;
+          }
+        }
+        if (vi < my_items) {
+          const int st = gv & 1, use = gv >> 1;
+          if (use == 0 || mbar_test(v_empty + 8 * st, (uint32_t)((use - 1) & 1))) {
+            const int item = blockIdx.x + vi * gridDim.x;
+            const uint8_t* kv = a.kvimg + (size_t)(item / a.QT) * a.KT * 65536;
+            const uint32_t half = a.split ? 32768u : 16384u;
+            mbar_expect_tx(v_full + 8 * st, half);
+            bulk_g2s(s0 + kAttnPV + st * 32768, kv + (size_t)vj * 65536 + 32768, half, v_full + 8 * st);
+            ++gv;
+            if (++vj == T) { vj = 0; ++vi; }
+            progress = true;
+          }
+        }
+        if (qi < my_items) {
+          // the staging buffer is free once the previous half has been moved to tensor memory
+          bool free;
+          // (the buffer also stages the output tile of item qi - 2, after that item's Q(qi - 1) halves have gone through)
+          if (qh == 0) free = (qi == 0) || (mbar_test(a.split ? ql_used : qh_used, (uint32_t)((qi - 1) & 1)) &&
+                                            (qi < 2 || mbar_test(stage_free, (uint32_t)((qi - 2) & 1))));
+          else free = mbar_test(qh_used, (uint32_t)(qi & 1));
+          if (free) {
+            const int item = blockIdx.x + qi * gridDim.x;
+            const uint8_t* qsrc = a.qimg + (size_t)item * 65536 + qh * 32768;
+            const uint32_t bar = qh ? ql_full : qh_full;
+            mbar_expect_tx(bar, 32768u);
+            bulk_g2s(s0 + kAttnPQ, qsrc, 32768u, bar);
+            if (qh == 0 && a.split)   // pull the lo half towards L2 now: it is staged late, at the item boundary
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(qsrc + 32768), "r"(32768u) : "memory");
+            if (++qh == qhalves) { qh = 0; ++qi; }
+            progress = true;
+          }
+        }
+        if (!progress) __nanosleep(64);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =====================================
+    const bool leader = elect_one();
+    auto issue_qk_pair = [&](int G) {   // global pair G: S tiles in columns 128 (G & 1) ... = Q K^T over 128 keys
+      const int st = G & 1, use = G >> 1;
+      mbar_wait(k_full + 8 * st, (uint32_t)(use & 1));
+      tc_fence_after();
+      if (leader) {
+        const uint32_t kb = s0 + kAttnPK + st * 65536;
+        issue_gemm_ts<2, 128>(tmem + 128 * st, tQ, tQ + 64, kb, kb + 32768, 16384, a.split, 0, FMT);
+        mma_commit(s_full + 8 * st);
+        mma_commit(k_empty + 8 * st);
+      }
+    };
+    int gv = 0;
+    const bool stamp_mma = leader && a.dbg != nullptr && blockIdx.x == 0;
+    for (int it = 0; it < my_items; ++it) {
+      const int gkb = it * TP;
+      mbar_wait(q_tmem, (uint32_t)(it & 1));   // this item's Q (hi | lo images) is resident in tensor memory
+      tc_fence_after();
+      if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 0);
+      for (int p = 0; p < TP && p < 2; ++p) issue_qk_pair(gkb + p);
+      if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 1);
+      for (int j = 0; j < T; ++j, ++gv) {
+        const int G = gkb + (j >> 1);
+        const int buf = 2 * (G & 1) + (j & 1);
+        const int vs = gv & 1;
+        mbar_wait(p_full + 8 * buf, (uint32_t)((G >> 1) & 1));
+        mbar_wait(v_full + 8 * vs, (uint32_t)((gv >> 1) & 1));
+        if (j == 0 && it > 0) mbar_wait(o_free, (uint32_t)((it - 1) & 1));   // previous item's O has been drained
+        tc_fence_after();
+        if (leader) {
+          const uint32_t vb = s0 + kAttnPV + vs * 32768;
+          const uint32_t tP = tmem + 64 * buf;   // P_j: hi image in columns [0,32), lo image in [32,64) of its S tile
+          issue_pv_mn(tO, tP, tP + 32, vb, vb + 16384, a.split, j > 0 ? 1u : 0u, FMT);
+          mma_commit(pv_done + 8 * vs);
+          mma_commit(v_empty + 8 * vs);
+        }
+        if (stamp_mma && j == 0) PDSC_STAMP1(a.dbg, it, 0, 2);
+        if (stamp_mma && j == T - 1) PDSC_STAMP1(a.dbg, it, 0, 3);
+        // after PV of the second tile of a pair, the pair two ahead may overwrite that S/P buffer (in-order execution)
+        if ((j & 1) && (j >> 1) + 2 < TP) issue_qk_pair(G + 2);
+      }
+      if (leader) mma_commit(o_done);
+    }
+    __syncwarp();
+  } else {
+    // ===================================== softmax =====================================
+    const int q4 = warp & 3;                 // TMEM lane quarter this warp may access
+    const int g = (warp - 2) >> 2;           // group: tiles j with (j & 1) == g
+    const int r = q4 * 32 + lane;            // query row within the tile == TMEM lane
+    const int gt = (warp - 2 - 4 * g) * 32 + lane;   // thread index within the group
+    const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
+    const size_t tile_stride = (size_t)a.QT << 13;
+    const bool ragged = (a.N & 63) != 0;
+    const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && gt == 0;
+
+    // move one half of the staged Q image (this thread's row) into tensor memory: hi by group 0, lo by group 1
+    auto convert_q = [&](int it_next) {
+      if (g == 0 || a.split) {
+        mbar_wait(g ? ql_full : qh_full, (uint32_t)(it_next & 1));
+        const uint8_t* qrow = smem + kAttnPQ + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+        for (int pnl = 0; pnl < 2; ++pnl) {
+          uint32_t qv[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 v = *reinterpret_cast<const uint4*>(qrow + pnl * 16384 + ((c ^ (r & 7)) << 4));
+            qv[4 * c] = v.x; qv[4 * c + 1] = v.y; qv[4 * c + 2] = v.z; qv[4 * c + 3] = v.w;
+          }
+          tmem_st32(tQ + lane_base + 64 * g + 32 * pnl, qv);
+        }
+        tmem_st_wait();
+        mbar_arrive(g ? ql_used : qh_used);
+      }
+      tc_fence_before();
+      mbar_arrive(q_tmem);
+    };
+
+    float sc[64];
+    auto load_sc = [&](int item, int j) {   // this thread's 64 SC values of key tile j: compile-time offsets c * 512 B
+      const float* p0 = a.sc + ((((size_t)(item / a.QT) * a.KT) * a.QT + (item % a.QT)) << 13) + (size_t)j * tile_stride + r;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) sc[c] = ldg_stream(p0 + c * 128);
+    };
+    if (my_items > 0) {
+      if (g < T) load_sc(blockIdx.x, g);
+      convert_q(0);
+    }
+    for (int it = 0; it < my_items; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int b = item / a.QT, qt = item % a.QT;
+      const int gkb = it * TP, gvb = it * T;
+      const float* sc_cta = a.sc + ((((size_t)b * a.KT) * a.QT + qt) << 13);
+      const float* sc_line = sc_cta + gt * 32;   // two 128-byte lines of each 32 KB tile per thread (L2 prefetch)
+      float my_ref = -INFINITY, l_sum = 0.f;
+      if (stamp) PDSC_STAMP1(a.dbg, it, 1 + g, 0);
+      if (g + 2 < T) { prefetch_l2(sc_line + (size_t)(g + 2) * tile_stride); prefetch_l2(sc_line + (size_t)(g + 2) * tile_stride + 4096); }
+      for (int j = g; j < T; j += 2) {
+        const int G = gkb + (j >> 1);
+        const int buf = 2 * (G & 1) + (j & 1);
+        const uint32_t tS = tmem + 64 * buf + lane_base;
+        if (j + 4 < T) { prefetch_l2(sc_line + (size_t)(j + 4) * tile_stride); prefetch_l2(sc_line + (size_t)(j + 4) * tile_stride + 4096); }
+        mbar_wait(s_full + 8 * (G & 1), (uint32_t)((G >> 1) & 1));
+        tc_fence_after();
+        if (stamp && j == g) PDSC_STAMP1(a.dbg, it, 1 + g, 1);
+        float l[64];
+        {
+          uint32_t raw[32];
+          tmem_ld32(tS, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) l[c] = __uint_as_float(raw[c]) * sc[c];
+          tmem_ld32(tS + 32, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) l[32 + c] = __uint_as_float(raw[c]) * sc[32 + c];
+        }
+        if (ragged && j == T - 1) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) l[c] = (j * 64 + c < a.N) ? l[c] : -INFINITY;
+        }
+        // the SC registers are dead: refill them with this group's next tile (of this item or of the next one)
+        if (j + 2 < T) load_sc(item, j + 2);
+        else if (it + 1 < my_items && g < T) load_sc(item + gridDim.x, g);
+        float tmax = l[0];
+#pragma unroll
+        for (int c = 1; c < 64; ++c) tmax = fmaxf(tmax, l[c]);
+        // running reference maximum of the row, handed from tile to tile between the row's two owner threads
+        float prev_ref = -INFINITY;
+        if (j > 0) {
+          const int pj = j - 1;
+          const int use = ((pj & 1) ? it * TO : it * TE) + (pj >> 1);
+          mbar_wait(ref_ready + 8 * (pj & 1), (uint32_t)(use & 1));
+          prev_ref = ref_s[(pj & 1) * 128 + r];
+        }
+        const bool advance = (j == 0) || (tmax > prev_ref + kRescaleThreshold);
+        const float new_ref = advance ? tmax : prev_ref;
+        ref_s[(j & 1) * 128 + r] = new_ref;
+        mbar_arrive(ref_ready + 8 * (j & 1));
+        l_sum *= ex2_approx(my_ref - new_ref);   // the reference may have moved since this thread's previous tile
+        my_ref = new_ref;
+        float rsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          l[c] = ex2_approx(l[c] - new_ref);
+          rsum += l[c];
+        }
+        l_sum += rsum;
+        // P (16-bit hi / lo images) over this thread's own S row: column c holds keys 2c | 2c+1
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) split_pair<FMT>(l[32 * hf + 2 * i], l[32 * hf + 2 * i + 1], hi[i], lo[i]);
+          tmem_st16(tS + 16 * hf, hi);
+          if (a.split) tmem_st16(tS + 32 + 16 * hf, lo);
+        }
+        // rare: the reference advanced, O (accumulated under the old reference) must be rescaled before PV_j
+        if (__any_sync(0xffffffffu, advance && j > 0)) {
+          const int gp = gvb + j - 1;
+          mbar_wait(pv_done + 8 * (gp & 1), (uint32_t)((gp >> 1) & 1));   // PV_{j-1} complete: O quiescent
+          tc_fence_after();
+          const float scale = (advance && j > 0) ? ex2_approx(prev_ref - new_ref) : 1.0f;
+#pragma unroll
+          for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld32(tO + lane_base + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * scale);
+            tmem_st32(tO + lane_base + c0, o);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full + 8 * buf);
+      }
+      // ---- item boundary ------------------------------------------------------------------------------------
+      if (stamp) PDSC_STAMP1(a.dbg, it, 1 + g, 2);
+      const int Gl = gkb + TP - 1;   // the item's last QK pair: once it has completed, the Q columns are free
+      if (it + 1 < my_items) {
+        mbar_wait(s_full + 8 * (Gl & 1), (uint32_t)((Gl >> 1) & 1));
+        tc_fence_after();
+        if (g >= T) load_sc(item + gridDim.x, g);   // (never true for T >= 2; keeps a one-tile item correct)
+        convert_q(it + 1);
+      }
+      if (stamp) PDSC_STAMP1(a.dbg, it, 1 + g, 3);
+      // ---- epilogue: O / l -> msg, straight from registers (the shared memory belongs to the next item's tiles) ----
+      {
+        const int jl = T - 1;
+        const int use = ((jl & 1) ? it * TO : it * TE) + (jl >> 1);
+        mbar_wait(ref_ready + 8 * (jl & 1), (uint32_t)(use & 1));
+        const float final_ref = ref_s[(jl & 1) * 128 + r];
+        lsum_s[g * 128 + r] = l_sum * ex2_approx(my_ref - final_ref);
+        mbar_wait(o_done, (uint32_t)(it & 1));   // last PV complete (and with it every earlier MMA)
+        tc_fence_after();
+        if (stamp) PDSC_STAMP1(a.dbg, it, 1 + g, 4);
+      }
+      softmax_all_sync();
+      if (stamp) PDSC_STAMP1(a.dbg, it, 1 + g, 5);
+      const float inv_l = 1.0f / (lsum_s[r] + lsum_s[128 + r]);
+      // group g drains columns [64 g, 64 g + 64) of every row, 32 columns at a time, through its 16 KB half of the Q
+      // staging buffer ([128 rows][128 B], 16-byte chunks XOR-swizzled by row) so that every store instruction writes
+      // four full 128-byte lines.  The buffer is free here: both halves of the next Q have already gone through it.
+      if (it + 1 < my_items && a.split && g == 0) mbar_wait(ql_used, (uint32_t)((it + 1) & 1));
+      uint8_t* ost = smem + kAttnPQ + g * 16384;
+      float* dst = a.msg + ((size_t)b * a.N + qt * 128) * kC + 64 * g;
+      const int rsub = gt >> 3, piece = gt & 7;   // read-out: rows rsub + 16 i, 16-byte piece of the 128-byte segment
+#pragma unroll
+      for (int sr = 0; sr < 2; ++sr) {
+        uint32_t o[32];
+        tmem_ld32(tO + lane_base + 64 * g + 32 * sr, o);
+        tmem_ld_wait();
+        if (sr == 1) {
+          tc_fence_before();
+          mbar_arrive(o_free);                  // O may be overwritten by the next item's first PV
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(ost + r * 128 + ((q ^ (r & 7)) << 4)) =
+              make_float4(__uint_as_float(o[4 * q]) * inv_l, __uint_as_float(o[4 * q + 1]) * inv_l,
+                          __uint_as_float(o[4 * q + 2]) * inv_l, __uint_as_float(o[4 * q + 3]) * inv_l);
+        group_sync(g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = rsub + 16 * i;
+          const float4 val = *reinterpret_cast<const float4*>(ost + rr * 128 + ((piece ^ (rr & 7)) << 4));
+          if (qt * 128 + rr < a.N) *reinterpret_cast<float4*>(dst + (size_t)rr * kC + 32 * sr + piece * 4) = val;
+        }
+        group_sync(g);
+      }
+      mbar_arrive(stage_free);
+      if (stamp) PDSC_STAMP1(a.dbg, it, 1 + g, 6);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace pdsc
