@@ -299,7 +299,7 @@ def run_engine(args, rank, world, local_rank):
     except Exception:
         pass
     executed = {"bf16x3": 3, "fp16x3": 3, "bf16": 1, "fp32": 1}[args.precision]
-    roofline = {"kernel": "tc_attention_kernel" if args.precision != "fp32" else "attention_simt_kernel",
+    roofline = {"kernel": "tc_attention_persistent_kernel" if args.precision != "fp32" else "attention_simt_kernel",
                 "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_flops_per_launch": flops_per_launch, "launch_ms": attn_ms / max(attn_launches, 1),
