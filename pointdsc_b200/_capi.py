@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpointdsc_b200.so")
+LIB_PATH = os.environ.get("POINTDSC_B200_LIB") or os.path.join(_HERE, "libpointdsc_b200.so")   # env: developer A/B builds
 
 PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2, "fp16x3": 3}
 SPANS = ["sc", "linear", "attention", "head", "seeds", "knn", "nsm", "hypotheses", "refine", "total"]

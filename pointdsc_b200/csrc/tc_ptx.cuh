@@ -43,6 +43,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+#ifndef PDSC_MBAR_HINT_NS
+#define PDSC_MBAR_HINT_NS 1000000u
+#endif
+constexpr uint32_t kMbarSuspendHintNs = PDSC_MBAR_HINT_NS;
 // try_wait with a suspend-time hint: the warp is parked by the hardware until the phase completes (or the hint
 // expires) instead of spinning through the issue slots the working warps of the same scheduler need.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
@@ -52,7 +56,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(1000000u)
+      : "r"(bar), "r"(parity), "r"(kMbarSuspendHintNs)
       : "memory");
   return ok != 0;
 }
