@@ -5,20 +5,21 @@
 //   MSG : msg --Wm0,relu--> --Wm1,relu--> --Wm2--> + feat1 --> feat (fp32 -> HBM)
 // (reference models/PointDSC.py:56-61 PointCN, :21-23/:36-38 projections, :12-20/:43-44 fc_message + residual)
 //
-// Persistent CTAs (one per SM), weights resident in shared memory, 128-row tiles.  Warp roles (512 threads, so that the
+// Persistent CTAs (one per SM), weights resident in shared memory, 128-row tiles.  The kernels are bound by the latency
+// of their epilogues (TMEM -> registers -> bias / ReLU / hi-lo split -> stores), not by the tensor core or by HBM, so
+// the two GEMM steps of a tile are drained by DIFFERENT warps working concurrently.  Warp roles (512 threads, so that the
 // register file divides into 128 registers per thread):
-//   warps 0-7   epilogue: two warpgroups; thread (row r, half h) owns TMEM lane r and half of the step's columns;
-//               bias / ReLU / residual, hi-lo split, stores
-//   warps 8-14  loaders : prefetch the NEXT tile's fp32 rows into registers (coalesced, rows lw, lw+7, ...), convert
-//               to the swizzled 16-bit A image once the tensor core has released the buffer
+//   warps 0-3   group A: thread = row r (TMEM lane), all columns.  PCQ: PointCN step (feat1 -> HBM and, as 16-bit hi | lo
+//               images, back into tensor memory for the Q GEMM).  KV: K image.  MSG: last step (+ residual, store).
+//   warps 4-7   group B: thread = row r, all columns.  PCQ: Q image.  KV: V image.  MSG: the two 64-wide hidden steps.
+//   warps 8-14  loaders : prefetch the NEXT tile's fp32 rows into registers (coalesced, rows lw + 7 i), convert them to
+//               the swizzled 16-bit A image once the tensor core has released the buffer; MSG: also the residual tile
 //   warp  15    MMA issuer (whole warp runs the control flow, one elected lane issues) + TMEM allocation
-// Chained steps never go back through shared memory: the epilogue writes the next step's A operand (16-bit hi | lo
-// images) over the accumulator columns it has just read, and the next MMA takes A FROM TENSOR MEMORY.  Chunk q (K
-// elements 32 q .. 32 q + 31) of such an operand sits at columns 32 q .. 32 q + 31 of the producing accumulator as
-// [hi: 16 columns | lo: 16 columns].  The shared-memory A buffer is therefore released as soon as the tile's first
-// MMA has consumed it, and the loaders convert tile t+1 under the epilogue of tile t.
-// Accumulators are double-buffered in TMEM by tile parity (2 x 256 columns).  Global stores are staged through a
-// per-warp swizzled smem buffer so that every store instruction writes full 64/128-byte segments.
+// Chained steps never go back through shared memory: the epilogue writes the next step's A operand over the accumulator
+// columns it has just read, and the next MMA takes A FROM TENSOR MEMORY.  Chunk q (K elements 32 q .. 32 q + 31) of such
+// an operand sits at columns 32 q .. 32 q + 31 of the producing accumulator as [hi: 16 columns | lo: 16 columns].
+// Accumulators are double-buffered in TMEM by tile parity (2 x 256 columns).  Global stores go through a 2 KB per-warp
+// staging buffer, 32 rows x 64 B at a time, so that every store instruction writes eight full 64-byte segments.
 #pragma once
 #include "tc_common.cuh"
 
@@ -28,7 +29,7 @@ constexpr int kChainThreads = 512;
 constexpr int kChLoaderWarps = 7, kChLoaderRows = 19;   // rows lw + 7 i, i < 19 (the last one only for lw < 2)
 constexpr int kChA = 0;                          // A image: [hi p0 16K][hi p1 16K][lo p0 16K][lo p1 16K]
 constexpr int kChW = 65536;                      // weight images (128 KB for PCQ / KV, 80 KB for MSG)
-constexpr int kChStage = 65536 + 131072;         // PCQ / KV: 8 x 4 KB store staging
+constexpr int kChStage = 65536 + 131072;         // PCQ / KV: 8 x 2 KB store staging
 constexpr int kChRes = 65536 + 81920;            // MSG: 64 KB residual tile (also the fp32 store staging)
 constexpr int kChBias = kChStage + 32768;        // 256 floats: this mode's biases
 constexpr int kChBars = kChBias + 1024;
@@ -46,9 +47,6 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
 __device__ __forceinline__ void st_global_v4(void* p, const uint4& v) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
-}
-__device__ __forceinline__ void st_global_u16(void* p, uint16_t v) {
-  asm volatile("st.global.b16 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "h"(v) : "memory");
 }
 __device__ __forceinline__ void quarter_sync(int q4) { asm volatile("bar.sync %0, 64;" ::"r"(2 + q4) : "memory"); }
 
@@ -96,6 +94,28 @@ __device__ __forceinline__ void locate_row(int b0, int n0, int rr, int N, int& b
   }
 }
 
+// One warp stores 32 rows x 64 B (16 words per thread, thread = row `lane`) through its 2 KB staging buffer: 16-byte
+// chunk q of row r is parked at chunk q ^ ((r >> 1) & 3) of the row's 64-byte slot (conflict-free both ways); in the
+// read-out lane l takes piece (l & 3) of rows (l >> 2) + 8 i, i < 4, so each store instruction writes 8 rows x 64 B.
+// dst(i, piece) returns the global address of that 16-byte piece, or nullptr for a row that does not exist.
+template <typename DstFn>
+__device__ __forceinline__ void stage_store64(uint8_t* stage, int lane, const uint32_t (&v)[16], DstFn dst) {
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(stage + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
+        make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  __syncwarp();
+  const int piece = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = (lane >> 2) + 8 * i;
+    const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
+    void* p = dst(i, piece);
+    if (p) st_global_v4(p, val);
+  }
+}
+
 template <int MODE, int FMT>
 __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -106,13 +126,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
   const uint32_t s0 = smem_u32(smem);
   const uint32_t bar_w = smem_u32(bars + 0), a_ready = smem_u32(bars + 1), a1_ready = smem_u32(bars + 2),
                  a_free = smem_u32(bars + 3), r_ready = smem_u32(bars + 4), r_free = smem_u32(bars + 5);
-  const uint32_t d_full = smem_u32(bars + 6);   // [step][parity] at + 8 * (step * 2 + parity)
-  const uint32_t d_free = smem_u32(bars + 12);  // [parity]
+  const uint32_t d_full = smem_u32(bars + 6);    // [step][parity] at + 8 * (step * 2 + parity)
+  const uint32_t d0_free = smem_u32(bars + 12);  // [parity]  group A has drained its accumulator(s) of the tile
+  const uint32_t d1_free = smem_u32(bars + 14);  // [parity]  group B has drained the second GEMM's accumulator
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_base = s0 + kChA, w_base = s0 + kChW;
-  constexpr int kSteps = (MODE == kMSG) ? 3 : 2;
   // this mode's biases, packed: PCQ b1|bq, KV bk|bv, MSG bm0|bm1|bm2
   constexpr int kBiasSrc = (MODE == kPCQ) ? kB1 : (MODE == kKV) ? kBk : kBm0;
+  const int N = a.N;
+  const long long rows = a.rows;
 
   if (tid == 0) {
     if (s0 & 1023u) {
@@ -121,13 +143,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
     }
     mbar_init(bar_w, 1);
     mbar_init(a_ready, kChLoaderWarps * 32);
-    mbar_init(a1_ready, 256);
+    mbar_init(a1_ready, 128);
     mbar_init(a_free, 1);
     mbar_init(r_ready, kChLoaderWarps * 32);
-    mbar_init(r_free, 256);
+    mbar_init(r_free, 128);
     for (int i = 0; i < 6; ++i) mbar_init(d_full + 8 * i, 1);
-    mbar_init(d_free, 256);
-    mbar_init(d_free + 8, 256);
+    mbar_init(d0_free, 128); mbar_init(d0_free + 8, 128);
+    mbar_init(d1_free, 128); mbar_init(d1_free + 8, 128);
     fence_barrier_init();
   }
   if (warp == 15) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -141,7 +163,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
     for (int off = 0; off < a.wbytes; off += 32768)
       bulk_g2s(w_base + off, a.wimg + off, (uint32_t)min(32768, a.wbytes - off), bar_w);
   }
-  const long long num_tiles = (a.rows + 127) / 128;
+  const long long num_tiles = (rows + 127) / 128;
 
   if (warp == 15) {
     // =================================== MMA issuer ===================================
@@ -154,22 +176,31 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
       const int par = it & 1, u = it >> 1;
       const uint32_t dcol = tmem + (uint32_t)par * 256u;
       if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 0);
-      mbar_wait(a_ready, (uint32_t)(it & 1));
+      if (MODE != kPCQ) mbar_wait(a_ready, (uint32_t)(it & 1));
       if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 1);
-      // PCQ: D0[par] is known drained (the a1_ready wait of tile t-2 covered it); D1[par] is checked before step 1
-      if (MODE != kPCQ && it >= 2) mbar_wait(d_free + 8 * par, (uint32_t)((u - 1) & 1));  // epilogue drained D[par]
-      if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 2);
-      tc_fence_after();
       if (MODE == kPCQ) {
-        if (leader) {
-          issue_gemm<2, 128>(dcol, a_base, a_base + 32768, 16384, w_base, w_base + 32768, 16384, a.split, 0, FMT);
-          mma_commit(d_full + 8 * (0 * 2 + par));
-          mma_commit(a_free);   // the smem A image is dead: step 1 reads feat1 from tensor memory
-        }
+        // Issue order  M0(t), M0(t+1)?, ... is software-pipelined: the PointCN GEMM of tile t + 1 goes out BEFORE the wait for
+        // group A's operand of tile t, so group A finds its next accumulator ready the moment it finishes a tile.
+        // D0[par] is free: the a1_ready wait of tile t - 2 covered group A's drain, and the Q GEMM of tile t - 2 (the last
+        // reader of the operand parked there) was issued before this MMA.
+        auto issue_m0 = [&](int itx) {
+          mbar_wait(a_ready, (uint32_t)(itx & 1));
+          tc_fence_after();
+          if (leader) {
+            const uint32_t dc = tmem + (uint32_t)(itx & 1) * 256u;
+            issue_gemm<2, 128>(dc, a_base, a_base + 32768, 16384, w_base, w_base + 32768, 16384, a.split, 0, FMT);
+            mma_commit(d_full + 8 * (0 * 2 + (itx & 1)));
+            mma_commit(a_free);   // the smem A image is dead: step 1 reads feat1 from tensor memory
+          }
+        };
+        if (it == 0) issue_m0(0);
         if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 3);
+        // M0(t+1) needs D0[par ^ 1]: drained by group A in tile t - 1 (covered by that tile's a1_ready wait) — but the Q GEMM
+        // of tile t - 1 must have been issued, which it was in the previous iteration.
+        if (tile + gridDim.x < num_tiles) issue_m0(it + 1);
         mbar_wait(a1_ready, a1_uses & 1);
         ++a1_uses;
-        if (it >= 2) mbar_wait(d_free + 8 * par, (uint32_t)((u - 1) & 1));  // E1(t-2) drained D1[par]
+        if (it >= 2) mbar_wait(d1_free + 8 * par, (uint32_t)((u - 1) & 1));  // group B drained D1[par] of tile t - 2
         tc_fence_after();
         if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 4);
         if (leader) {
@@ -178,6 +209,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         }
         if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 5);
       } else if (MODE == kKV) {
+        if (it >= 2) {
+          mbar_wait(d0_free + 8 * par, (uint32_t)((u - 1) & 1));
+          mbar_wait(d1_free + 8 * par, (uint32_t)((u - 1) & 1));
+        }
+        tc_fence_after();
         if (leader) {
           issue_gemm<2, 128>(dcol, a_base, a_base + 32768, 16384, w_base, w_base + 32768, 16384, a.split, 0, FMT);
           mma_commit(d_full + 8 * (0 * 2 + par));
@@ -188,6 +224,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         }
       } else {
         // Wm0: 64 x 128 (hi 16K | lo 16K, panel 8K)   Wm1: 64 x 64 (hi 8K | lo 8K)   Wm2: 128 x 64 (hi 16K | lo 16K)
+        // D0 / D1 [par] are free: the a1_ready waits of tile t - 2 covered group B's drains (and the later MMAs of that tile,
+        // their last readers, were issued before this one)
+        tc_fence_after();
         if (leader) {
           issue_gemm<2, 64>(dcol, a_base, a_base + 32768, 16384, w_base, w_base + 16384, 8192, a.split, 0, FMT);
           mma_commit(d_full + 8 * (0 * 2 + par));
@@ -202,6 +241,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         }
         mbar_wait(a1_ready, a1_uses & 1);
         ++a1_uses;
+        if (it >= 2) mbar_wait(d0_free + 8 * par, (uint32_t)((u - 1) & 1));  // group A drained D2[par] of tile t - 2
         tc_fence_after();
         if (leader) {
           issue_gemm_tchunk<2, 128>(dcol + 128, dcol + 64, w_base + 49152, w_base + 49152 + 16384, 16384, a.split, FMT);
@@ -222,8 +262,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
       for (int i = 0; i < kChLoaderRows; ++i) {
         const int rr = lw + kChLoaderWarps * i;
         const long long grow = row0 + rr;
-        v[i] = (rr < 128 && grow < a.rows) ? __ldg(reinterpret_cast<const float4*>(a.in + grow * kC) + lane)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = (rr < 128 && grow < rows) ? __ldg(reinterpret_cast<const float4*>(a.in + grow * kC) + lane)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (stamp_ld) PDSC_STAMP1(a.dbg, it, 1, 0);
       if (it > 0) mbar_wait(a_free, (uint32_t)((it - 1) & 1));
@@ -253,215 +293,256 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           if (r < 128) {
             const long long grow = row0 + r;
             const uint32_t dst = s0 + kChRes + (uint32_t)r * 512u + (uint32_t)(((lane & ~7) | ((lane ^ r) & 7)) << 4);
-            const bool ok = grow < a.rows;
+            const bool ok = grow < rows;
             cp_async16(dst, ok ? (const void*)(a.res + grow * kC + lane * 4) : (const void*)a.res, ok ? 16u : 0u);
           }
         }
         cp_async_arrive_noinc(r_ready);
       }
     }
-  } else {
-    // =================================== epilogue: 2 warpgroups ===================================
-    const int q4 = warp & 3, h = warp >> 2;
-    const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
-    uint8_t* stage = smem + kChStage + warp * 4096;          // PCQ / KV: [32 rows][128 B], 16-byte chunks XOR-swizzled by row
-    uint8_t* resq = smem + kChRes + q4 * 32 * 512;           // MSG: the 32 residual rows of this lane quarter
-    const int sub = lane >> 3, piece = lane & 7;             // read-out phase: rows sub + 4 i, 16-byte piece of the row
-    const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-    // one epilogue step of one tile (all per-tile addressing is derived here, so steps of different tiles can interleave)
-    auto run_step = [&](const long long tile, const int it, const int step) {
-      const int par = it & 1, u = it >> 1;
-      if (stamp) PDSC_STAMP1(a.dbg, it, 3, 6);
-      const uint32_t dcol = tmem + lane_base + (uint32_t)par * 256u;
-      const long long row0 = tile * 128 + q4 * 32;          // first global row of this lane quarter
-      // (set, index) of the quarter's first row: one division per tile, the 32 rows follow by comparison
-      const int b0 = (int)((unsigned)row0 / (unsigned)a.N);
-      const int n0 = (int)((unsigned)row0 - (unsigned)b0 * (unsigned)a.N);
-      int my_b, my_n;
-      locate_row(b0, n0, lane, a.N, my_b, my_n);
-      // image destinations of the 8 rows this lane stores in the read-out phase (PCQ: Q, KV: K)
-      uint8_t* img_row[8];
-      uint32_t img_rx[8];
-      if (MODE == kPCQ || MODE == kKV) {
+  } else if (warp >= 4) {
+    // =================================== group B: thread = row ===================================
+    if (MODE == kPCQ || MODE == kKV) {
+      const int q4 = warp & 3;
+      const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
+      uint8_t* stage = smem + kChStage + warp * 2048;
+      const float* bvec = bias + 128;
+      uint8_t* const img = (MODE == kPCQ) ? a.qimg : a.kvimg;
+      const uint32_t panel_bytes = (MODE == kPCQ) ? 16384u : 8192u;
+      const uint32_t lo_off = (MODE == kPCQ) ? 32768u : 16384u;
+      const uint32_t base_off = (MODE == kPCQ) ? 0u : 32768u;   // V sits behind K in the tile's image
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int par = it & 1, u = it >> 1;
+        const uint32_t dcol = tmem + lane_base + (uint32_t)par * 256u + 128u;
+        const long long row0 = tile * 128 + q4 * 32;
+        const int b0 = (int)((unsigned)row0 / (unsigned)N);
+        const int n0 = (int)((unsigned)row0 - (unsigned)b0 * (unsigned)N);
+        // image rows of the 4 rows this lane stores in the read-out phase
+        size_t roff[4];
+        uint32_t rx[4];
+        bool rok[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = sub + 4 * i;
-          img_row[i] = nullptr;
-          img_rx[i] = 0;
-          if (row0 + rr < a.rows) {
-            int bb, nn;
-            locate_row(b0, n0, rr, a.N, bb, nn);
-            if (MODE == kPCQ) {
-              const uint32_t rit = (uint32_t)(nn & 127);
-              img_row[i] = a.qimg + ((size_t)bb * a.QT + (nn >> 7)) * 65536 + (rit >> 3) * 1024u + (rit & 7u) * 128u;
-              img_rx[i] = rit & 7u;
-            } else {
-              const uint32_t rit = (uint32_t)(nn & 63);
-              img_row[i] = a.kvimg + ((size_t)bb * a.KT + (nn >> 6)) * 65536 + (rit >> 3) * 1024u + (rit & 7u) * 128u;
-              img_rx[i] = rit & 7u;
-            }
+        for (int i = 0; i < 4; ++i) {
+          const int rr = (lane >> 2) + 8 * i;
+          int bb, nn;
+          locate_row(b0, n0, rr, N, bb, nn);
+          rok[i] = row0 + rr < rows;
+          if (MODE == kPCQ) {
+            const uint32_t rit = (uint32_t)(nn & 127);
+            roff[i] = ((size_t)bb * a.QT + (nn >> 7)) * 65536 + rit * 128u;
+            rx[i] = rit & 7u;
+          } else {
+            const uint32_t rit = (uint32_t)(nn & 63);
+            roff[i] = ((size_t)bb * a.KT + (nn >> 6)) * 65536 + rit * 128u;
+            rx[i] = rit & 7u;
           }
         }
-      }
-
-      if (stamp) PDSC_STAMP1(a.dbg, it, 3, 7);
-        if (stamp) PDSC_STAMP1(a.dbg, it, 2, step * 2);
-        mbar_wait(d_full + 8 * (step * 2 + par), (uint32_t)(u & 1));
-        if (stamp) PDSC_STAMP1(a.dbg, it, 2, step * 2 + 1);
+        mbar_wait(d_full + 8 * (1 * 2 + par), (uint32_t)(u & 1));
         tc_fence_after();
-        if (MODE == kMSG && step == 2) mbar_wait(r_ready, (uint32_t)(it & 1));
-        const int ncols = (MODE == kMSG && step < 2) ? 64 : 128;
-        const uint32_t dstep = (MODE == kMSG) ? (step == 0 ? 0u : (step == 1 ? 64u : 128u)) : (uint32_t)step * 128u;
-        const float* bvec = bias + ((MODE == kMSG) ? (step == 0 ? 0 : (step == 1 ? 64 : 128)) : step * 128);
-        const int cbeg = h * (ncols / 2), cend = cbeg + ncols / 2;
-        const bool chained = (MODE == kPCQ && step == 0) || (MODE == kMSG && step < 2);   // feeds the next MMA
-        if ((MODE == kPCQ && step == 1) || MODE == kKV) {
-          // Q / K / V image -> HBM (V has the K format: rows = keys; the PV MMA reads it as an MN-major B operand).  This thread's 64 columns are exactly one 128-byte panel row (hi) and one (lo): stage
-          // the warp's 32 rows x 128 B, then every store instruction writes four full 128-byte lines.
-          if (stamp && step == 1) PDSC_STAMP1(a.dbg, it, 3, 0);
-          uint32_t hi[32], lo[32];
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            uint32_t raw[32];
-            tmem_ld32(dcol + dstep + cbeg + 32 * cc, raw);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 bv = *reinterpret_cast<const float4*>(bvec + cbeg + 32 * cc + i);
-              split_pair<FMT>(__uint_as_float(raw[i]) + bv.x, __uint_as_float(raw[i + 1]) + bv.y, hi[16 * cc + (i >> 1)],
-                              lo[16 * cc + (i >> 1)]);
-              split_pair<FMT>(__uint_as_float(raw[i + 2]) + bv.z, __uint_as_float(raw[i + 3]) + bv.w,
-                              hi[16 * cc + (i >> 1) + 1], lo[16 * cc + (i >> 1) + 1]);
-            }
-          }
-          if (stamp && step == 1) PDSC_STAMP1(a.dbg, it, 3, 1);
-          const uint32_t panel_off = (uint32_t)h * ((MODE == kPCQ) ? 16384u : 8192u) + ((MODE == kKV && step == 1) ? 32768u : 0u);
-          const uint32_t lo_off = (MODE == kPCQ) ? 32768u : 16384u;
-#pragma unroll
-          for (int part = 0; part < 2; ++part) {
-            if (part == 1 && !a.split) break;
-            __syncwarp();
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const uint32_t* src = part ? lo : hi;
-              *reinterpret_cast<uint4*>(stage + lane * 128 + ((g ^ (lane & 7)) << 4)) =
-                  make_uint4(src[4 * g], src[4 * g + 1], src[4 * g + 2], src[4 * g + 3]);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = sub + 4 * i;
-              const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((piece ^ (rr & 7)) << 4));
-              if (img_row[i]) st_global_v4(img_row[i] + panel_off + (((uint32_t)piece ^ img_rx[i]) << 4) + (part ? lo_off : 0u), val);
-            }
-          }
-          if (stamp && step == 1) PDSC_STAMP1(a.dbg, it, 3, 4);
-        } else
-        for (int c0 = cbeg; c0 < cend; c0 += 32) {
-          const bool st0 = stamp && step == 0 && c0 == cbeg;   // timeline: loader slots 4-7 carry the step-0 epilogue detail
-          if (st0) PDSC_STAMP1(a.dbg, it, 1, 4);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {           // 32 columns = half of one 128-byte image row of panel c >> 1
           uint32_t raw[32];
-          tmem_ld32(dcol + dstep + c0, raw);
+          tmem_ld32(dcol + 32 * c, raw);
           tmem_ld_wait();
-          if (st0) PDSC_STAMP1(a.dbg, it, 3, 2);
-          float x[32];
+          uint32_t hi[16], lo[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(bvec + c0 + i);
-            x[i] = __uint_as_float(raw[i]) + bv.x;
-            x[i + 1] = __uint_as_float(raw[i + 1]) + bv.y;
-            x[i + 2] = __uint_as_float(raw[i + 2]) + bv.z;
-            x[i + 3] = __uint_as_float(raw[i + 3]) + bv.w;
+            const float4 bv = *reinterpret_cast<const float4*>(bvec + 32 * c + i);
+            split_pair<FMT>(__uint_as_float(raw[i]) + bv.x, __uint_as_float(raw[i + 1]) + bv.y, hi[i >> 1], lo[i >> 1]);
+            split_pair<FMT>(__uint_as_float(raw[i + 2]) + bv.z, __uint_as_float(raw[i + 3]) + bv.w, hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
           }
-          if (chained) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
-            // next step's A operand, in place over the columns just read: [hi 16 | lo 16]
+          if (c == 3) {
+            tc_fence_before();
+            mbar_arrive(d1_free + 8 * par);      // D1[par] drained (the values live in registers now)
+          }
+          const uint32_t poff = base_off + (uint32_t)(c >> 1) * panel_bytes;
+          const uint32_t m = (uint32_t)(c & 1);  // which 64-byte half of the 128-byte row
+          stage_store64(stage, lane, hi, [&](int i, int piece) -> void* {
+            return rok[i] ? img + roff[i] + poff + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
+          });
+          if (a.split)
+            stage_store64(stage, lane, lo, [&](int i, int piece) -> void* {
+              return rok[i] ? img + roff[i] + poff + lo_off + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
+            });
+        }
+      }
+    }
+    if (MODE == kMSG) {
+      // ---- the two hidden steps of fc_message: 64 columns each, result parked in place as the next step's A operand ----
+      const int q4 = warp & 3;
+      const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int par = it & 1, u = it >> 1;
+        const uint32_t dcol = tmem + lane_base + (uint32_t)par * 256u;
+#pragma unroll 1
+        for (int step = 0; step < 2; ++step) {
+          mbar_wait(d_full + 8 * (step * 2 + par), (uint32_t)(u & 1));
+          tc_fence_after();
+          const uint32_t dstep = step == 0 ? 0u : 64u;
+          const float* bvec = bias + (step == 0 ? 0 : 64);
+#pragma unroll 1
+          for (int c0 = 0; c0 < 64; c0 += 32) {
+            uint32_t raw[32];
+            tmem_ld32(dcol + dstep + c0, raw);
+            tmem_ld_wait();
             uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) split_pair<FMT>(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
-            if (st0) PDSC_STAMP1(a.dbg, it, 3, 3);
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(bvec + c0 + i);
+              split_pair<FMT>(fmaxf(__uint_as_float(raw[i]) + bv.x, 0.f), fmaxf(__uint_as_float(raw[i + 1]) + bv.y, 0.f), hi[i >> 1], lo[i >> 1]);
+              split_pair<FMT>(fmaxf(__uint_as_float(raw[i + 2]) + bv.z, 0.f), fmaxf(__uint_as_float(raw[i + 3]) + bv.w, 0.f), hi[(i >> 1) + 1],
+                              lo[(i >> 1) + 1]);
+            }
             tmem_st16(dcol + dstep + c0, hi);
             if (a.split) tmem_st16(dcol + dstep + c0 + 16, lo);
-            if (st0) PDSC_STAMP1(a.dbg, it, 1, 5);
           }
-
-          if (MODE == kMSG && step == 2) {
-            // feat = feat1 + fc_message(msg): add the residual in place in the smem tile (store-out below)
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const int c = (c0 >> 2) + g;  // 16-byte chunk index within the 512-byte row
-              float4* slot = reinterpret_cast<float4*>(resq + lane * 512 + (((c & ~7) | ((c ^ lane) & 7)) << 4));
-              float4 rv = *slot;
-              rv.x += x[g * 4]; rv.y += x[g * 4 + 1]; rv.z += x[g * 4 + 2]; rv.w += x[g * 4 + 3];
-              *slot = rv;
-            }
-          }
-          if (MODE == kPCQ && step == 0) {
-            // feat1 fp32 -> HBM through the staging buffer (full-line stores)
-            __syncwarp();
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              *reinterpret_cast<float4*>(stage + lane * 128 + ((g ^ (lane & 7)) << 4)) =
-                  make_float4(x[g * 4], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = sub + 4 * i;
-              const long long g = row0 + rr;
-              const float4 val = *reinterpret_cast<const float4*>(stage + rr * 128 + ((piece ^ (rr & 7)) << 4));
-              if (g < a.rows) *reinterpret_cast<float4*>(a.out_f32 + g * kC + c0 + piece * 4) = val;
-            }
-            if (st0) PDSC_STAMP1(a.dbg, it, 1, 6);
-          }
-        }
-        if (chained) {
           tmem_st_wait();        // A operand written through tcgen05.st, read by the tensor core
           tc_fence_before();
           mbar_arrive(a1_ready);
-          if (stamp && step == 0) PDSC_STAMP1(a.dbg, it, 1, 7);
         }
-    };
-    if (MODE == kPCQ) {
-      // Software-pipelined order  E0(t), E1(t-1), E0(t+1), E1(t), ...: the step-1 MMA of tile t (which needs E0(t)'s
-      // output) runs under E1(t-1), so the epilogue warps never sit waiting for the tensor core.
-      long long prev = -1;
-      int it = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        run_step(tile, it, 0);
-        if (it > 0) {
-          run_step(prev, it - 1, 1);
-          tc_fence_before();
-          mbar_arrive(d_free + 8 * ((it - 1) & 1));   // D1[par] drained
-        }
-        prev = tile;
       }
-      if (it > 0) {
-        run_step(prev, it - 1, 1);
-        tc_fence_before();
-        mbar_arrive(d_free + 8 * ((it - 1) & 1));
-      }
-    } else {
-      int it = 0;
-      for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int par = it & 1;
-        const long long row0 = tile * 128 + q4 * 32;
+    }
+  } else {
+    // =================================== group A: thread = row ===================================
+    const int q4 = warp & 3;
+    const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
+    uint8_t* stage = smem + kChStage + warp * 2048;          // PCQ / KV
+    uint8_t* resq = smem + kChRes + q4 * 32 * 512;           // MSG: the 32 residual rows of this lane quarter
+    const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int par = it & 1, u = it >> 1;
+      const uint32_t dcol = tmem + lane_base + (uint32_t)par * 256u;
+      const long long row0 = tile * 128 + q4 * 32;          // first global row of this lane quarter
+      if (MODE == kPCQ) {
+        // ---- PointCN: feat1 = relu(D0 + b1)  ->  HBM (fp32) and tensor memory (16-bit hi | lo operand of the Q GEMM) ----
+        if (stamp) PDSC_STAMP1(a.dbg, it, 2, 0);
+        mbar_wait(d_full + 8 * (0 * 2 + par), (uint32_t)(u & 1));
+        if (stamp) PDSC_STAMP1(a.dbg, it, 2, 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c0 = 32 * cc;
+          uint32_t raw[32];
+          tmem_ld32(dcol + c0, raw);
+          tmem_ld_wait();
+          uint32_t xb[32];
 #pragma unroll
-        for (int step = 0; step < kSteps; ++step) run_step(tile, it, step);
-        if (MODE == kMSG) {
-          // store the finished fp32 tile: one full 512-byte row per instruction, 16 rows per warp
-          quarter_sync(q4);  // both column halves of these 32 rows are in place
-#pragma unroll 4
-          for (int i = 0; i < 16; ++i) {
-            const int rr = 16 * h + i;
-            const long long g = row0 + rr;
-            const float4 val = *reinterpret_cast<const float4*>(resq + rr * 512 + (((lane & ~7) | ((lane ^ rr) & 7)) << 4));
-            if (g < a.rows) *reinterpret_cast<float4*>(a.out_f32 + g * kC + lane * 4) = val;
+          for (int i = 0; i < 32; i += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(bias + c0 + i);
+            xb[i] = __float_as_uint(fmaxf(__uint_as_float(raw[i]) + bv.x, 0.f));
+            xb[i + 1] = __float_as_uint(fmaxf(__uint_as_float(raw[i + 1]) + bv.y, 0.f));
+            xb[i + 2] = __float_as_uint(fmaxf(__uint_as_float(raw[i + 2]) + bv.z, 0.f));
+            xb[i + 3] = __float_as_uint(fmaxf(__uint_as_float(raw[i + 3]) + bv.w, 0.f));
           }
-          mbar_arrive(r_free);
+          {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split_pair<FMT>(__uint_as_float(xb[2 * i]), __uint_as_float(xb[2 * i + 1]), hi[i], lo[i]);
+            tmem_st16(dcol + c0, hi);
+            if (a.split) tmem_st16(dcol + c0 + 16, lo);
+          }
+          if (cc == 3) {
+            tmem_st_wait();        // A operand written through tcgen05.st, read by the tensor core
+            tc_fence_before();
+            mbar_arrive(a1_ready);
+            if (stamp) PDSC_STAMP1(a.dbg, it, 2, 2);
+          }
+          // fp32 rows -> HBM, 16 columns (64 B) at a time
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t seg[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) seg[i] = xb[16 * hf + i];
+            stage_store64(stage, lane, seg, [&](int i, int piece) -> void* {
+              const long long g = row0 + (lane >> 2) + 8 * i;
+              return g < rows ? (void*)(a.out_f32 + g * kC + c0 + 16 * hf + piece * 4) : nullptr;
+            });
+          }
         }
-        tc_fence_before();
-        mbar_arrive(d_free + 8 * par);  // D[par] drained
+        if (stamp) PDSC_STAMP1(a.dbg, it, 2, 3);
+      } else if (MODE == kKV) {
+        // ---- K image: 32 columns = half of one 128-byte image row of panel c >> 1 ----
+        const int b0 = (int)((unsigned)row0 / (unsigned)N);
+        const int n0 = (int)((unsigned)row0 - (unsigned)b0 * (unsigned)N);
+        size_t roff[4];
+        uint32_t rx[4];
+        bool rok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int rr = (lane >> 2) + 8 * i;
+          int bb, nn;
+          locate_row(b0, n0, rr, N, bb, nn);
+          rok[i] = row0 + rr < rows;
+          const uint32_t rit = (uint32_t)(nn & 63);
+          roff[i] = ((size_t)bb * a.KT + (nn >> 6)) * 65536 + rit * 128u;
+          rx[i] = rit & 7u;
+        }
+        mbar_wait(d_full + 8 * (0 * 2 + par), (uint32_t)(u & 1));
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(dcol + 32 * c, raw);
+          tmem_ld_wait();
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(bias + 32 * c + i);
+            split_pair<FMT>(__uint_as_float(raw[i]) + bv.x, __uint_as_float(raw[i + 1]) + bv.y, hi[i >> 1], lo[i >> 1]);
+            split_pair<FMT>(__uint_as_float(raw[i + 2]) + bv.z, __uint_as_float(raw[i + 3]) + bv.w, hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
+          }
+          if (c == 3) {
+            tc_fence_before();
+            mbar_arrive(d0_free + 8 * par);
+          }
+          const uint32_t poff = (uint32_t)(c >> 1) * 8192u;
+          const uint32_t m = (uint32_t)(c & 1);
+          stage_store64(stage, lane, hi, [&](int i, int piece) -> void* {
+            return rok[i] ? a.kvimg + roff[i] + poff + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
+          });
+          if (a.split)
+            stage_store64(stage, lane, lo, [&](int i, int piece) -> void* {
+              return rok[i] ? a.kvimg + roff[i] + poff + 16384u + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
+            });
+        }
+      } else {
+        // ---- MSG, last step: feat = feat1 + (D2 + bm2), through the residual tile in shared memory ----
+        mbar_wait(d_full + 8 * (2 * 2 + par), (uint32_t)(u & 1));
+        tc_fence_after();
+        mbar_wait(r_ready, (uint32_t)(it & 1));
+        const float* bvec = bias + 128;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(dcol + 128 + c0, raw);
+          tmem_ld_wait();
+          if (c0 == 96) {
+            tc_fence_before();
+            mbar_arrive(d0_free + 8 * par);  // D2[par] drained
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 bv = *reinterpret_cast<const float4*>(bvec + c0 + 4 * g);
+            const int c = (c0 >> 2) + g;  // 16-byte chunk index within the 512-byte row
+            float4* slot = reinterpret_cast<float4*>(resq + lane * 512 + (((c & ~7) | ((c ^ lane) & 7)) << 4));
+            float4 rv = *slot;
+            rv.x += __uint_as_float(raw[g * 4]) + bv.x; rv.y += __uint_as_float(raw[g * 4 + 1]) + bv.y;
+            rv.z += __uint_as_float(raw[g * 4 + 2]) + bv.z; rv.w += __uint_as_float(raw[g * 4 + 3]) + bv.w;
+            *slot = rv;
+          }
+        }
+        // store the finished fp32 rows: one full 512-byte row per instruction
+        __syncwarp();
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const long long g = row0 + rr;
+          const float4 val = *reinterpret_cast<const float4*>(resq + rr * 512 + (((lane & ~7) | ((lane ^ rr) & 7)) << 4));
+          if (g < rows) *reinterpret_cast<float4*>(a.out_f32 + g * kC + lane * 4) = val;
+        }
+        mbar_arrive(r_free);
       }
     }
   }
