@@ -111,7 +111,6 @@ class PointDSC(nn.Module):
         self._engine_device = None
         self._pushed_signature = None
         self._workspace = None
-        self._host_out = None
 
     # ------------------------------------------------------------------------------------------
     # engine plumbing
@@ -219,16 +218,15 @@ class PointDSC(nn.Module):
             if taps or inject:
                 raise ValueError("taps / inject need device tensors")
             cp, s, t = (x.to(torch.float32).contiguous() for x in (corr_pos, src_keypts, tgt_keypts))
-            # pinned result staging is allocated once per shape (cudaHostAlloc costs milliseconds), results are copied out
-            if self._host_out is None or self._host_out[0].shape != (B, 4, 4) or self._host_out[1].shape != (B, N):
-                self._host_out = (torch.empty(B, 4, 4, dtype=torch.float32).pin_memory(),
-                                  torch.empty(B, N, dtype=torch.float32).pin_memory())
-            trans, labels = self._host_out
+            # fresh caller-owned result tensors, written by the library's device->host copies (pageable destination: the
+            # 1 MB copy is staged by the driver; a torch-side clone out of a pinned buffer costs more than the copy itself)
+            trans = torch.empty(B, 4, 4, dtype=torch.float32)
+            labels = torch.empty(B, N, dtype=torch.float32)
             with torch.cuda.device(dev):
                 _capi.check(lib.pdsc_forward_host(self._engine, B, N, C.c_void_p(cp.data_ptr()), C.c_void_p(s.data_ptr()),
                                                   C.c_void_p(t.data_ptr()), C.c_void_p(trans.data_ptr()),
                                                   C.c_void_p(labels.data_ptr()), stream))
-            return {"final_trans": trans.clone(), "final_labels": labels.clone()}
+            return {"final_trans": trans, "final_labels": labels}
         if corr_pos.device != dev:
             raise ValueError(f"inputs are on {corr_pos.device}, module is on {dev}")
         cp, s, t = (x.to(torch.float32).contiguous() for x in (corr_pos, src_keypts, tgt_keypts))
