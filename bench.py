@@ -291,6 +291,9 @@ def run_engine(args, rank, world, local_rank):
     attn_ms, attn_launches = prof["attention"]
     flops_per_launch = 4.0 * 128 * N * N * B          # QK^T + PV of one layer over the rank's B sets (algorithmic)
     achieved = flops_per_launch / (attn_ms / max(attn_launches, 1) * 1e-3) / 1e12 if attn_ms > 0 else None
+    ns = (N + 63) // 64 * 64
+    hbm_bytes = 4.0 * N * ns * B + 4.0 * 128 * N * B * 3 + 4.0 * 128 * N * B   # SC tiles + Q,K,V images (hi+lo) + msg
+    hbm_gbs = hbm_bytes / (attn_ms / max(attn_launches, 1) * 1e-3) / 1e9 if attn_ms > 0 else None
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "attention_traffic.json")))
@@ -304,6 +307,9 @@ def run_engine(args, rank, world, local_rank):
                 "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_flops_per_launch": flops_per_launch, "launch_ms": attn_ms / max(attn_launches, 1),
                 "launches_timed": attn_launches,
+                # the same launch seen from the memory side: SC (re-read by every layer) + Q/K/V images + msg
+                "hbm_algorithmic_bytes_per_launch": hbm_bytes, "hbm_achieved_gbs": hbm_gbs,
+                "hbm_frac_of_copy_peak": (hbm_gbs / float(peaks.get("hbm_gbs", 6568.4))) if hbm_gbs else None,
                 "note": f"algorithmic FLOPs = 4*C*N^2*B per layer; {args.precision} executes {executed}x that on the tensor pipe"}
     total_ms = prof["total"][0]
     stages = {k: {"ms_per_step": v[0] / args.steps, "share": (v[0] / total_ms if total_ms > 0 else None)}
