@@ -11,7 +11,7 @@ namespace pdsc {
 void launch_sc_matrix(const float* src, const float* tgt, float* sc, int B, int N, int NS, float sigma_d,
                       cudaStream_t st);
 
-// tensor-core path: sc_t[b][kt][qt][64][128] tiles (see sc_matrix.cu); size B * ceil(N/64) * ceil(N/128) * 8192 floats
+// tensor-core path: sc_t[b][kt][qt][16][128][4] tiles (see sc_matrix.cu); size B * ceil(N/64) * ceil(N/128) * 8192 floats
 void launch_sc_matrix_tiled(const float* src, const float* tgt, float* sc, int B, int N, float sigma_d, cudaStream_t st);
 void launch_sc_untile(const float* sc_t, float* out, int B, int N, cudaStream_t st);
 

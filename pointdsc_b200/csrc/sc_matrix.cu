@@ -56,9 +56,10 @@ void launch_sc_matrix(const float* src, const float* tgt, float* sc, int B, int 
 }
 
 // ---- tiled layout for the tensor-core attention (tc_attention.cuh) ---------------------------------------
-// sc_t[b][kt][qt][64 keys][128 queries]: every (64-key x 128-query) tile the attention CTA (b, qt) consumes at key
-// step kt is one contiguous 32 KB block, so a softmax thread (query row r) reads its 32 SC values at compile-time
-// offsets from one per-tile base pointer, coalesced over the 128 rows, with no per-element address arithmetic.
+// sc_t[b][kt][qt][16 key groups][128 queries][4 keys]: every (64-key x 128-query) tile the attention CTA (b, qt) consumes
+// at key step kt is one contiguous 32 KB block, and inside it the 4 keys of a group are adjacent, so a softmax thread
+// (query row r) reads its 64 SC values as 16 fully coalesced 16-byte loads at compile-time offsets (g * 2048 B) from one
+// per-tile base pointer — no per-element address arithmetic, a quarter of the load instructions of a [key][query] tile.
 // SC is exactly symmetric in fp32 ((x_i - x_j)^2 == (x_j - x_i)^2), so element (key, q) is computed as SC[q][key].
 // Pad rows / columns (key >= N or q >= N) are written as 0.
 // One CTA = one 128 x 128 super-block (A <= Bq) of one set: it evaluates V[i][j] = SC[128 A + i][128 Bq + j] ONCE and
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(256) sc_matrix_tiled_kernel(const float* __res
     // orientation 1: key = 128 A + i, query = j   ->  tile (kt = 2 A + (ic >> 1), qt = Bq), element [(i & 63)][jl]
     const int kt1 = 2 * A + (ic >> 1);
     const int il0 = ic * 32 + half * 16;
-    float* out1 = sc + ((set_base + (size_t)min(kt1, KT - 1) * QT + Bq) << 13) + (il0 & 63) * 128 + jl;
+    float* out1 = sc + ((set_base + (size_t)min(kt1, KT - 1) * QT + Bq) << 13) + (((il0 & 63) >> 2) * 128 + jl) * 4;
     float* trw = tr + (half * 16) * kScTStride + jl;
     const bool col_ok = j < N;
     const int i_lim = N - A * 128 - il0;       // rows ii < i_lim are real correspondences
@@ -109,20 +110,23 @@ __global__ void __launch_bounds__(256) sc_matrix_tiled_kernel(const float* __res
       vals[ii] = (col_ok && ii < i_lim) ? v : 0.0f;
     }
     if (kt1 < KT) {
+      // keys (il0 & 63) + ii, ii < 16: four key groups, each one float4 per query
 #pragma unroll
-      for (int ii = 0; ii < 16; ++ii) out1[ii * 128] = vals[ii];
+      for (int gq = 0; gq < 4; ++gq)
+        *reinterpret_cast<float4*>(out1 + gq * 512) = make_float4(vals[4 * gq], vals[4 * gq + 1], vals[4 * gq + 2], vals[4 * gq + 3]);
     }
     if (A != Bq) {
 #pragma unroll
       for (int ii = 0; ii < 16; ++ii) trw[ii * kScTStride] = vals[ii];
       __syncthreads();
-      // orientation 2: key = 128 Bq + j, query = 128 A + i  ->  tile (kt = 2 Bq + (j >> 6), qt = A), element [(j & 63)][i]
+      // orientation 2: key = 128 Bq + j, query = 128 A + i  ->  tile (kt = 2 Bq + (j >> 6), qt = A), element (j & 63, i)
       const int kt2 = 2 * Bq + (tg >> 2);      // the warp's 16 j share one key tile
       if (kt2 < KT) {
-        float* out2 = sc + ((set_base + (size_t)kt2 * QT + A) << 13) + ((tg & 3) * 16) * 128 + ic * 32 + ti;
+        float* out2 = sc + ((set_base + (size_t)kt2 * QT + A) << 13) + (((tg & 3) * 4) * 128 + ic * 32 + ti) * 4;
         const float* trr = tr + ti * kScTStride + tg * 16;
 #pragma unroll
-        for (int jj = 0; jj < 16; ++jj) out2[jj * 128] = trr[jj];
+        for (int gq = 0; gq < 4; ++gq)
+          *reinterpret_cast<float4*>(out2 + gq * 512) = make_float4(trr[4 * gq], trr[4 * gq + 1], trr[4 * gq + 2], trr[4 * gq + 3]);
       }
       __syncthreads();
     }
@@ -141,7 +145,7 @@ __global__ void sc_untile_kernel(const float* __restrict__ sc_t, float* __restri
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N) return;
   const float* tile = sc_t + ((((size_t)b * KT + (i >> 6)) * QT + (j >> 7)) << 13);
-  out[((size_t)b * N + i) * N + j] = tile[(i & 63) * 128 + (j & 127)];
+  out[((size_t)b * N + i) * N + j] = tile[((((i & 63) >> 2) * 128 + (j & 127)) << 2) + (i & 3)];
 }
 void launch_sc_untile(const float* sc_t, float* out, int B, int N, cudaStream_t st) {
   const int KT = (N + 63) / 64, QT = (N + 127) / 128;

@@ -26,7 +26,7 @@ struct AttnArgs {
   int N, NS, QT, KT, split;
   const uint8_t* qimg;
   const uint8_t* kvimg;
-  const float* sc;    // tiled: [B][KT][QT][64 keys][128 queries]
+  const float* sc;    // tiled: [B][KT][QT][16 key groups][128 queries][4 keys]
   float* msg;
   long long* dbg;
   int items;          // B * QT work items (persistent kernel)
@@ -56,6 +56,19 @@ __device__ __forceinline__ float ldg_stream(const float* p) {
   float v;
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
+}
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+// this thread's (query row r) 64 SC values of one tile [16 key groups][128 queries][4 keys]: 16 coalesced 16-byte loads
+__device__ __forceinline__ void load_sc_tile(float (&sc)[64], const float* tile, int r) {
+#pragma unroll
+  for (int g = 0; g < 16; ++g) {
+    const float4 v = ldg_stream4(tile + (g * 128 + r) * 4);
+    sc[4 * g] = v.x; sc[4 * g + 1] = v.y; sc[4 * g + 2] = v.z; sc[4 * g + 3] = v.w;
+  }
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -261,8 +274,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
     const int r = q4 * 32 + lane;            // query row within the tile == TMEM lane
     const int gt = (warp - 2 - 4 * g) * 32 + lane;   // thread index within the group
     const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
-    // SC tiles of this CTA: sc_t[b][j][qt][64 keys][128 queries]; thread r reads element (c, r) of tile j at the
-    // compile-time offset c * 512 B from one per-tile pointer, coalesced over the 128 rows.
+    // SC tiles of this CTA: sc_t[b][j][qt][16 key groups][128 queries][4 keys]; thread r reads its 64 values of tile j at the
+    // compile-time offsets g * 2048 B (16 float4 loads) from one per-tile pointer, coalesced over the 128 rows.
     const size_t tile_stride = (size_t)a.QT << 13;
     const float* sc_cta = a.sc + ((((size_t)b * a.KT) * a.QT + qt) << 13);
     const float* sc_line = sc_cta + gt * 32;   // two 128-byte lines of each 32 KB tile per thread (L2 prefetch)
@@ -272,9 +285,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
 
     float sc[64];
     if (g < T) {
-      const float* p0 = sc_cta + (size_t)g * tile_stride + r;
-#pragma unroll
-      for (int c = 0; c < 64; ++c) sc[c] = ldg_stream(p0 + c * 128);
+      load_sc_tile(sc, sc_cta + (size_t)g * tile_stride, r);
     }
     if (g + 2 < T) { prefetch_l2(sc_line + (size_t)(g + 2) * tile_stride); prefetch_l2(sc_line + (size_t)(g + 2) * tile_stride + 4096); }
     // Q image: shared memory (landed by bulk copy) -> tensor memory, this thread's row; group 0 moves the hi image,
@@ -321,9 +332,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
         for (int c = 0; c < 64; ++c) l[c] = (j * 64 + c < a.N) ? l[c] : -INFINITY;
       }
       if (j + 2 < T) {  // the SC registers are dead: refill them with this group's next tile under the rest of the work
-        const float* pn = sc_cta + (size_t)(j + 2) * tile_stride + r;
-#pragma unroll
-        for (int c = 0; c < 64; ++c) sc[c] = ldg_stream(pn + c * 128);
+        load_sc_tile(sc, sc_cta + (size_t)(j + 2) * tile_stride, r);
       }
       float tmax = l[0];
 #pragma unroll

@@ -5,16 +5,21 @@
 //     P = softmax_j( SC_ij * (q_i . k_j) / sqrt(C) ),   msg_i = sum_j P_ij v_j          (heads = 1, C = 128)
 // SC multiplies the logit (it is not a mask): SC_ij = 0 leaves logit 0, which still takes softmax mass.
 //
-// The per-item machinery is that of tc_attention.cuh (Q and P as A operands in tensor memory, S = Q K^T as N = 128 MMAs over
-// pairs of 64-key tiles, two softmax groups on alternate key tiles with the running row maximum handed over through
-// shared memory, lazy rescale of O).  What is new is that NOTHING is torn down between items: barriers keep their phase
-// (running use counts), the K / V rings and the S / P buffers keep rotating, and
+// The per-item machinery is that of tc_attention.cuh (Q and P as A operands in tensor memory, two softmax groups on
+// alternate key tiles with the running row maximum handed over through shared memory, lazy rescale of O), except that
+// S = Q K^T is issued and committed per 64-key tile (N = 64: the tensor time is the same as for N = 128 pairs, but the two
+// groups receive their tiles at different times and stay staggered instead of contending for the same pipes in the same
+// phase).  What is new is that NOTHING is torn down between items: barriers keep their phase (running use counts or
+// explicit phase bits), the K / V rings and the S / P buffers keep rotating, and
 //   * the loader streams the next item's K / V tiles and its Q image (through a 32 KB staging buffer, hi then lo half)
 //     while the current item is still being computed;
 //   * the softmax groups move the next Q into tensor memory right after their last tile of the current item (the Q
 //     columns are free once the item's last QK pair has completed);
-//   * the MMA warp issues the next item's first two QK pairs directly behind the current item's last PV, so the tensor
-//     core works on them while the softmax groups drain O (registers -> global, no shared-memory staging).
+//   * the MMA warp issues the next item's first four QK tiles directly behind the current item's last PV, so the tensor
+//     core works on them while the softmax groups drain O;
+//   * in the MMA warp every normally-satisfied wait (K pair, V tile, O drained) is taken before the wait for P_j, so one
+//     mbarrier wake-up separates a group's arrival from the PV_j / QK_{j+4} issue (a satisfied wait still costs
+//     200-300 cycles on a sub-partition shared with two busy softmax warps).
 // Per-item fixed cost drops from ~14 k cycles (TMEM allocation, barrier set-up, cold Q / K / SC loads, output drain,
 // CTA launch) to the ~2 k-cycle output drain.
 #pragma once
@@ -22,12 +27,13 @@
 
 namespace pdsc {
 
-constexpr int kAttnPK = 0;                                   // K: 2 pair stages x 64 KB
-constexpr int kAttnPV = 131072;                              // V: 2 tile stages x 32 KB
+constexpr int kAttnPK = 0;                                   // K: 3 tile stages x 32 KB ([hi p0][hi p1][lo p0][lo p1], 8 KB each)
+constexpr int kAttnPV = 98304;                               // V: 3 tile stages x 32 KB
 constexpr int kAttnPQ = 196608;                              // Q staging: one 32 KB half image
 constexpr int kAttnPBars = 229376;
-constexpr int kAttnPRef = kAttnPBars + 256;                  // float ref[2][128], lsum[2][128]
-constexpr int kAttnPSmem = kAttnPRef + 2048;                 // 231,680 B (limit 232,448)
+constexpr int kAttnPRef = kAttnPBars + 320;                  // float ref[2][128], lsum[2][128]
+constexpr int kAttnPSmem = kAttnPRef + 2048;                 // 231,744 B (limit 232,448)
+constexpr int kAttnRing = 3;                                 // K / V ring depth: a stage freed by MMA t is refilled for tile t + 3
 
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory"); }
 
@@ -35,38 +41,41 @@ template <int FMT>
 __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kernel(AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAttnPBars);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
   float* ref_s = reinterpret_cast<float*>(smem + kAttnPRef);  // [2][128] reference maximum after tile j (slot j & 1)
   float* lsum_s = ref_s + 256;                                // [2][128] per-group row sums (epilogue)
   const uint32_t s0 = smem_u32(smem);
-  const uint32_t k_full = smem_u32(bars + 0), k_empty = smem_u32(bars + 2);      // [2] per pair stage
-  const uint32_t v_full = smem_u32(bars + 4), v_empty = smem_u32(bars + 6);      // [2] per tile stage
-  const uint32_t s_full = smem_u32(bars + 8);                                    // [2] per S pair buffer
-  const uint32_t p_full = smem_u32(bars + 10);                                   // [4] per S/P tile buffer
-  const uint32_t pv_done = smem_u32(bars + 14), ref_ready = smem_u32(bars + 16); // [2]
-  const uint32_t qh_full = smem_u32(bars + 18), ql_full = smem_u32(bars + 19);   // staging holds the hi / lo half image
-  const uint32_t qh_used = smem_u32(bars + 20), ql_used = smem_u32(bars + 21);   // ... and has been moved to TMEM
-  const uint32_t q_tmem = smem_u32(bars + 22), o_done = smem_u32(bars + 23), o_free = smem_u32(bars + 24);
-  const uint32_t stage_free = smem_u32(bars + 25);   // the item's output has left the staging buffer
+  const uint32_t k_full = smem_u32(bars + 0), k_empty = smem_u32(bars + 3);      // [3] per K tile stage
+  const uint32_t v_full = smem_u32(bars + 6), v_empty = smem_u32(bars + 9);      // [3] per V tile stage
+  const uint32_t p_full = smem_u32(bars + 12), s_full = smem_u32(bars + 16);     // [4] per S/P tile buffer
+  const uint32_t pv_done = smem_u32(bars + 20), ref_ready = smem_u32(bars + 22); // [2]
+  const uint32_t qh_full = smem_u32(bars + 24), ql_full = smem_u32(bars + 25);   // staging holds the hi / lo half image
+  const uint32_t qh_used = smem_u32(bars + 26), ql_used = smem_u32(bars + 27);   // ... and has been moved to TMEM
+  const uint32_t q_tmem = smem_u32(bars + 28), o_done = smem_u32(bars + 29), o_free = smem_u32(bars + 30);
+  const uint32_t stage_free = smem_u32(bars + 31);   // the item's output has left the staging buffer
+  const uint32_t qk_done = smem_u32(bars + 32);      // the item's last QK has completed: the Q columns are free
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int T = a.KT, TP = (a.KT + 1) >> 1;
+  const int T = a.KT;
   const int TE = (T + 1) >> 1, TO = T >> 1;                   // tiles per item with even / odd index
   const int my_items = (a.items > (int)blockIdx.x) ? (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
+  const long long t_begin = (a.dbg != nullptr) ? clock64() : 0;
+  unsigned long long ns_begin = 0;
+  if (a.dbg != nullptr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
   if (tid == 0) {
     if (s0 & 1023u) {
       printf("pointdsc_b200: dynamic shared memory is not 1024-byte aligned\n");
       __trap();
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAttnRing; ++i) {
       mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 1);
       mbar_init(v_full + 8 * i, 1); mbar_init(v_empty + 8 * i, 1);
-      mbar_init(s_full + 8 * i, 1);
-      mbar_init(pv_done + 8 * i, 1); mbar_init(ref_ready + 8 * i, 128);
     }
-    for (int i = 0; i < 4; ++i) mbar_init(p_full + 8 * i, 128);
+    for (int i = 0; i < 2; ++i) { mbar_init(pv_done + 8 * i, 1); mbar_init(ref_ready + 8 * i, 128); }
+    for (int i = 0; i < 4; ++i) { mbar_init(p_full + 8 * i, 128); mbar_init(s_full + 8 * i, 1); }
     mbar_init(qh_full, 1); mbar_init(ql_full, 1);
     mbar_init(qh_used, 128); mbar_init(ql_used, 128);
+    mbar_init(qk_done, 1);
     mbar_init(q_tmem, 256); mbar_init(o_done, 1); mbar_init(o_free, 256); mbar_init(stage_free, 256);
     fence_barrier_init();
   }
@@ -82,43 +91,31 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
     // ===================================== loader =====================================
     if (lane == 0) {
       // three independent streams over this CTA's items, each gated only by its own ring / staging slot
-      int ki = 0, kp = 0, gk = 0;        // K: item ordinal, pair within the item, global pair count
-      int vi = 0, vj = 0, gv = 0;        // V: item ordinal, tile within the item, global tile count
-      int qi = 0, qh = 0;                // Q: item ordinal, half (0 = hi, 1 = lo)
+      int ki = 0, kj = 0, kst = 0, kuse = 0;   // K: item ordinal, tile within the item, ring stage and its use count
+      int vi = 0, vj = 0, vst = 0, vuse = 0;   // V: the same
+      int qi = 0, qh = 0;                      // Q: item ordinal, half (0 = hi, 1 = lo)
       const int qhalves = a.split ? 2 : 1;
+      const uint32_t tile_bytes = a.split ? 32768u : 16384u;   // hi (+ lo) image of one 64-key tile
       while (ki < my_items || vi < my_items || qi < my_items) {
         bool progress = false;
         if (ki < my_items) {
-          const int st = gk & 1, use = gk >> 1;
-          if (use == 0 || mbar_test(k_empty + 8 * st, (uint32_t)((use - 1) & 1))) {
+          if (kuse == 0 || mbar_test(k_empty + 8 * kst, (uint32_t)((kuse - 1) & 1))) {
             const int item = blockIdx.x + ki * gridDim.x;
-            const uint8_t* kv = a.kvimg + (size_t)(item / a.QT) * a.KT * 65536;
-            const int ntiles = (2 * kp + 1 < T) ? 2 : 1;
-            mbar_expect_tx(k_full + 8 * st, (a.split ? 32768u : 16384u) * ntiles);
-            for (int hh = 0; hh < ntiles; ++hh) {
-              const uint8_t* src = kv + (size_t)(2 * kp + hh) * 65536;
-              const uint32_t dst = s0 + kAttnPK + st * 65536 + hh * 8192;
-              bulk_g2s(dst, src, 8192u, k_full + 8 * st);                          // hi, channels 0-63
-              bulk_g2s(dst + 16384, src + 8192, 8192u, k_full + 8 * st);           // hi, channels 64-127
-              if (a.split) {
-                bulk_g2s(dst + 32768, src + 16384, 8192u, k_full + 8 * st);        // lo
-                bulk_g2s(dst + 49152, src + 24576, 8192u, k_full + 8 * st);
-              }
-            }
-            ++gk;
-            if (++kp == TP) { kp = 0; ++ki; }
+            const uint8_t* kv = a.kvimg + ((size_t)(item / a.QT) * a.KT + kj) * 65536;
+            mbar_expect_tx(k_full + 8 * kst, tile_bytes);
+            bulk_g2s(s0 + kAttnPK + kst * 32768, kv, tile_bytes, k_full + 8 * kst);
+            if (++kst == kAttnRing) { kst = 0; ++kuse; }
+            if (++kj == T) { kj = 0; ++ki; }
             progress = true;
           }
         }
         if (vi < my_items) {
-          const int st = gv & 1, use = gv >> 1;
-          if (use == 0 || mbar_test(v_empty + 8 * st, (uint32_t)((use - 1) & 1))) {
+          if (vuse == 0 || mbar_test(v_empty + 8 * vst, (uint32_t)((vuse - 1) & 1))) {
             const int item = blockIdx.x + vi * gridDim.x;
-            const uint8_t* kv = a.kvimg + (size_t)(item / a.QT) * a.KT * 65536;
-            const uint32_t half = a.split ? 32768u : 16384u;
-            mbar_expect_tx(v_full + 8 * st, half);
-            bulk_g2s(s0 + kAttnPV + st * 32768, kv + (size_t)vj * 65536 + 32768, half, v_full + 8 * st);
-            ++gv;
+            const uint8_t* kv = a.kvimg + ((size_t)(item / a.QT) * a.KT + vj) * 65536 + 32768;
+            mbar_expect_tx(v_full + 8 * vst, tile_bytes);
+            bulk_g2s(s0 + kAttnPV + vst * 32768, kv, tile_bytes, v_full + 8 * vst);
+            if (++vst == kAttnRing) { vst = 0; ++vuse; }
             if (++vj == T) { vj = 0; ++vi; }
             progress = true;
           }
@@ -142,52 +139,66 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
             progress = true;
           }
         }
-        if (!progress) __nanosleep(64);
+        if (!progress) __nanosleep(400);   // the rings turn over every ~2.5k cycles: poll rarely, the issue slots are the softmax warps'
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ===================================== MMA issuer =====================================
     const bool leader = elect_one();
-    auto issue_qk_pair = [&](int G) {   // global pair G: S tiles in columns 128 (G & 1) ... = Q K^T over 128 keys
-      const int st = G & 1, use = G >> 1;
-      mbar_wait(k_full + 8 * st, (uint32_t)(use & 1));
-      tc_fence_after();
+    // S_t = Q K_t^T for ONE 64-key tile (N = 64, 24 MMAs of 32 cycles) into S/P buffer t & 3, t the CTA's running tile
+    // count.  One commit per tile: the two softmax groups receive their tiles 768 tensor cycles apart and stay staggered
+    // (with N = 128 pairs both groups ran the same phase at the same time and contended for the same pipes).
+    // QK runs kAttnRing tiles ahead of PV: behind PV_j (in-order execution) tile j + 3 overwrites the S/P buffer that
+    // PV_{j-1} has read, from the K stage that QK_j released.
+    int qst = 0;                                   // K ring stage of the next QK
+    auto issue_qk_tile = [&](int gt, bool last) {  // gt: running tile count; last: the item's final tile
+      const int buf = gt & 3;
       if (leader) {
-        const uint32_t kb = s0 + kAttnPK + st * 65536;
-        issue_gemm_ts<2, 128>(tmem + 128 * st, tQ, tQ + 64, kb, kb + 32768, 16384, a.split, 0, FMT);
-        mma_commit(s_full + 8 * st);
-        mma_commit(k_empty + 8 * st);
+        const uint32_t kb = s0 + kAttnPK + qst * 32768;
+        issue_gemm_ts<2, 64>(tmem + 64 * buf, tQ, tQ + 64, kb, kb + 16384, 8192, a.split, 0, FMT);
+        mma_commit(s_full + 8 * buf);
+        mma_commit(k_empty + 8 * qst);
+        if (last) mma_commit(qk_done);
       }
+      if (++qst == kAttnRing) qst = 0;
     };
-    int gv = 0;
+    int gv = 0, vst = 0;
     const bool stamp_mma = leader && a.dbg != nullptr && blockIdx.x == 0;
     for (int it = 0; it < my_items; ++it) {
-      const int gkb = it * TP;
+      const int gtb = it * T;
+      // the item's first tiles: K resident (the later ones are vouched for by the softmax groups, see below)
+      for (int j = 0; j < T && j < kAttnRing; ++j) {
+        const int g3 = gtb + j;
+        mbar_wait(k_full + 8 * (g3 % kAttnRing), (uint32_t)((g3 / kAttnRing) & 1));
+      }
       mbar_wait(q_tmem, (uint32_t)(it & 1));   // this item's Q (hi | lo images) is resident in tensor memory
       tc_fence_after();
       if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 0);
-      for (int p = 0; p < TP && p < 2; ++p) issue_qk_pair(gkb + p);
+      for (int j = 0; j < T && j < kAttnRing; ++j) issue_qk_tile(gtb + j, j == T - 1);
       if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 1);
       for (int j = 0; j < T; ++j, ++gv) {
-        const int G = gkb + (j >> 1);
-        const int buf = 2 * (G & 1) + (j & 1);
-        const int vs = gv & 1;
-        mbar_wait(p_full + 8 * buf, (uint32_t)((G >> 1) & 1));
-        mbar_wait(v_full + 8 * vs, (uint32_t)((gv >> 1) & 1));
+        const int buf = gv & 3;
+        // p_full(j) also vouches for V_j and for K_{j+3}: the softmax group waits for those (normally long-satisfied)
+        // barriers before it arrives, so this warp - the critical path of the kernel, and slow per instruction on a
+        // sub-partition it shares with two busy softmax warps - has ONE wait per tile
         if (j == 0 && it > 0) mbar_wait(o_free, (uint32_t)((it - 1) & 1));   // previous item's O has been drained
+        mbar_wait(p_full + 8 * buf, (uint32_t)((gv >> 2) & 1));
         tc_fence_after();
+        if (stamp_mma && it == 2) PDSC_STAMP1(a.dbg, j, 3, 0);   // P_j seen
         if (leader) {
-          const uint32_t vb = s0 + kAttnPV + vs * 32768;
+          const uint32_t vb = s0 + kAttnPV + vst * 32768;
           const uint32_t tP = tmem + 64 * buf;   // P_j: hi image in columns [0,32), lo image in [32,64) of its S tile
           issue_pv_mn(tO, tP, tP + 32, vb, vb + 16384, a.split, j > 0 ? 1u : 0u, FMT);
-          mma_commit(pv_done + 8 * vs);
-          mma_commit(v_empty + 8 * vs);
+          mma_commit(pv_done + 8 * (gv & 1));
+          mma_commit(v_empty + 8 * vst);
         }
+        if (++vst == kAttnRing) vst = 0;
+        if (stamp_mma && it == 2) PDSC_STAMP1(a.dbg, j, 3, 7);   // PV_j issued
         if (stamp_mma && j == 0) PDSC_STAMP1(a.dbg, it, 0, 2);
         if (stamp_mma && j == T - 1) PDSC_STAMP1(a.dbg, it, 0, 3);
-        // after PV of the second tile of a pair, the pair two ahead may overwrite that S/P buffer (in-order execution)
-        if ((j & 1) && (j >> 1) + 2 < TP) issue_qk_pair(G + 2);
+        if (j + kAttnRing < T) issue_qk_tile(gv + kAttnRing, j + kAttnRing == T - 1);
+        if (stamp_mma && it == 2) PDSC_STAMP1(a.dbg, j, 3, 5);   // QK_{j+3} issued
       }
       if (leader) mma_commit(o_done);
     }
@@ -226,10 +237,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
     };
 
     float sc[64];
-    auto load_sc = [&](int item, int j) {   // this thread's 64 SC values of key tile j: compile-time offsets c * 512 B
-      const float* p0 = a.sc + ((((size_t)(item / a.QT) * a.KT) * a.QT + (item % a.QT)) << 13) + (size_t)j * tile_stride + r;
-#pragma unroll
-      for (int c = 0; c < 64; ++c) sc[c] = ldg_stream(p0 + c * 128);
+    auto load_sc = [&](int item, int j) {   // this thread's 64 SC values of key tile j: 16 coalesced float4 loads
+      load_sc_tile(sc, a.sc + ((((size_t)(item / a.QT) * a.KT) * a.QT + (item % a.QT)) << 13) + (size_t)j * tile_stride, r);
     };
     if (my_items > 0) {
       if (g < T) load_sc(blockIdx.x, g);
@@ -238,20 +247,22 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
     for (int it = 0; it < my_items; ++it) {
       const int item = blockIdx.x + it * gridDim.x;
       const int b = item / a.QT, qt = item % a.QT;
-      const int gkb = it * TP, gvb = it * T;
+      const int gvb = it * T;   // the CTA's running tile count at the item's first tile
       const float* sc_cta = a.sc + ((((size_t)b * a.KT) * a.QT + qt) << 13);
       const float* sc_line = sc_cta + gt * 32;   // two 128-byte lines of each 32 KB tile per thread (L2 prefetch)
       float my_ref = -INFINITY, l_sum = 0.f;
       if (stamp) PDSC_STAMP1(a.dbg, it, 1 + g, 0);
       if (g + 2 < T) { prefetch_l2(sc_line + (size_t)(g + 2) * tile_stride); prefetch_l2(sc_line + (size_t)(g + 2) * tile_stride + 4096); }
       for (int j = g; j < T; j += 2) {
-        const int G = gkb + (j >> 1);
-        const int buf = 2 * (G & 1) + (j & 1);
+        const int tn = gvb + j;   // running tile count
+        const int buf = tn & 3;
         const uint32_t tS = tmem + 64 * buf + lane_base;
         if (j + 4 < T) { prefetch_l2(sc_line + (size_t)(j + 4) * tile_stride); prefetch_l2(sc_line + (size_t)(j + 4) * tile_stride + 4096); }
-        mbar_wait(s_full + 8 * (G & 1), (uint32_t)((G >> 1) & 1));
+        const bool tstamp = stamp && it == 2;   // per-tile detail of one steady-state item: role 3, row = tile
+        mbar_wait(s_full + 8 * buf, (uint32_t)((tn >> 2) & 1));
         tc_fence_after();
         if (stamp && j == g) PDSC_STAMP1(a.dbg, it, 1 + g, 1);
+        if (tstamp) PDSC_STAMP1(a.dbg, j, 3, 1);   // S_j seen
         float l[64];
         {
           uint32_t raw[32];
@@ -276,12 +287,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
         for (int c = 1; c < 64; ++c) tmax = fmaxf(tmax, l[c]);
         // running reference maximum of the row, handed from tile to tile between the row's two owner threads
         float prev_ref = -INFINITY;
+        if (tstamp) PDSC_STAMP1(a.dbg, j, 3, 2);   // row maximum done
         if (j > 0) {
           const int pj = j - 1;
           const int use = ((pj & 1) ? it * TO : it * TE) + (pj >> 1);
           mbar_wait(ref_ready + 8 * (pj & 1), (uint32_t)(use & 1));
           prev_ref = ref_s[(pj & 1) * 128 + r];
         }
+        if (tstamp) PDSC_STAMP1(a.dbg, j, 3, 3);   // reference received
         const bool advance = (j == 0) || (tmax > prev_ref + kRescaleThreshold);
         const float new_ref = advance ? tmax : prev_ref;
         ref_s[(j & 1) * 128 + r] = new_ref;
@@ -295,6 +308,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
           rsum += l[c];
         }
         l_sum += rsum;
+        if (tstamp) PDSC_STAMP1(a.dbg, j, 3, 4);   // exponentials and row sum done
         // P (16-bit hi / lo images) over this thread's own S row: column c holds keys 2c | 2c+1
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -320,15 +334,23 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
             tmem_st32(tO + lane_base + c0, o);
           }
         }
+        // vouch for the operands the MMA warp will issue behind P_j: V_j and K_{j+3} (loaded three tile periods ago)
+        {
+          mbar_wait(v_full + 8 * (tn % kAttnRing), (uint32_t)((tn / kAttnRing) & 1));
+          if (j + kAttnRing < T) {
+            const int gk3 = tn + kAttnRing;
+            mbar_wait(k_full + 8 * (gk3 % kAttnRing), (uint32_t)((gk3 / kAttnRing) & 1));
+          }
+        }
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(p_full + 8 * buf);
+        if (tstamp) PDSC_STAMP1(a.dbg, j, 3, 6);   // P_j written, operands vouched for, arrived
       }
       // ---- item boundary ------------------------------------------------------------------------------------
       if (stamp) PDSC_STAMP1(a.dbg, it, 1 + g, 2);
-      const int Gl = gkb + TP - 1;   // the item's last QK pair: once it has completed, the Q columns are free
       if (it + 1 < my_items) {
-        mbar_wait(s_full + 8 * (Gl & 1), (uint32_t)((Gl >> 1) & 1));
+        mbar_wait(qk_done, (uint32_t)(it & 1));   // the item's last QK has completed: the Q columns are free
         tc_fence_after();
         if (g >= T) load_sc(item + gridDim.x, g);   // (never true for T >= 2; keeps a one-tile item correct)
         convert_q(it + 1);
@@ -385,6 +407,19 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+  if (a.dbg != nullptr && tid == 0) {   // spread of the CTA lifetimes: rows 14 / 15 of role 0 (never used by an item)
+    const long long dt = clock64() - t_begin;
+    atomicMax(reinterpret_cast<unsigned long long*>(a.dbg + (14 * 4) * 8 + 0), (unsigned long long)dt);
+    atomicAdd(reinterpret_cast<unsigned long long*>(a.dbg + (14 * 4) * 8 + 1), (unsigned long long)dt);
+    if (my_items == 14) atomicMax(reinterpret_cast<unsigned long long*>(a.dbg + (14 * 4) * 8 + 2), (unsigned long long)dt);
+    if (blockIdx.x < 8) a.dbg[(15 * 4) * 8 + blockIdx.x] = dt;
+    if (blockIdx.x == 0) {   // SM clock during this launch = cycles / ns
+      unsigned long long ns_end;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
+      a.dbg[(15 * 4 + 1) * 8 + 0] = (long long)(ns_end - ns_begin);
+      a.dbg[(15 * 4 + 1) * 8 + 1] = dt;
+    }
+  }
 }
 
 }  // namespace pdsc

@@ -15,11 +15,16 @@ cp, s, t = (base[k].repeat(rep, 1, 1)[:a.b].cuda() for k in ("corr_pos", "src_ke
 m.run(cp, s, t)
 out = m.run(cp, s, t, taps=["timeline"], layer_tap=3)
 tl = out["timeline"].cpu().numpy()
-for k, name, roles in ((0, "chain<PCQ>", ["mma", "loader", "epilogue", "epi-detail"]), (1, "attention", ["mma", "softmax-g0", "softmax-g1", "life"])):
-    d = tl[k]; t0 = d[d > 0].min()
+for k, name, roles in ((0, "chain<PCQ>", ["mma", "loader", "epilogue", "epi-detail"]), (1, "attention", ["mma", "softmax-g0", "softmax-g1", "item2-tiles(mmaSawP,S,max,ref,exp,QKj+3issued,arrive,PVissued)"])):
+    d = tl[k]; t0 = d[:14][d[:14] > 0].min()
     print(f"== {name}: cycles since first stamp; rows = tile/iteration, per role events")
-    for it in range(16):
+    for it in range(14 if k == 1 else 16):
         line = f"it{it:2d}"
         for ri, rn in enumerate(roles):
             ev = d[it, ri]; line += f" | {rn}:" + " ".join(f"{int(x - t0):7d}" if x > 0 else "      -" for x in ev)
         print(line)
+
+d = tl[1]
+ns, cyc = int(d[15, 1, 0]), int(d[15, 1, 1])
+print("attention CTA lifetimes (cycles): max", int(d[14, 0, 0]), "mean", int(d[14, 0, 1]) // 148, "first 8 CTAs", [int(x) for x in d[15, 0]],
+      "| CTA 0:", cyc, "cycles in", ns, "ns ->", round(cyc / max(ns, 1), 3), "GHz during the launch")
