@@ -75,6 +75,10 @@ struct pdsc_engine {
   size_t host_ws_bytes = 0;
   float* host_io = nullptr;
   size_t host_io_floats = 0;
+  // pdsc_forward_host copies corr_pos on a side stream while the SC kernel (which only reads the key points) runs
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_fork = nullptr, corr_ready = nullptr;
+  bool corr_pending = false;             // the next pdsc_forward waits for corr_ready before its first reader of corr_pos
   // live profiling (pdsc_profile_*)
   bool profiling = false;
   bool profile_pending = false;
@@ -283,6 +287,9 @@ int pdsc_destroy(pdsc_engine* e) {
   pdsc::tc_free_weights(&e->tc);
   cudaFree(e->host_ws);
   cudaFree(e->host_io);
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->copy_fork) cudaEventDestroy(e->copy_fork);
+  if (e->corr_ready) cudaEventDestroy(e->corr_ready);
   for (auto& ev : e->ev) cudaEventDestroy(ev);
   delete e;
   return PDSC_OK;
@@ -429,6 +436,10 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
     if (simt) launch_sc_matrix(d_src, d_tgt, w.sc, B, N, NS, e->sigma_spat, st);
     else launch_sc_matrix_tiled(d_src, d_tgt, w.sc, B, N, e->sigma_spat, st);
     mark(1);
+    if (e->corr_pending) {   // host path: corr_pos is still arriving on the side stream
+      PDSC_CUDA(cudaStreamWaitEvent(st, e->corr_ready, 0));
+      e->corr_pending = false;
+    }
     if (io && io->out_sc) {
       if (simt)
         cudaMemcpy2DAsync(io->out_sc, (size_t)N * sizeof(float), w.sc, (size_t)NS * sizeof(float), (size_t)N * sizeof(float),
@@ -615,10 +626,25 @@ int pdsc_forward_host(pdsc_engine* e, int32_t B, int32_t N, const float* h_corr_
   float* d_tgt = d_src + R * 3;
   float* d_lab = d_tgt + R * 3;
   float* d_tr = d_lab + R;
-  PDSC_CUDA(cudaMemcpyAsync(d_corr, h_corr_pos, R * in_dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (!e->copy_stream) {
+    PDSC_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    PDSC_CUDA(cudaEventCreateWithFlags(&e->copy_fork, cudaEventDisableTiming));
+    PDSC_CUDA(cudaEventCreateWithFlags(&e->corr_ready, cudaEventDisableTiming));
+  }
+  // key points first (the SC kernel reads only those); corr_pos (half of the input bytes) follows on the side stream,
+  // ordered behind whatever the caller's stream held, and is awaited right behind the SC launch
   PDSC_CUDA(cudaMemcpyAsync(d_src, h_src, R * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
   PDSC_CUDA(cudaMemcpyAsync(d_tgt, h_tgt, R * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  PDSC_CUDA(cudaEventRecord(e->copy_fork, st));
+  PDSC_CUDA(cudaStreamWaitEvent(e->copy_stream, e->copy_fork, 0));
+  PDSC_CUDA(cudaMemcpyAsync(d_corr, h_corr_pos, R * in_dim * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
+  PDSC_CUDA(cudaEventRecord(e->corr_ready, e->copy_stream));
+  e->corr_pending = true;
   const int rc = pdsc_forward(e, B, N, d_corr, d_src, d_tgt, d_tr, d_lab, nullptr, e->host_ws, e->host_ws_bytes, cuda_stream);
+  if (e->corr_pending) {   // the forward failed before its wait: join the side stream so the buffers may be reused
+    cudaStreamWaitEvent(st, e->corr_ready, 0);
+    e->corr_pending = false;
+  }
   if (rc) return rc;
   PDSC_CUDA(cudaMemcpyAsync(h_final_trans, d_tr, (size_t)B * 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
   PDSC_CUDA(cudaMemcpyAsync(h_final_labels, d_lab, R * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -258,11 +258,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
         const int buf = tn & 3;
         const uint32_t tS = tmem + 64 * buf + lane_base;
         if (j + 4 < T) { prefetch_l2(sc_line + (size_t)(j + 4) * tile_stride); prefetch_l2(sc_line + (size_t)(j + 4) * tile_stride + 4096); }
-        const bool tstamp = stamp && it == 2;   // per-tile detail of one steady-state item: role 3, row = tile
         mbar_wait(s_full + 8 * buf, (uint32_t)((tn >> 2) & 1));
         tc_fence_after();
-        if (stamp && j == g) PDSC_STAMP1(a.dbg, it, 1 + g, 1);
-        if (tstamp) PDSC_STAMP1(a.dbg, j, 3, 1);   // S_j seen
         float l[64];
         {
           uint32_t raw[32];
@@ -287,14 +284,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
         for (int c = 1; c < 64; ++c) tmax = fmaxf(tmax, l[c]);
         // running reference maximum of the row, handed from tile to tile between the row's two owner threads
         float prev_ref = -INFINITY;
-        if (tstamp) PDSC_STAMP1(a.dbg, j, 3, 2);   // row maximum done
         if (j > 0) {
           const int pj = j - 1;
           const int use = ((pj & 1) ? it * TO : it * TE) + (pj >> 1);
           mbar_wait(ref_ready + 8 * (pj & 1), (uint32_t)(use & 1));
           prev_ref = ref_s[(pj & 1) * 128 + r];
         }
-        if (tstamp) PDSC_STAMP1(a.dbg, j, 3, 3);   // reference received
         const bool advance = (j == 0) || (tmax > prev_ref + kRescaleThreshold);
         const float new_ref = advance ? tmax : prev_ref;
         ref_s[(j & 1) * 128 + r] = new_ref;
@@ -308,7 +303,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
           rsum += l[c];
         }
         l_sum += rsum;
-        if (tstamp) PDSC_STAMP1(a.dbg, j, 3, 4);   // exponentials and row sum done
         // P (16-bit hi / lo images) over this thread's own S row: column c holds keys 2c | 2c+1
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -345,7 +339,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(p_full + 8 * buf);
-        if (tstamp) PDSC_STAMP1(a.dbg, j, 3, 6);   // P_j written, operands vouched for, arrived
       }
       // ---- item boundary ------------------------------------------------------------------------------------
       if (stamp) PDSC_STAMP1(a.dbg, it, 1 + g, 2);
