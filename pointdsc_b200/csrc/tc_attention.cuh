@@ -263,6 +263,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_kernel(AttnArgs 
       }
       if (stamp_mma) PDSC_STAMP1(a.dbg, j, 0, 3);
       // after PV of the second tile of pair p, pair p + 2 may overwrite that S/P buffer (in-order execution)
+#if PDSC_STRICT_TMEM_WAR
+      if ((j & 1) && (j >> 1) + 2 < TP) { mbar_wait(pv_done + 8 * vs, (uint32_t)((j >> 1) & 1)); tc_fence_after(); }
+#endif
       if ((j & 1) && (j >> 1) + 2 < TP) issue_qk_pair((j >> 1) + 2);
     }
     if (leader) mma_commit(o_done);

@@ -330,6 +330,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
         }
         // vouch for the operands the MMA warp will issue behind P_j: V_j and K_{j+3} (loaded three tile periods ago)
         {
+#if PDSC_STRICT_TMEM_WAR
+          // ... and for the completion of PV_{j-1}: QK_{j+3}, issued behind PV_j, overwrites the S/P buffer PV_{j-1} reads
+          if (j > 0) mbar_wait(pv_done + 8 * ((tn - 1) & 1), (uint32_t)(((tn - 1) >> 1) & 1));
+#endif
           mbar_wait(v_full + 8 * (tn % kAttnRing), (uint32_t)((tn / kAttnRing) & 1));
           if (j + kAttnRing < T) {
             const int gk3 = tn + kAttnRing;

@@ -185,6 +185,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         // reader of the operand parked there) was issued before this MMA.
         auto issue_m0 = [&](int itx) {
           mbar_wait(a_ready, (uint32_t)(itx & 1));
+#if PDSC_STRICT_TMEM_WAR
+          // M0(itx) overwrites D0[itx & 1], which the Q GEMM of tile itx - 2 reads as its A operand.  That MMA directly
+          // precedes this one in the issue order; the PTX pipeline rules order two tcgen05.mma only when they share
+          // accumulator and shape, so wait for its COMPLETION (group B has drained D1 of tile itx - 2) instead of relying on
+          // in-order execution.
+          if (itx >= 2) mbar_wait(d1_free + 8 * (itx & 1), (uint32_t)(((itx >> 1) - 1) & 1));
+#endif
           tc_fence_after();
           if (leader) {
             const uint32_t dc = tmem + (uint32_t)(itx & 1) * 256u;

@@ -30,6 +30,14 @@ struct ChainArgs {
   long long* dbg;        // optional timeline: clock64() stamps of CTA 0 (tools/tc_timeline.py)
 };
 
+// PDSC_STRICT_TMEM_WAR=1: never rely on the issue order of two tcgen05.mma with DIFFERENT accumulators for a write-after-read
+// hazard on tensor memory (an MMA overwriting columns that an earlier MMA reads as its A operand): wait for the reader's
+// completion through a commit barrier instead.  Default 0 = the measured configuration; tools/build_variant.py builds the
+// strict library next to it for A/B runs ("Run-to-run reproducibility").
+#ifndef PDSC_STRICT_TMEM_WAR
+#define PDSC_STRICT_TMEM_WAR 0
+#endif
+
 // timeline stamp: slot = role * 64 + event (CTA 0 only, first 16 tiles)
 #define PDSC_STAMP(dbg, it, role, ev)                                                       \
   do {                                                                                       \
