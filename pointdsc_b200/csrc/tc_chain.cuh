@@ -48,7 +48,6 @@ __device__ __forceinline__ void st_global_v4(void* p, const uint4& v) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(__cvta_generic_to_global(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
-__device__ __forceinline__ void quarter_sync(int q4) { asm volatile("bar.sync %0, 64;" ::"r"(2 + q4) : "memory"); }
 
 // D[128 x NOUT] (+)= A[128 x 32 KCH] * B[NOUT x 32 KCH]^T, A in tensor memory in the chunked in-place layout described
 // above (chunk q at a_base + 32 q), B K-major SWIZZLE_128B panels of 64 K elements in shared memory.

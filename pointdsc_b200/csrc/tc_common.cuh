@@ -85,13 +85,4 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint3
   }
 }
 
-// 8 consecutive fp32 values -> one 16-byte hi chunk and one 16-byte lo chunk
-template <int FMT>
-__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
-  split_pair<FMT>(x[0], x[1], hi.x, lo.x);
-  split_pair<FMT>(x[2], x[3], hi.y, lo.y);
-  split_pair<FMT>(x[4], x[5], hi.z, lo.z);
-  split_pair<FMT>(x[6], x[7], hi.w, lo.w);
-}
-
 }  // namespace pdsc
