@@ -136,7 +136,10 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
 
 /* Same call with HOST buffers (the end-to-end form): copies the inputs host->device, runs
  * pdsc_forward, copies the two outputs device->host and synchronises the stream before returning.
- * Device staging and workspace are owned by the engine and grown on demand. */
+ * Device staging and workspace are owned by the engine and grown on demand.  The key points are copied
+ * on `cuda_stream`; corr_pos (half of the input bytes) is copied on an engine-owned side stream, ordered
+ * behind `cuda_stream` by an event, while the spatial-consistency kernel (which reads only the key points)
+ * runs, and joined again before the first kernel that reads corr_pos. */
 int pdsc_forward_host(pdsc_engine* e, int32_t B, int32_t N, const float* h_corr_pos, const float* h_src_keypts,
                       const float* h_tgt_keypts, float* h_final_trans, float* h_final_labels, void* cuda_stream);
 
