@@ -93,3 +93,26 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(root, f)).read()
                 assert "oracle" not in text.replace("oracle/", "").replace("CPU oracle", "") or f == "synth.py", f
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the engine) prints ONE JSON line with the contract's
+    keys; a reduced configuration keeps it to a few seconds here."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--n", "160", "--batch", "2"], capture_output=True, text=True, timeout=300, check=True).stdout
+    lines = [ln for ln in out.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "sets/s" and d["higher_is_better"] is True
+    assert d["metric"] == "correspondence-sets/sec (PointDSC.forward, N=160, B=2)"   # not the headline label
+    for key in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config",
+                "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
