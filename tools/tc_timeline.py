@@ -15,7 +15,7 @@ cp, s, t = (base[k].repeat(rep, 1, 1)[:a.b].cuda() for k in ("corr_pos", "src_ke
 m.run(cp, s, t)
 out = m.run(cp, s, t, taps=["timeline"], layer_tap=3)
 tl = out["timeline"].cpu().numpy()
-for k, name, roles in ((0, "chain<PCQ>", ["mma", "loader", "epilogue", "epi-detail"]), (1, "attention", ["mma", "softmax-g0", "softmax-g1", "item2-tiles(mmaSawP,S,max,ref,exp,QKj+3issued,arrive,PVissued)"])):
+for k, name, roles in ((0, "chain<PCQ>", ["mma", "loader", "epilogue", "epi-detail"]), (1, "attention", ["mma", "softmax-g0", "softmax-g1", "item2-tiles(ev0 = MMA saw P_j, ev5 = QK_{j+3} issued, ev7 = PV_j issued; the softmax loop carries no stamps)"])):
     d = tl[k]; t0 = d[:14][d[:14] > 0].min()
     print(f"== {name}: cycles since first stamp; rows = tile/iteration, per role events")
     for it in range(14 if k == 1 else 16):
