@@ -183,6 +183,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
         // barriers before it arrives, so this warp - the critical path of the kernel, and slow per instruction on a
         // sub-partition it shares with two busy softmax warps - has ONE wait per tile
         if (j == 0 && it > 0) mbar_wait(o_free, (uint32_t)((it - 1) & 1));   // previous item's O has been drained
+#if PDSC_ATTN_MMA_WAITS_OPERANDS
+        // diagnostic variant: do not rely on the softmax group's vouching, observe the TMA barriers in the issuing thread
+        mbar_wait(v_full + 8 * vst, (uint32_t)((gv / kAttnRing) & 1));
+        if (j + kAttnRing < T) mbar_wait(k_full + 8 * qst, (uint32_t)(((gv + kAttnRing) / kAttnRing) & 1));
+#endif
         mbar_wait(p_full + 8 * buf, (uint32_t)((gv >> 2) & 1));
         tc_fence_after();
         if (stamp_mma && it == 2) PDSC_STAMP1(a.dbg, j, 3, 0);   // P_j seen

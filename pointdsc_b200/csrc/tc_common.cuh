@@ -37,6 +37,11 @@ struct ChainArgs {
 #ifndef PDSC_STRICT_TMEM_WAR
 #define PDSC_STRICT_TMEM_WAR 0
 #endif
+// PDSC_ATTN_MMA_WAITS_OPERANDS=1 (diagnostic): the MMA warp of the persistent attention kernel waits for the K / V tile
+// barriers itself instead of relying on the softmax group's wait-then-arrive ("vouching") on p_full.
+#ifndef PDSC_ATTN_MMA_WAITS_OPERANDS
+#define PDSC_ATTN_MMA_WAITS_OPERANDS 0
+#endif
 
 // timeline stamp: slot = role * 64 + event (CTA 0 only, first 16 tiles)
 #define PDSC_STAMP(dbg, it, role, ev)                                                       \
