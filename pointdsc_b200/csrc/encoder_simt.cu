@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(256) layer0_kernel(const float* __restrict__ x
 void launch_layer0(const float* corr_pos, const float* W, const float* bias, float* out, long long rows, int in_dim,
                    cudaStream_t st) {
   long long blocks = (rows + 7) / 8;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  const long long max_blocks = 8LL * device_sm_count();
+  if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   layer0_kernel<<<(unsigned)blocks, 256, 0, st>>>(corr_pos, W, bias, out, rows, in_dim);
 }
@@ -271,11 +272,7 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const float* __rest
 
 void launch_attention_simt(const float* q, const float* k, const float* v, const float* sc, float* msg, int B, int N,
                            int NS, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-    configured = true;
-  }
+  ensure_dynamic_smem(reinterpret_cast<const void*>(attention_simt_kernel), kAttnSmem);
   dim3 grid((N + AQ - 1) / AQ, B);
   attention_simt_kernel<<<grid, 256, kAttnSmem, st>>>(q, k, v, sc, msg, N, NS);
 }

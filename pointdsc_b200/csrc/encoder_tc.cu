@@ -158,32 +158,13 @@ __global__ void tc_decode_kernel(const uint8_t* qimg, const uint8_t* kvimg, floa
 // =========================================================================================================
 // host orchestration
 // =========================================================================================================
-static int g_num_sms = 0;
-static int g_attn_persistent = 1;   // PDSC_ATTN_PERSISTENT=0 selects the one-CTA-per-item kernel (developer switch)
-
 template <int FMT>
 static cudaError_t tc_configure_fmt() {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(tc_chain_kernel<kPCQ, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem))) return e;
-  if ((e = cudaFuncSetAttribute(tc_chain_kernel<kKV, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem))) return e;
-  if ((e = cudaFuncSetAttribute(tc_chain_kernel<kMSG, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem))) return e;
-  if ((e = cudaFuncSetAttribute(tc_attention_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemTc))) return e;
-  if ((e = cudaFuncSetAttribute(tc_attention_persistent_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnPSmem))) return e;
-  return cudaSuccess;
-}
-
-static cudaError_t tc_configure() {
-  static bool done = false;
-  if (done) return cudaSuccess;
-  cudaError_t e;
-  int dev = 0;
-  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-  if ((e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-  if (const char* env = getenv("PDSC_ATTN_PERSISTENT")) g_attn_persistent = atoi(env) != 0;
-  if ((e = tc_configure_fmt<kFmtF16>()) != cudaSuccess) return e;
-  if ((e = tc_configure_fmt<kFmtBF16>()) != cudaSuccess) return e;
-  done = true;
-  return cudaSuccess;
+  if ((e = ensure_dynamic_smem(reinterpret_cast<const void*>(tc_chain_kernel<kPCQ, FMT>), kChainSmem))) return e;
+  if ((e = ensure_dynamic_smem(reinterpret_cast<const void*>(tc_chain_kernel<kKV, FMT>), kChainSmem))) return e;
+  if ((e = ensure_dynamic_smem(reinterpret_cast<const void*>(tc_chain_kernel<kMSG, FMT>), kChainSmem))) return e;
+  return ensure_dynamic_smem(reinterpret_cast<const void*>(tc_attention_persistent_kernel<FMT>), kAttnPSmem);
 }
 
 template <int FMT>
@@ -195,7 +176,9 @@ static int tc_encoder_forward_fmt(const TcWeights& w, const TcForwardArgs& a, cu
   qimg = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(qimg) + 1023) & ~uintptr_t(1023));
   uint8_t* kvimg = qimg + (size_t)a.B * QT * 65536;
   const long long tiles = (rows + 127) / 128;
-  const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+  const int num_sms = device_sm_count();
+  if (num_sms <= 0) return (int)cudaErrorInvalidDevice;
+  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
   const uint8_t* arena = static_cast<const uint8_t*>(w.arena) + (size_t)FMT * w.num_layers * kLayerBytes;
 
   launch_layer0(a.corr_pos, a.l0w, a.l0b, a.feat, rows, a.in_dim, st);
@@ -216,11 +199,9 @@ static int tc_encoder_forward_fmt(const TcWeights& w, const TcForwardArgs& a, cu
     AttnArgs at{a.N, a.NS, QT, KT, a.split, qimg, kvimg, a.sc, a.msg,
                 (a.timeline && a.debug_layer == l) ? a.timeline + 512 : nullptr, a.B * QT};
     if (a.attn_events) cudaEventRecord(a.attn_events[2 * l], st);
-    if (g_attn_persistent) {
+    {
       const int items = a.B * QT;
-      tc_attention_persistent_kernel<FMT><<<items < g_num_sms ? items : g_num_sms, kAttnThreads, kAttnPSmem, st>>>(at);
-    } else {
-      tc_attention_kernel<FMT><<<a.B * QT, kAttnThreads, kAttnSmemTc, st>>>(at);
+      tc_attention_persistent_kernel<FMT><<<items < num_sms ? items : num_sms, kAttnThreads, kAttnPSmem, st>>>(at);
     }
     if (a.attn_events) cudaEventRecord(a.attn_events[2 * l + 1], st);
     if (a.debug_out && a.debug_layer == l) {
@@ -240,7 +221,7 @@ static int tc_encoder_forward_fmt(const TcWeights& w, const TcForwardArgs& a, cu
 }
 
 int tc_encoder_forward(const TcWeights& w, const TcForwardArgs& a, cudaStream_t st) {
-  cudaError_t e = tc_configure();
+  const cudaError_t e = a.fmt == kFmtBF16 ? tc_configure_fmt<kFmtBF16>() : tc_configure_fmt<kFmtF16>();
   if (e != cudaSuccess) return (int)e;
   return a.fmt == kFmtBF16 ? tc_encoder_forward_fmt<kFmtBF16>(w, a, st) : tc_encoder_forward_fmt<kFmtF16>(w, a, st);
 }

@@ -115,14 +115,11 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(const float* __re
 void launch_head(const float* feat, const HeadWeights& w, float* normed, float* conf, long long rows, int want_conf,
                  cudaStream_t st) {
   long long blocks = ((rows + 31) / 32 + kHeadWarps - 1) / kHeadWarps;
-  if (blocks > 148 * 2) blocks = 148 * 2;
+  const long long max_blocks = 2LL * device_sm_count();
+  if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   constexpr int kSmem = (kC * 32 + 32 * 32 + 96 + kHeadWarps * kC * kHeadStride) * (int)sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    configured = true;
-  }
+  ensure_dynamic_smem(reinterpret_cast<const void*>(head_kernel), kSmem);
   head_kernel<<<(unsigned)blocks, kHeadWarps * 32, kSmem, st>>>(feat, w, normed, conf, rows, want_conf);
 }
 

@@ -71,6 +71,11 @@ void launch_select_refine(const float* src, const float* tgt, const float* seed_
                           float* init_trans_out, int32_t* best_out, int32_t* refine_solves, int B, int N, int S,
                           float inlier_threshold, float refine_threshold, int max_refine, cudaStream_t st);
 
+// ---- per-device launch configuration (device_state.cu) ----------------------------------------------------
+// opt `kernel` in to `bytes` of dynamic shared memory on the CURRENT device (no-op if already granted there)
+cudaError_t ensure_dynamic_smem(const void* kernel, int bytes);
+int device_sm_count();   // SM count of the current device
+
 // ---- misc ---------------------------------------------------------------------------------------
 void launch_fill_u32(uint32_t* p, uint32_t v, long long n, cudaStream_t st);
 void launch_fill_u64(unsigned long long* p, unsigned long long v, long long n, cudaStream_t st);

@@ -187,11 +187,7 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_dist_tc_kernel(const float
 
 void launch_knn_dist_tc(const float* normed, const int32_t* seeds, float* dist, int B, int N, int S, cudaStream_t st) {
   if (S <= 0) return;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(knn_dist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKnnSmem);
-    configured = true;
-  }
+  ensure_dynamic_smem(reinterpret_cast<const void*>(knn_dist_tc_kernel), kKnnSmem);
   knn_dist_tc_kernel<<<dim3((S + 127) / 128, B), kKnnThreads, kKnnSmem, st>>>(normed, seeds, dist, N, S);
 }
 

@@ -135,11 +135,7 @@ void launch_knn_select(const float* dist, int32_t* knn_idx, int B, int N, int S,
     return;
   }
   const int smem = N * (int)sizeof(unsigned long long);
-  static int configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(knn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8);
-    configured = 16384 * 8;
-  }
+  ensure_dynamic_smem(reinterpret_cast<const void*>(knn_select_kernel), smem);
   knn_select_kernel<<<rows, 128, smem, st>>>(dist, knn_idx, N, S, k);
 }
 
@@ -319,11 +315,7 @@ void launch_nsm_power(const float* normed, const float* src, const float* tgt, c
   const int ms = k | 1;
   const int kp = (k + 3) & ~3;
   const int smem = (kC * kp + k * ms + 6 * k + k + 4) * (int)sizeof(float);
-  static int configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaFuncSetAttribute(nsm_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    configured = 160 * 1024;
-  }
+  ensure_dynamic_smem(reinterpret_cast<const void*>(nsm_power_kernel), smem);
   nsm_power_kernel<<<dim3(S, B), kNsmThreads, smem, st>>>(normed, src, tgt, knn_idx, iterates, conv_mask, compat_out, N, S, k,
                                                           iters, sigma * sigma, sigma_d * sigma_d);
 }

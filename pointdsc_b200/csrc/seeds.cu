@@ -100,11 +100,7 @@ void launch_pick_seeds(const float* src, const float* conf, int32_t* seeds, floa
   int P = 2;
   while (P < N) P <<= 1;
   const int smem = P * (int)sizeof(unsigned long long);
-  static int configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(seed_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSeedMaxN * 8);
-    configured = kSeedMaxN * 8;
-  }
+  ensure_dynamic_smem(reinterpret_cast<const void*>(seed_sort_kernel), smem);
   const int threads = P / 2 < 1024 ? (P / 2 < 32 ? 32 : P / 2) : 1024;
   seed_sort_kernel<<<B, threads, smem, st>>>(key_scratch, seeds, N, P, S);
 }

@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
     // S_t = Q K_t^T for ONE 64-key tile (N = 64, 24 MMAs of 32 cycles) into S/P buffer t & 3, t the CTA's running tile
     // count.  One commit per tile: the two softmax groups receive their tiles 768 tensor cycles apart and stay staggered
     // (with N = 128 pairs both groups ran the same phase at the same time and contended for the same pipes).
-    // QK runs kAttnRing tiles ahead of PV: behind PV_j (in-order execution) tile j + 3 overwrites the S/P buffer that
-    // PV_{j-1} has read, from the K stage that QK_j released.
+    // QK runs kAttnRing tiles ahead of PV: behind PV_j, tile j + 3 overwrites the S/P buffer that PV_{j-1} has read (its
+    // completion is vouched for by the softmax group before it arrives on p_full(j)), from the K stage QK_j released.
     int qst = 0;                                   // K ring stage of the next QK
     auto issue_qk_tile = [&](int gt, bool last) {  // gt: running tile count; last: the item's final tile
       const int buf = gt & 3;
@@ -183,11 +183,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
         // barriers before it arrives, so this warp - the critical path of the kernel, and slow per instruction on a
         // sub-partition it shares with two busy softmax warps - has ONE wait per tile
         if (j == 0 && it > 0) mbar_wait(o_free, (uint32_t)((it - 1) & 1));   // previous item's O has been drained
-#if PDSC_ATTN_MMA_WAITS_OPERANDS
-        // diagnostic variant: do not rely on the softmax group's vouching, observe the TMA barriers in the issuing thread
-        mbar_wait(v_full + 8 * vst, (uint32_t)((gv / kAttnRing) & 1));
-        if (j + kAttnRing < T) mbar_wait(k_full + 8 * qst, (uint32_t)(((gv + kAttnRing) / kAttnRing) & 1));
-#endif
         mbar_wait(p_full + 8 * buf, (uint32_t)((gv >> 2) & 1));
         tc_fence_after();
         if (stamp_mma && it == 2) PDSC_STAMP1(a.dbg, j, 3, 0);   // P_j seen
@@ -335,10 +330,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
         }
         // vouch for the operands the MMA warp will issue behind P_j: V_j and K_{j+3} (loaded three tile periods ago)
         {
-#if PDSC_STRICT_TMEM_WAR
-          // ... and for the completion of PV_{j-1}: QK_{j+3}, issued behind PV_j, overwrites the S/P buffer PV_{j-1} reads
+          // ... and for the COMPLETION of PV_{j-1}: QK_{j+3}, issued behind PV_j, overwrites the S/P buffer PV_{j-1} reads as
+          // its A operand (rule in tc_common.cuh).  For j = 0 the o_free wait of the MMA warp covers the previous item's PVs.
           if (j > 0) mbar_wait(pv_done + 8 * ((tn - 1) & 1), (uint32_t)(((tn - 1) >> 1) & 1));
-#endif
           mbar_wait(v_full + 8 * (tn % kAttnRing), (uint32_t)((tn / kAttnRing) & 1));
           if (j + kAttnRing < T) {
             const int gk3 = tn + kAttnRing;

@@ -180,17 +180,14 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
       if (MODE == kPCQ) {
         // Issue order  M0(t), M0(t+1)?, ... is software-pipelined: the PointCN GEMM of tile t + 1 goes out BEFORE the wait for
         // group A's operand of tile t, so group A finds its next accumulator ready the moment it finishes a tile.
-        // D0[par] is free: the a1_ready wait of tile t - 2 covered group A's drain, and the Q GEMM of tile t - 2 (the last
-        // reader of the operand parked there) was issued before this MMA.
+        // D0[par] is free: the a1_ready wait of tile t - 2 covered group A's drain, and issue_m0 waits for the completion of
+        // the Q GEMM of tile t - 2 (the last reader of the operand parked there).
         auto issue_m0 = [&](int itx) {
           mbar_wait(a_ready, (uint32_t)(itx & 1));
-#if PDSC_STRICT_TMEM_WAR
-          // M0(itx) overwrites D0[itx & 1], which the Q GEMM of tile itx - 2 reads as its A operand.  That MMA directly
-          // precedes this one in the issue order; the PTX pipeline rules order two tcgen05.mma only when they share
-          // accumulator and shape, so wait for its COMPLETION (group B has drained D1 of tile itx - 2) instead of relying on
-          // in-order execution.
-          if (itx >= 2) mbar_wait(d1_free + 8 * (itx & 1), (uint32_t)(((itx >> 1) - 1) & 1));
-#endif
+          // M0(itx) overwrites D0[itx & 1], which the Q GEMM of tile itx - 2 reads as its A operand, and that MMA directly
+          // precedes this one in the issue order: wait for its COMPLETION (its own commit barrier; the next phase of that
+          // barrier is the Q GEMM of tile itx, which this warp has not issued yet) — see the rule in tc_common.cuh.
+          if (itx >= 2) mbar_wait(d_full + 8 * (1 * 2 + (itx & 1)), (uint32_t)(((itx >> 1) - 1) & 1));
           tc_fence_after();
           if (leader) {
             const uint32_t dc = tmem + (uint32_t)(itx & 1) * 256u;
@@ -201,8 +198,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         };
         if (it == 0) issue_m0(0);
         if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 3);
-        // M0(t+1) needs D0[par ^ 1]: drained by group A in tile t - 1 (covered by that tile's a1_ready wait) — but the Q GEMM
-        // of tile t - 1 must have been issued, which it was in the previous iteration.
+        // M0(t+1) needs D0[par ^ 1]: drained by group A in tile t - 1 (covered by that tile's a1_ready wait) and no longer
+        // read by the Q GEMM of tile t - 1 (completion awaited inside issue_m0).
         if (tile + gridDim.x < num_tiles) issue_m0(it + 1);
         mbar_wait(a1_ready, a1_uses & 1);
         ++a1_uses;
@@ -230,8 +227,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         }
       } else {
         // Wm0: 64 x 128 (hi 16K | lo 16K, panel 8K)   Wm1: 64 x 64 (hi 8K | lo 8K)   Wm2: 128 x 64 (hi 16K | lo 16K)
-        // D0 / D1 [par] are free: the a1_ready waits of tile t - 2 covered group B's drains (and the later MMAs of that tile,
-        // their last readers, were issued before this one)
+        // D0 / D1 [par] are free: the a1_ready waits of tile t - 2 covered group B's drains, and the MMAs of that tile that read
+        // them as A operands have COMPLETED (group B arrived on a1_ready of tile t - 1 only after it saw that tile's first
+        // commit, which tracks every MMA issued before it)
         tc_fence_after();
         if (leader) {
           issue_gemm<2, 64>(dcol, a_base, a_base + 32768, 16384, w_base, w_base + 16384, 8192, a.split, 0, FMT);

@@ -30,18 +30,11 @@ struct ChainArgs {
   long long* dbg;        // optional timeline: clock64() stamps of CTA 0 (tools/tc_timeline.py)
 };
 
-// PDSC_STRICT_TMEM_WAR=1: never rely on the issue order of two tcgen05.mma with DIFFERENT accumulators for a write-after-read
-// hazard on tensor memory (an MMA overwriting columns that an earlier MMA reads as its A operand): wait for the reader's
-// completion through a commit barrier instead.  Default 0 = the measured configuration; tools/build_variant.py builds the
-// strict library next to it for A/B runs ("Run-to-run reproducibility").
-#ifndef PDSC_STRICT_TMEM_WAR
-#define PDSC_STRICT_TMEM_WAR 0
-#endif
-// PDSC_ATTN_MMA_WAITS_OPERANDS=1 (diagnostic): the MMA warp of the persistent attention kernel waits for the K / V tile
-// barriers itself instead of relying on the softmax group's wait-then-arrive ("vouching") on p_full.
-#ifndef PDSC_ATTN_MMA_WAITS_OPERANDS
-#define PDSC_ATTN_MMA_WAITS_OPERANDS 0
-#endif
+// TMEM write-after-read rule (measured, round 2: profiles/r02_determinism_campaign.txt).  Two tcgen05.mma with DIFFERENT
+// accumulators are NOT executed in issue order as far as tensor memory is concerned: an MMA that overwrites columns which
+// an earlier MMA reads as its A operand can corrupt that operand (one 32-lane quarter of a tile, about once in four
+// forwards at B = 256).  Every such overwrite therefore waits for the reader's COMPLETION through a commit barrier
+// (tcgen05.commit tracks all MMAs issued before it by the thread); issue order alone is never relied upon.
 
 // timeline stamp: slot = role * 64 + event (CTA 0 only, first 16 tiles)
 #define PDSC_STAMP(dbg, it, role, ev)                                                       \
