@@ -128,6 +128,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
   const uint32_t d_full = smem_u32(bars + 6);    // [step][parity] at + 8 * (step * 2 + parity)
   const uint32_t d0_free = smem_u32(bars + 12);  // [parity]  group A has drained its accumulator(s) of the tile
   const uint32_t d1_free = smem_u32(bars + 14);  // [parity]  group B has drained the second GEMM's accumulator
+  // PCQ: group A's operand of the Q GEMM is in tensor memory, one barrier PER TILE PARITY.  The PointCN GEMM is issued one
+  // tile ahead, so a fast warp of group A can finish tile t + 1 while a slow one is still on tile t: on a single barrier
+  // its second arrival would be counted towards tile t's phase, the phase would complete without the slow warp, and the
+  // Q GEMM would read that warp's 32 rows before they were written (the round-1 "one corrupted lane quarter about once in
+  // four forwards": profiles/r02_determinism_campaign.txt).  With two barriers a warp's next arrival on the same barrier
+  // is for tile t + 2, whose PointCN GEMM is only issued after the MMA warp has passed tile t's wait.
+  const uint32_t a1_par = smem_u32(bars + 16);   // [parity]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t a_base = s0 + kChA, w_base = s0 + kChW;
   // this mode's biases, packed: PCQ b1|bq, KV bk|bv, MSG bm0|bm1|bm2
@@ -149,6 +156,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
     for (int i = 0; i < 6; ++i) mbar_init(d_full + 8 * i, 1);
     mbar_init(d0_free, 128); mbar_init(d0_free + 8, 128);
     mbar_init(d1_free, 128); mbar_init(d1_free + 8, 128);
+    mbar_init(a1_par, 128); mbar_init(a1_par + 8, 128);
     fence_barrier_init();
   }
   if (warp == 15) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -201,8 +209,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         // M0(t+1) needs D0[par ^ 1]: drained by group A in tile t - 1 (covered by that tile's a1_ready wait) and no longer
         // read by the Q GEMM of tile t - 1 (completion awaited inside issue_m0).
         if (tile + gridDim.x < num_tiles) issue_m0(it + 1);
-        mbar_wait(a1_ready, a1_uses & 1);
-        ++a1_uses;
+        mbar_wait(a1_par + 8 * par, (uint32_t)(u & 1));
         if (it >= 2) mbar_wait(d1_free + 8 * par, (uint32_t)((u - 1) & 1));  // group B drained D1[par] of tile t - 2
         tc_fence_after();
         if (stamp_mma) PDSC_STAMP1(a.dbg, it, 0, 4);
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           if (cc == 3) {
             tmem_st_wait();        // A operand written through tcgen05.st, read by the tensor core
             tc_fence_before();
-            mbar_arrive(a1_ready);
+            mbar_arrive(a1_par + 8 * par);
             if (stamp) PDSC_STAMP1(a.dbg, it, 2, 2);
           }
           // fp32 rows -> HBM, 16 columns (64 B) at a time

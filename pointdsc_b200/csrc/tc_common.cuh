@@ -30,11 +30,17 @@ struct ChainArgs {
   long long* dbg;        // optional timeline: clock64() stamps of CTA 0 (tools/tc_timeline.py)
 };
 
-// TMEM write-after-read rule (measured, round 2: profiles/r02_determinism_campaign.txt).  Two tcgen05.mma with DIFFERENT
-// accumulators are NOT executed in issue order as far as tensor memory is concerned: an MMA that overwrites columns which
-// an earlier MMA reads as its A operand can corrupt that operand (one 32-lane quarter of a tile, about once in four
-// forwards at B = 256).  Every such overwrite therefore waits for the reader's COMPLETION through a commit barrier
-// (tcgen05.commit tracks all MMAs issued before it by the thread); issue order alone is never relied upon.
+// Two synchronisation rules of the tensor-core kernels (round 2; evidence: profiles/r02_determinism_campaign.txt).
+//  1. COUNTED mbarriers and warps that run ahead.  A barrier that several independent warps arrive on must not be
+//     reachable twice by one warp before its phase has completed: the second arrival is counted towards the CURRENT phase,
+//     which then completes without the slowest warp.  This was the round-1 reproducibility bug: chain<PCQ> issues the
+//     PointCN GEMM one tile ahead, so a fast epilogue warp could deliver tile t + 1's operand while a slow one was still
+//     writing tile t's, on ONE barrier; the Q GEMM then read 32 rows (one lane quarter) of tensor memory before they were
+//     written - about once in four forwards at B = 256.  Fix: one barrier per tile parity (tc_chain.cuh).  Every counted
+//     barrier of these kernels is annotated with the reason a second arrival cannot overtake its phase.
+//  2. Tensor-memory write-after-read.  PTX orders two tcgen05.mma only when they share accumulator and shape, so an MMA
+//     that overwrites columns which an earlier MMA reads as its A operand waits for that MMA's COMPLETION through a commit
+//     barrier (tcgen05.commit tracks all MMAs the thread issued before it); issue order alone is not relied upon.
 
 // timeline stamp: slot = role * 64 + event (CTA 0 only, first 16 tiles)
 #define PDSC_STAMP(dbg, it, role, ev)                                                       \

@@ -39,7 +39,9 @@ CTOR = {
     "3dmatch": dict(inlier_threshold=0.10, sigma_d=0.10, nms_radius=0.10),
     "kitti": dict(inlier_threshold=0.6, sigma_d=1.2, nms_radius=0.6),
 }
-# (dataset, N, seed, inlier_ratio, detail)   detail: "full" keeps N x N matrices and layer features
+# (dataset, N, seed, inlier_ratio, detail[, k])   detail: "full" keeps N x N matrices and layer features, "full1k" the same
+# without src_dist (bench-size case: SC tiling with 8 query tiles and per-layer features at N = 1000); k = ctor `k`
+# (neighbourhood size, default: the snapshot's 40)
 CASES = [
     ("3dmatch", 256, 0, 0.5, "full"),
     ("3dmatch", 256, 1, 0.2, "full"),
@@ -57,13 +59,25 @@ CASES = [
     ("kitti", 1000, 1, 0.3, "feat"),
     ("kitti", 1000, 2, 0.1, "io"),
     ("kitti", 2000, 3, 0.3, "io"),
+    # round 2: every BASELINE.json configuration (B: KITTI N = 5000; C: N = 2000 with k = 80; D: N = 5000 3DMatch),
+    # the low inlier ratios of SURVEY.md §8(d), and one bench-size case with the N x N / per-layer tensors
+    ("kitti", 5000, 4, 0.3, "io"),
+    ("kitti", 5000, 5, 0.5, "io"),
+    ("3dmatch", 5000, 8, 0.3, "io"),
+    ("3dmatch", 2000, 9, 0.3, "io", 80),
+    ("3dmatch", 2000, 10, 0.2, "io", 80),
+    ("3dmatch", 2000, 11, 0.05, "io"),
+    ("3dmatch", 2000, 12, 0.1, "io"),
+    ("3dmatch", 1000, 13, 0.1, "io", 80),
+    ("kitti", 1000, 6, 0.05, "io"),
+    ("3dmatch", 1000, 14, 0.3, "full1k"),
 ]
 
 
-def build_model(dataset):
+def build_model(dataset, k=None):
     cfg = json.load(open(os.path.join(REF, "snapshot", SNAP[dataset], "config.json")))
     model = ref_mod.PointDSC(in_dim=cfg["in_dim"], num_layers=cfg["num_layers"], num_channels=cfg["num_channels"],
-                             num_iterations=cfg["num_iterations"], ratio=cfg["ratio"], k=cfg["k"], **CTOR[dataset])
+                             num_iterations=cfg["num_iterations"], ratio=cfg["ratio"], k=k or cfg["k"], **CTOR[dataset])
     sd = torch.load(os.path.join(REF, "snapshot", SNAP[dataset], "models", "model_best.pkl"), map_location="cpu")
     res = model.load_state_dict(sd, strict=False)
     assert res.missing_keys == [] and res.unexpected_keys == ["gamma"], res
@@ -151,7 +165,8 @@ def run_case(model, dataset, n, seed, ratio, detail):
     keep_io = ["confidence", "seeds", "knn_idx", "eig", "seed_weights", "seed_trans", "fitness", "best",
                "init_trans", "final_labels", "final_trans", "power_iters", "refine_solves"]
     keep = {"io": keep_io, "feat": keep_io + ["features", "normed"],
-            "full": keep_io + ["features", "normed", "sc", "src_dist", "layer_features", "compat"]}[detail]
+            "full": keep_io + ["features", "normed", "sc", "src_dist", "layer_features", "compat"],
+            "full1k": keep_io + ["features", "normed", "sc", "layer_features", "compat"]}[detail]
     arrays = {k: rec[k].detach().cpu().numpy() for k in keep}
     for k in ("seeds", "knn_idx"):
         arrays[k] = arrays[k].astype(np.int32)
@@ -159,27 +174,36 @@ def run_case(model, dataset, n, seed, ratio, detail):
                   tgt_keypts=pair["tgt_keypts"].numpy(), gt_trans=pair["gt_trans"].numpy(),
                   gt_labels=pair["gt_labels"].numpy().astype(np.uint8))
     meta = dict(dataset=dataset, n=n, seed=seed, inlier_ratio=ratio, detail=detail, torch=torch.__version__,
-                layer_features_layers=[0, 5, 11], **CTOR[dataset])
+                layer_features_layers=[0, 5, 11], k=int(model.k), **CTOR[dataset])
     arrays["meta"] = np.array(json.dumps(meta))
     return arrays
 
 
 def main():
+    """Existing fixture files are kept (pass --force to regenerate everything)."""
+    force = "--force" in sys.argv
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     for dataset in SNAP:
         model, sd = build_model(dataset)
-        np.savez(os.path.join(HERE, f"snapshot_{dataset}.npz"), **{k: v.numpy() for k, v in sd.items()})
-        for (ds, n, seed, ratio, detail) in CASES:
+        snap_path = os.path.join(HERE, f"snapshot_{dataset}.npz")
+        if force or not os.path.exists(snap_path):
+            np.savez(snap_path, **{k: v.numpy() for k, v in sd.items()})
+        for case in CASES:
+            ds, n, seed, ratio, detail = case[:5]
+            k = case[5] if len(case) > 5 else None
             if ds != dataset:
                 continue
-            arrays = run_case(model, ds, n, seed, ratio, detail)
-            path = os.path.join(HERE, f"case_{ds}_n{n}_s{seed}.npz")
+            path = os.path.join(HERE, f"case_{ds}_n{n}_s{seed}" + (f"_k{k}" if k else "") + ".npz")
+            if os.path.exists(path) and not force:
+                continue
+            m = model if k is None else build_model(ds, k)[0]
+            arrays = run_case(m, ds, n, seed, ratio, detail)
             np.savez_compressed(path, **arrays)
             gt, ft = arrays["gt_trans"], arrays["final_trans"]
             print(f"{os.path.basename(path)}: |T-gt|max={np.abs(gt - ft).max():.4f} inl={int(arrays['final_labels'].sum())} "
                   f"iters={int(arrays['power_iters'])} solves={int(arrays['refine_solves'])} "
-                  f"{os.path.getsize(path) / 1e3:.0f} KB")
+                  f"{os.path.getsize(path) / 1e3:.0f} KB", flush=True)
 
 
 if __name__ == "__main__":
