@@ -134,6 +134,15 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
                  const float* d_tgt_keypts, float* d_final_trans, float* d_final_labels,
                  const pdsc_stage_io* io, void* d_workspace, size_t workspace_bytes, void* cuda_stream);
 
+/* pdsc_forward as ONE graph launch: the first call with a given (B, N, buffer addresses) runs eagerly and captures the
+ * forward's kernels into a CUDA graph; later calls with the same arguments replay it (one cudaGraphLaunch instead of ~60
+ * kernel launches: the small-batch / bs = 1 case of the evaluation loops, evaluation/test_3DMatch.py:133).  The caller keeps
+ * the buffers alive and at the same addresses; up to 8 graphs are cached per engine.  Inside a foreign stream capture, or
+ * with profiling enabled, it degrades to pdsc_forward. */
+int pdsc_forward_graph(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, const float* d_src_keypts,
+                       const float* d_tgt_keypts, float* d_final_trans, float* d_final_labels, void* d_workspace,
+                       size_t workspace_bytes, void* cuda_stream);
+
 /* Same call with HOST buffers (the end-to-end form): copies the inputs host->device, runs
  * pdsc_forward, copies the two outputs device->host and synchronises the stream before returning.
  * Device staging and workspace are owned by the engine and grown on demand.  The key points are copied
@@ -142,6 +151,38 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
  * runs, and joined again before the first kernel that reads corr_pos. */
 int pdsc_forward_host(pdsc_engine* e, int32_t B, int32_t N, const float* h_corr_pos, const float* h_src_keypts,
                       const float* h_tgt_keypts, float* h_final_trans, float* h_final_labels, void* cuda_stream);
+
+/* ---- the same module call WITHOUT the 'testing' key (validation during training, PointDSC.py:158-165, :176, :190-191):
+ * seeds are the top-S correspondences by confidence (no suppression), the power iteration's early exit is decided over the
+ * whole batch (the reference's allclose spans [bs*S, k]), there is no post-refinement, `d_confidence` [B,N] receives the
+ * classification logits (the reference returns them as final_labels) and, if `d_M` is not NULL, it receives the feature
+ * similarity matrix M = clamp(1 - (1 - F F^T) / sigma^2, 0, 1) with a zero diagonal, [B,N,N].  Eval-mode BatchNorm only
+ * (running statistics): the training-mode forward and the backward pass are outside this engine. */
+int pdsc_forward_eval(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, const float* d_src_keypts,
+                      const float* d_tgt_keypts, float* d_final_trans, float* d_confidence, float* d_M,
+                      const pdsc_stage_io* io, void* d_workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* ---- next rows of the path ---------------------------------------------------------------
+ * f3: per-pair evaluation statistics, replacing libs/loss.py:34-63 (TransformationLoss) + :94-100 (ClassificationLoss,
+ * scikit-learn on the host) and the per-pair host synchronisation of evaluation/test_3DMatch.py:83-101.
+ * d_stats [B,10] = [success, RE deg, TE cm, #gt inliers, gt inlier ratio, #gt inliers among the kept, precision, recall,
+ * f1, rmse]; thresholds as the drivers pass them (3DMatch: 15 deg / 30 cm, KITTI: 5 deg / 60 cm). */
+int pdsc_eval_stats(pdsc_engine* e, int32_t B, int32_t N, const float* d_pred_trans, const float* d_gt_trans,
+                    const float* d_src_keypts, const float* d_tgt_keypts, const float* d_pred_labels,
+                    const float* d_gt_labels, float re_thre, float te_thre, float* d_stats, void* cuda_stream);
+
+/* f1: the correspondence front end, replacing datasets/ThreeDMatch.py:283-291 + :299-308 (the same lines in
+ * datasets/KITTI.py:80-114, demo_registration.py:101-108): nearest neighbour of every source descriptor among the target
+ * descriptors under sqrt(2 - 2 <a,b> + 1e-6) evaluated in the descriptors' own dtype (desc_is_fp64: 0 = fp32 FCGF,
+ * 1 = fp64 FPFH), first minimum wins, optional mutual check, then the in_dim = 6 network input.  One pair per call.
+ * Outputs in the layout pdsc_forward consumes, sized for the worst case M = Ns: d_corr [Ns,2] int32 (source, target),
+ * d_count [1] = M, d_corr_pos [Ns,6] (centred), d_out_src / d_out_tgt [Ns,3]; only the first M rows are written.
+ * D <= 64; d_scratch holds pdsc_match_scratch_bytes(Ns, Nt) bytes, 8-byte aligned. */
+size_t pdsc_match_scratch_bytes(int32_t Ns, int32_t Nt);
+int pdsc_match(pdsc_engine* e, int32_t Ns, int32_t Nt, int32_t D, const void* d_src_desc, const void* d_tgt_desc,
+               int32_t desc_is_fp64, const float* d_src_keypts, const float* d_tgt_keypts, int32_t use_mutual,
+               int32_t* d_corr, int32_t* d_count, float* d_corr_pos, float* d_out_src, float* d_out_tgt, void* d_scratch,
+               size_t scratch_bytes, void* cuda_stream);
 
 /* ---- live profiling with CUDA events on the caller's stream ------------------------------------------
  * When enabled, pdsc_forward() records an event pair around each stage below (and around EVERY launch of

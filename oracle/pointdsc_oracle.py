@@ -309,6 +309,46 @@ def forward_batch(sd, cfg, corr_pos, src, tgt):
     return torch.stack(tr, 0), torch.stack(lb, 0)
 
 
+def feature_similarity(normed: torch.Tensor, sigma: float) -> torch.Tensor:
+    """M = clamp(1 - (1 - F F^T) / sigma^2, 0, 1) with a zero diagonal  (PointDSC.py:160-165)."""
+    m = normed @ normed.t()
+    m = torch.clamp(1 - (1 - m) / sigma ** 2, min=0, max=1)
+    m[torch.arange(m.shape[0]), torch.arange(m.shape[0])] = 0
+    return m
+
+
+def forward_validation(sd: Mapping[str, torch.Tensor], cfg: Mapping[str, float], corr_pos, src, tgt):
+    """The forward WITHOUT the 'testing' key, eval-mode BatchNorm (PointDSC.py:158-165, :176, :182, :190-191), for a batch
+    [B,N,...]: seeds = top-S by confidence (no suppression), ONE power-iteration exit for the whole batch (the reference's
+    allclose spans [bs * S, k, 1]), no refinement, final_labels = confidence logits.
+    Returns final_trans [B,4,4], confidence [B,N], M [B,N,N], seeds [B,S], iterations run."""
+    with torch.no_grad():
+        bsz, n = corr_pos.shape[0], corr_pos.shape[1]
+        sigma_d, sigma = float(sd["sigma_spat"][0]), float(sd["sigma"][0])
+        num_seeds = int(n * float(cfg["ratio"]))
+        k = min(int(cfg["k"]), n - 1)
+        confs, normeds, seeds, knns, compats = [], [], [], [], []
+        for b in range(bsz):
+            _, sc = sc_matrix(src[b], tgt[b], sigma_d)
+            feat = encoder(corr_pos[b], sc, sd, int(cfg["num_layers"]))
+            normed = normalize_features(feat)
+            conf = classify(feat, sd)
+            sd_b = top_confidence_seeds(conf, num_seeds)
+            knn_idx = knn_seed_rows(normed, sd_b, k)
+            confs.append(conf); normeds.append(normed); seeds.append(sd_b); knns.append(knn_idx)
+            compats.append(seed_compatibility(normed, src[b], tgt[b], knn_idx, sigma, sigma_d))
+        eig, iters = leading_eigenvector(torch.cat(compats, 0), int(cfg["num_iterations"]))     # batch-wide early exit
+        eig = eig.view(bsz, num_seeds, k)
+        trans = []
+        for b in range(bsz):
+            _, seed_trans = seed_hypotheses(src[b], tgt[b], knns[b], eig[b])
+            _, _, init_trans, _ = select_hypothesis(seed_trans, src[b], tgt[b], float(cfg["inlier_threshold"]))
+            trans.append(init_trans)
+        m = torch.stack([feature_similarity(x, sigma) for x in normeds], 0)
+        return dict(final_trans=torch.stack(trans, 0), final_labels=torch.stack(confs, 0), M=m, seeds=torch.stack(seeds, 0),
+                    power_iters=iters)
+
+
 def default_config(dataset: str = "3dmatch") -> Dict[str, float]:
     """Constructor arguments the reference's eval drivers use.
     3DMatch: evaluation/test_3DMatch.py:215-224 (inlier_threshold left at the ctor default 0.10,

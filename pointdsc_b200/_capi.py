@@ -57,8 +57,18 @@ SYMBOLS = {
     "pdsc_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32]),
     "pdsc_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.POINTER(StageIO), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "pdsc_forward_graph": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "pdsc_forward_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
+    "pdsc_forward_eval": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.POINTER(StageIO), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "pdsc_eval_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "pdsc_match_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "pdsc_match": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                             C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_size_t, C.c_void_p]),
     "pdsc_launches_per_forward": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32]),
     "pdsc_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "pdsc_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
@@ -82,6 +92,20 @@ def load():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+_util_engines = {}
+
+
+def utility_engine(device_index: int):
+    """An engine handle for the stateless entry points (pdsc_match, pdsc_eval_stats): they only need the device."""
+    if device_index not in _util_engines:
+        lib = load()
+        cfg = Config(6, 12, 128, 10, 0.1, 0.1, 0.1, 40, 0.1, PRECISIONS["fp16x3"], device_index)
+        handle = C.c_void_p()
+        check(lib.pdsc_create(C.byref(cfg), C.byref(handle)))
+        _util_engines[device_index] = handle
+    return _util_engines[device_index]
 
 
 def check(rc: int):

@@ -67,6 +67,8 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(LinearArgs a) {
       float v = acc[i][j];
       if (a.epi == 1) {
         v = 2.0f - 2.0f * v;
+      } else if (a.epi == 2) {
+        v = (r == o) ? 0.0f : fminf(fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fsub_rn(1.0f, v), a.epi_param)), 0.0f), 1.0f);
       } else {
         if (a.bias) v += a.bias[o];
         if (a.relu) v = fmaxf(v, 0.f);

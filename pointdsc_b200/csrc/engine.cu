@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/pointdsc_b200.h"
@@ -49,6 +50,7 @@ struct DeviceGuard {
   }
 };
 
+constexpr size_t kGraphRows = 32768;   // B * N up to which the host path replays a captured graph (launch-bound regime)
 constexpr double kBnEps = 1e-5;  // torch.nn.BatchNorm1d default (reference PointDSC.py:14, :59)
 
 struct LayerOffsets {  // offsets (in floats) into the device weight arena
@@ -85,6 +87,15 @@ struct pdsc_engine {
   std::vector<cudaEvent_t> ev;          // [0..2L) attention pairs, then stage boundary events
   float span_ms[PDSC_SPAN_COUNT] = {};
   int span_launches[PDSC_SPAN_COUNT] = {};
+  // pdsc_forward_graph: instantiated CUDA graphs of whole forwards, keyed by shape AND buffer addresses (they are baked
+  // into the kernel nodes); a small most-recently-used list
+  struct GraphEntry {
+    int B, N;
+    const void *corr_pos, *src, *tgt, *trans, *labels, *workspace;
+    int precision;
+    cudaGraphExec_t exec;
+  };
+  std::vector<GraphEntry> graphs;
 };
 
 namespace {
@@ -291,6 +302,7 @@ int pdsc_destroy(pdsc_engine* e) {
   if (e->copy_fork) cudaEventDestroy(e->copy_fork);
   if (e->corr_ready) cudaEventDestroy(e->corr_ready);
   for (auto& ev : e->ev) cudaEventDestroy(ev);
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
   delete e;
   return PDSC_OK;
 }
@@ -351,6 +363,8 @@ int pdsc_commit_params(pdsc_engine* e) {
   auto s2 = e->params.find("sigma_spat");
   if (s2 != e->params.end() && s2->second.size() == 1) e->sigma_spat = s2->second[0];
 
+  for (auto& gq : e->graphs) cudaGraphExecDestroy(gq.exec);   // captured graphs hold the old weight pointers
+  e->graphs.clear();
   cudaFree(e->d_weights);
   e->d_weights = nullptr;
   PDSC_CUDA(cudaMalloc(&e->d_weights, arena.size() * sizeof(float)));
@@ -396,10 +410,14 @@ int32_t pdsc_launches_per_forward(const pdsc_engine* e, int32_t B, int32_t N) {
   return 1 + enc + 1 + 2 + ((e->cfg.precision == PDSC_FP32_SIMT) ? 3 : 2) + 2 + 3;
 }
 
-int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, const float* d_src, const float* d_tgt,
-                 float* d_final_trans, float* d_final_labels, const pdsc_stage_io* io, void* d_workspace,
-                 size_t workspace_bytes, void* cuda_stream) {
+// mode 0: testing (PointDSC.py: NMS seeds, per-set early exit, labels = inlier mask, post-refinement)
+// mode 1: non-testing / validation (PointDSC.py:158-165, :176, :190-191): seeds = top-S by confidence, batch-global early
+//         exit, no refinement, final_labels = confidence logits, optional feature-similarity matrix M [B,N,N]
+static int forward_impl(pdsc_engine* e, int mode, int32_t B, int32_t N, const float* d_corr_pos, const float* d_src,
+                        const float* d_tgt, float* d_final_trans, float* d_final_labels, float* d_M, const pdsc_stage_io* io,
+                        void* d_workspace, size_t workspace_bytes, void* cuda_stream) {
   using namespace pdsc;
+  const int mask_stride = mode == 0 ? 1 : 0;
   if (!e) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine");
   if (!e->committed) return fail(PDSC_ERR_NOT_COMMITTED, "pdsc_commit_params() has not been called since the last pdsc_set_param()");
   if (B <= 0 || N <= 1) return fail(PDSC_ERR_SHAPE, "need B >= 1 and N >= 2 (got B=%d N=%d)", B, N);
@@ -488,8 +506,10 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
   if (S > 0) {
     if (io && io->in_seeds)
       PDSC_CUDA(cudaMemcpyAsync(w.seeds, io->in_seeds, (size_t)B * S * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-    else
+    else if (mode == 0)
       launch_pick_seeds(d_src, w.conf, w.seeds, w.key, B, N, S, e->cfg.nms_radius, st);
+    else
+      launch_top_seeds(w.conf, w.seeds, B, N, S, st);
     if (io) copy_tap(io->out_seeds, w.seeds, (size_t)B * S * sizeof(int32_t), st);
     mark(4);
 
@@ -518,12 +538,12 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
     launch_fill_u32(w.conv_mask, 0xFFFFFFFFu, B, st);
     launch_fill_u64(w.best_key, 0ull, B, st);
     launch_nsm_power(w.normed, d_src, d_tgt, w.knn, w.iterates, w.conv_mask, io ? io->out_compat : nullptr, B, N, S, k, T,
-                     e->sigma, e->sigma_spat, st);
+                     e->sigma, e->sigma_spat, mask_stride, st);
     mark(6);
     // ---- a10 + a11 --------------------------------------------------------------------------------
     launch_seed_hypotheses(d_src, d_tgt, w.knn, w.iterates, w.conv_mask, io ? io->in_seed_trans : nullptr, w.seed_trans,
                            w.counts, w.best_key, io ? io->out_eig : nullptr, io ? io->out_power_iters : nullptr, B, N, S,
-                           k, T, e->cfg.inlier_threshold, st);
+                           k, T, e->cfg.inlier_threshold, mask_stride, st);
     if (io) {
       copy_tap(io->out_seed_trans, w.seed_trans, (size_t)B * S * 16 * sizeof(float), st);
       copy_tap(io->out_inlier_counts, w.counts, (size_t)B * S * sizeof(int32_t), st);
@@ -534,16 +554,128 @@ int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, 
     mark(4); mark(5); mark(6); mark(7);
   }
   // ---- a11 (labels) + a12 ---------------------------------------------------------------------------
-  launch_select_refine(d_src, d_tgt, w.seed_trans, w.best_key, d_final_trans, d_final_labels,
+  launch_select_refine(d_src, d_tgt, w.seed_trans, w.best_key, d_final_trans, mode == 0 ? d_final_labels : nullptr,
                        io ? io->out_init_trans : nullptr, io ? io->out_best : nullptr,
                        io ? io->out_refine_solves : nullptr, B, N, S, e->cfg.inlier_threshold,
-                       refinement_threshold(e->cfg.inlier_threshold), 20, st);
+                       refinement_threshold(e->cfg.inlier_threshold), mode == 0 ? 20 : 0, st);
+  if (mode == 1) {
+    PDSC_CUDA(cudaMemcpyAsync(d_final_labels, w.conf, R * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (d_M) {   // M = clamp(1 - (1 - F F^T) / sigma^2, 0, 1), zero diagonal  (PointDSC.py:160-165)
+      LinearArgs a{};
+      a.A = w.normed; a.strideA = (long long)N * kC; a.lda = kC;
+      a.W = w.normed; a.strideW = (long long)N * kC; a.ldw = kC;
+      a.bias = nullptr; a.res = nullptr; a.ldres = 0;
+      a.out = d_M; a.strideO = (long long)N * N; a.ldo = N;
+      a.M = N; a.K = kC; a.Nout = N; a.relu = 0; a.epi = 2; a.batch = B;
+      a.epi_param = e->sigma * e->sigma;
+      launch_linear_simt(a, st);
+    }
+  }
   mark(8);
   if (bev) {
     e->profile_pending = true;
     e->span_launches[PDSC_SPAN_ATTENTION] += inject_feat ? 0 : L;
     e->span_launches[PDSC_SPAN_TOTAL] += 1;
   }
+  PDSC_CUDA(cudaGetLastError());
+  return PDSC_OK;
+}
+
+int pdsc_forward(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, const float* d_src, const float* d_tgt,
+                 float* d_final_trans, float* d_final_labels, const pdsc_stage_io* io, void* d_workspace,
+                 size_t workspace_bytes, void* cuda_stream) {
+  return forward_impl(e, 0, B, N, d_corr_pos, d_src, d_tgt, d_final_trans, d_final_labels, nullptr, io, d_workspace,
+                      workspace_bytes, cuda_stream);
+}
+
+int pdsc_forward_graph(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, const float* d_src, const float* d_tgt,
+                       float* d_final_trans, float* d_final_labels, void* d_workspace, size_t workspace_bytes,
+                       void* cuda_stream) {
+  if (!e) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  DeviceGuard g(e->cfg.device);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  PDSC_CUDA(cudaStreamIsCapturing(st, &cap));
+  if (cap != cudaStreamCaptureStatusNone || e->profiling || !e->committed)   // already inside someone's capture (or nothing to cache): plain enqueue
+    return forward_impl(e, 0, B, N, d_corr_pos, d_src, d_tgt, d_final_trans, d_final_labels, nullptr, nullptr, d_workspace,
+                        workspace_bytes, cuda_stream);
+  for (size_t i = 0; i < e->graphs.size(); ++i) {
+    const auto& q = e->graphs[i];
+    if (q.B == B && q.N == N && q.corr_pos == d_corr_pos && q.src == d_src && q.tgt == d_tgt && q.trans == d_final_trans &&
+        q.labels == d_final_labels && q.workspace == d_workspace && q.precision == e->cfg.precision) {
+      if (i) std::swap(e->graphs[0], e->graphs[i]);
+      PDSC_CUDA(cudaGraphLaunch(e->graphs[0].exec, st));
+      return PDSC_OK;
+    }
+  }
+  // first call with these buffers: run once eagerly (per-device opt-ins, lazy module loading), then capture
+  int rc = forward_impl(e, 0, B, N, d_corr_pos, d_src, d_tgt, d_final_trans, d_final_labels, nullptr, nullptr, d_workspace,
+                        workspace_bytes, cuda_stream);
+  if (rc) return rc;
+  PDSC_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  rc = forward_impl(e, 0, B, N, d_corr_pos, d_src, d_tgt, d_final_trans, d_final_labels, nullptr, nullptr, d_workspace,
+                    workspace_bytes, cuda_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t end = cudaStreamEndCapture(st, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (end != cudaSuccess) return fail(PDSC_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(end));
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t inst = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (inst != cudaSuccess) return fail(PDSC_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(inst));
+  if (e->graphs.size() >= 8) {
+    cudaGraphExecDestroy(e->graphs.back().exec);
+    e->graphs.pop_back();
+  }
+  e->graphs.insert(e->graphs.begin(), pdsc_engine::GraphEntry{B, N, d_corr_pos, d_src, d_tgt, d_final_trans, d_final_labels,
+                                                              d_workspace, e->cfg.precision, exec});
+  return PDSC_OK;   // the eager run above already produced this call's result
+}
+
+int pdsc_forward_eval(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr_pos, const float* d_src, const float* d_tgt,
+                      float* d_final_trans, float* d_confidence, float* d_M, const pdsc_stage_io* io, void* d_workspace,
+                      size_t workspace_bytes, void* cuda_stream) {
+  return forward_impl(e, 1, B, N, d_corr_pos, d_src, d_tgt, d_final_trans, d_confidence, d_M, io, d_workspace,
+                      workspace_bytes, cuda_stream);
+}
+
+int pdsc_eval_stats(pdsc_engine* e, int32_t B, int32_t N, const float* d_pred_trans, const float* d_gt_trans,
+                    const float* d_src, const float* d_tgt, const float* d_pred_labels, const float* d_gt_labels,
+                    float re_thre, float te_thre, float* d_stats, void* cuda_stream) {
+  if (!e) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine");
+  if (B <= 0 || N <= 0) return fail(PDSC_ERR_SHAPE, "need B >= 1 and N >= 1 (got B=%d N=%d)", B, N);
+  if (!d_pred_trans || !d_gt_trans || !d_src || !d_tgt || !d_pred_labels || !d_gt_labels || !d_stats)
+    return fail(PDSC_ERR_INVALID_ARGUMENT, "pdsc_eval_stats: null tensor pointer");
+  DeviceGuard g(e->cfg.device);
+  pdsc::launch_eval_stats(d_pred_trans, d_gt_trans, d_src, d_tgt, d_pred_labels, d_gt_labels, d_stats, B, N, re_thre, te_thre,
+                          static_cast<cudaStream_t>(cuda_stream));
+  PDSC_CUDA(cudaGetLastError());
+  return PDSC_OK;
+}
+
+size_t pdsc_match_scratch_bytes(int32_t Ns, int32_t Nt) {
+  return (Ns > 0 && Nt > 0) ? pdsc::match_scratch_bytes(Ns, Nt) : 0;
+}
+
+int pdsc_match(pdsc_engine* e, int32_t Ns, int32_t Nt, int32_t D, const void* d_src_desc, const void* d_tgt_desc,
+               int32_t desc_is_fp64, const float* d_src_keypts, const float* d_tgt_keypts, int32_t use_mutual,
+               int32_t* d_corr, int32_t* d_count, float* d_corr_pos, float* d_out_src, float* d_out_tgt, void* d_scratch,
+               size_t scratch_bytes, void* cuda_stream) {
+  if (!e) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine");
+  if (Ns <= 0 || Nt <= 0) return fail(PDSC_ERR_SHAPE, "need Ns >= 1 and Nt >= 1 (got %d, %d)", Ns, Nt);
+  if (D < 1 || D > pdsc::match_max_dim()) return fail(PDSC_ERR_UNSUPPORTED, "descriptor dimension %d outside [1, %d]", D, pdsc::match_max_dim());
+  if (e->cfg.in_dim != 6) return fail(PDSC_ERR_UNSUPPORTED, "pdsc_match builds the in_dim = 6 input (engine has in_dim = %d)", e->cfg.in_dim);
+  if (!d_src_desc || !d_tgt_desc || !d_src_keypts || !d_tgt_keypts || !d_corr || !d_count || !d_corr_pos || !d_out_src || !d_out_tgt)
+    return fail(PDSC_ERR_INVALID_ARGUMENT, "pdsc_match: null tensor pointer");
+  if (!d_scratch || scratch_bytes < pdsc::match_scratch_bytes(Ns, Nt))
+    return fail(PDSC_ERR_WORKSPACE, "pdsc_match: scratch too small (%zu bytes given, %zu needed)", scratch_bytes, pdsc::match_scratch_bytes(Ns, Nt));
+  if (reinterpret_cast<uintptr_t>(d_scratch) % 8) return fail(PDSC_ERR_WORKSPACE, "pdsc_match: scratch must be 8-byte aligned");
+  DeviceGuard g(e->cfg.device);
+  pdsc::launch_match(d_src_desc, d_tgt_desc, desc_is_fp64, d_src_keypts, d_tgt_keypts, Ns, Nt, D, use_mutual, d_scratch, d_corr,
+                     d_count, d_corr_pos, d_out_src, d_out_tgt, static_cast<cudaStream_t>(cuda_stream));
   PDSC_CUDA(cudaGetLastError());
   return PDSC_OK;
 }
@@ -635,6 +767,17 @@ int pdsc_forward_host(pdsc_engine* e, int32_t B, int32_t N, const float* h_corr_
   // ordered behind whatever the caller's stream held, and is awaited right behind the SC launch
   PDSC_CUDA(cudaMemcpyAsync(d_src, h_src, R * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
   PDSC_CUDA(cudaMemcpyAsync(d_tgt, h_tgt, R * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (R <= kGraphRows && !e->profiling) {
+    // small call (the evaluation loops' bs = 1): launch-bound, so everything stays on one stream and the forward is one
+    // graph launch over the engine-owned (address-stable) buffers
+    PDSC_CUDA(cudaMemcpyAsync(d_corr, h_corr_pos, R * in_dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    const int rc = pdsc_forward_graph(e, B, N, d_corr, d_src, d_tgt, d_tr, d_lab, e->host_ws, e->host_ws_bytes, cuda_stream);
+    if (rc) return rc;
+    PDSC_CUDA(cudaMemcpyAsync(h_final_trans, d_tr, (size_t)B * 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PDSC_CUDA(cudaMemcpyAsync(h_final_labels, d_lab, R * sizeof(float), cudaMemcpyDeviceToHost, st));
+    PDSC_CUDA(cudaStreamSynchronize(st));
+    return PDSC_OK;
+  }
   PDSC_CUDA(cudaEventRecord(e->copy_fork, st));
   PDSC_CUDA(cudaStreamWaitEvent(e->copy_stream, e->copy_fork, 0));
   PDSC_CUDA(cudaMemcpyAsync(d_corr, h_corr_pos, R * in_dim * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));

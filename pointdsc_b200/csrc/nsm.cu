@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kNsmThreads) nsm_power_kernel(const float* __r
                                                                 const int32_t* __restrict__ knn_idx,
                                                                 float* __restrict__ iterates, uint32_t* __restrict__ conv_mask,
                                                                 float* __restrict__ compat_out, int N, int S, int k, int iters,
-                                                                float sigma2, float sigmad2) {
+                                                                float sigma2, float sigmad2, int mask_stride) {
   extern __shared__ __align__(16) float sm[];
   const int ms = k | 1;                  // odd row stride of M: conflict-free row-per-thread reads
   const int kp = (k + 3) & ~3;
@@ -305,19 +305,21 @@ __global__ void __launch_bounds__(kNsmThreads) nsm_power_kernel(const float* __r
     if (all_ok) mask |= (1u << t);
     __syncthreads();
   }
-  if (tid == 0) atomicAnd(conv_mask + b, mask);
+  // testing mode: the early exit is a per-set decision (mask_stride 1); non-testing mode: the reference's allclose spans
+  // the whole [bs * S, k] batch (PointDSC.py:354), so every set ANDs into word 0 (mask_stride 0)
+  if (tid == 0) atomicAnd(conv_mask + (size_t)b * mask_stride, mask);
 }
 
 void launch_nsm_power(const float* normed, const float* src, const float* tgt, const int32_t* knn_idx, float* iterates,
                       uint32_t* conv_mask, float* compat_out, int B, int N, int S, int k, int iters, float sigma,
-                      float sigma_d, cudaStream_t st) {
+                      float sigma_d, int mask_stride, cudaStream_t st) {
   if (S <= 0) return;
   const int ms = k | 1;
   const int kp = (k + 3) & ~3;
   const int smem = (kC * kp + k * ms + 6 * k + k + 4) * (int)sizeof(float);
   ensure_dynamic_smem(reinterpret_cast<const void*>(nsm_power_kernel), smem);
   nsm_power_kernel<<<dim3(S, B), kNsmThreads, smem, st>>>(normed, src, tgt, knn_idx, iterates, conv_mask, compat_out, N, S, k,
-                                                          iters, sigma * sigma, sigma_d * sigma_d);
+                                                          iters, sigma * sigma, sigma_d * sigma_d, mask_stride);
 }
 
 }  // namespace pdsc

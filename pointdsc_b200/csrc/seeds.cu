@@ -89,6 +89,21 @@ __global__ void __launch_bounds__(1024) seed_sort_kernel(const float* __restrict
 
 int pick_seeds_max_n() { return kSeedMaxN; }
 
+static void launch_seed_sort(const float* key, int32_t* seeds, int B, int N, int S, cudaStream_t st) {
+  int P = 2;
+  while (P < N) P <<= 1;
+  const int smem = P * (int)sizeof(unsigned long long);
+  ensure_dynamic_smem(reinterpret_cast<const void*>(seed_sort_kernel), smem);
+  const int threads = P / 2 < 1024 ? (P / 2 < 32 ? 32 : P / 2) : 1024;
+  seed_sort_kernel<<<B, threads, smem, st>>>(key, seeds, N, P, S);
+}
+
+// a6' — the non-testing seed rule (models/PointDSC.py:176): argsort(confidence, descending)[:S], no suppression.
+// Ties: lowest index first (the reference's argsort is unstable).
+void launch_top_seeds(const float* conf, int32_t* seeds, int B, int N, int S, cudaStream_t st) {
+  if (S > 0) launch_seed_sort(conf, seeds, B, N, S, st);
+}
+
 void launch_pick_seeds(const float* src, const float* conf, int32_t* seeds, float* key_scratch, int B, int N, int S,
                        float radius, cudaStream_t st) {
   // smallest float x with sqrtf(x) >= radius (IEEE sqrt on the host == the device's sqrt.rn)
@@ -97,12 +112,7 @@ void launch_pick_seeds(const float* src, const float* conf, int32_t* seeds, floa
   while (std::sqrt(d2_min) < radius) d2_min = std::nextafter(d2_min, INFINITY);
   dim3 g1((N + kNmsTile - 1) / kNmsTile, B);
   nms_key_kernel<<<g1, kNmsTile, 0, st>>>(src, conf, key_scratch, N, d2_min);
-  int P = 2;
-  while (P < N) P <<= 1;
-  const int smem = P * (int)sizeof(unsigned long long);
-  ensure_dynamic_smem(reinterpret_cast<const void*>(seed_sort_kernel), smem);
-  const int threads = P / 2 < 1024 ? (P / 2 < 32 ? 32 : P / 2) : 1024;
-  seed_sort_kernel<<<B, threads, smem, st>>>(key_scratch, seeds, N, P, S);
+  launch_seed_sort(key_scratch, seeds, B, N, S, st);
 }
 
 }  // namespace pdsc

@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(256) seed_hypotheses_kernel(
     const float* __restrict__ src, const float* __restrict__ tgt, const int32_t* __restrict__ knn_idx,
     const float* __restrict__ iterates, const uint32_t* __restrict__ conv_mask, const float* __restrict__ seed_trans_in,
     float* __restrict__ seed_trans, int32_t* __restrict__ inlier_counts, unsigned long long* __restrict__ best_key,
-    float* __restrict__ eig_out, int32_t* __restrict__ power_iters, int N, int S, int k, int iters, float thr) {
+    float* __restrict__ eig_out, int32_t* __restrict__ power_iters, int N, int S, int k, int iters, float thr,
+    int mask_stride) {
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int s = blockIdx.x * 8 + warp;
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(256) seed_hypotheses_kernel(
   const float* pt = tgt + (size_t)b * N * 3;
 
   // exit iteration of this set: first iteration at which every seed passed allclose, else the cap
-  const uint32_t m = conv_mask[b] & ((iters >= 32) ? 0xFFFFFFFFu : ((1u << iters) - 1u));
+  const uint32_t m = conv_mask[(size_t)b * mask_stride] & ((iters >= 32) ? 0xFFFFFFFFu : ((1u << iters) - 1u));
   const int t_exit = m ? (__ffs(m) - 1) : (iters - 1);
   if (s == 0 && lane == 0 && power_iters) power_iters[b] = t_exit + 1;
 
@@ -130,11 +131,12 @@ __global__ void __launch_bounds__(256) seed_hypotheses_kernel(
 void launch_seed_hypotheses(const float* src, const float* tgt, const int32_t* knn_idx, const float* iterates,
                             const uint32_t* conv_mask, const float* seed_trans_in, float* seed_trans,
                             int32_t* inlier_counts, unsigned long long* best_key, float* eig_out, int32_t* power_iters,
-                            int B, int N, int S, int k, int iters, float inlier_threshold, cudaStream_t st) {
+                            int B, int N, int S, int k, int iters, float inlier_threshold, int mask_stride,
+                            cudaStream_t st) {
   if (S <= 0) return;
   seed_hypotheses_kernel<<<dim3((S + 7) / 8, B), 256, 0, st>>>(src, tgt, knn_idx, iterates, conv_mask, seed_trans_in,
                                                               seed_trans, inlier_counts, best_key, eig_out, power_iters,
-                                                              N, S, k, iters, inlier_threshold);
+                                                              N, S, k, iters, inlier_threshold, mask_stride);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -183,7 +185,8 @@ __global__ void __launch_bounds__(kRefThreads) select_refine_kernel(
   if (tid == 0 && best_out) best_out[b] = best;
 
   // final_labels: inlier mask of the selected hypothesis BEFORE refinement (PointDSC.py:333-335)
-  for (int j = tid; j < N; j += kRefThreads) {
+  // (non-testing mode returns the confidence logits instead, PointDSC.py:190-191: final_labels is null there)
+  for (int j = tid; final_labels && j < N; j += kRefThreads) {
     const float d = residual(T, ps[(size_t)j * 3], ps[(size_t)j * 3 + 1], ps[(size_t)j * 3 + 2], pt[(size_t)j * 3],
                              pt[(size_t)j * 3 + 1], pt[(size_t)j * 3 + 2]);
     final_labels[(size_t)b * N + j] = (d < thr) ? 1.0f : 0.0f;

@@ -154,3 +154,18 @@ def test_kabsch_recovers_known_motion():
     out = O.weighted_kabsch(a, b, torch.rand(4, 50, generator=g))
     assert torch.allclose(out[:, :3, :3], q.expand(4, 3, 3), atol=1e-5)
     assert torch.allclose(out[:, :3, 3], t.expand(4, 3), atol=1e-5)
+
+
+def test_validation_forward_matches_reference():
+    """The forward WITHOUT the 'testing' key (rows a6' / f4): oracle vs the reference's own batched eval-mode output
+    (tests/golden/make_eval_golden.py)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "eval_3dmatch_n256_b3.npz"))
+    sd = load_snapshot("3dmatch")
+    out = O.forward_validation(sd, O.default_config("3dmatch"), _t(z["corr_pos"]), _t(z["src_keypts"]), _t(z["tgt_keypts"]))
+    assert np.abs(out["final_labels"].numpy() - z["final_labels"]).max() < 5e-3       # confidence logits (fp32 summation order)
+    assert np.abs(out["M"].numpy() - z["M"]).max() < 2e-4
+    assert np.array_equal(np.diagonal(out["M"].numpy(), axis1=1, axis2=2), np.zeros((3, 256), np.float32))
+    same = (out["seeds"].numpy() == z["seeds"]).mean()
+    assert same > 0.9                                                                   # ranking of near-equal logits
+    assert np.abs(out["final_trans"].numpy() - z["final_trans"]).max() < 1e-4
