@@ -4,17 +4,22 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one testing-mode forward over one batch of B synthetic correspondence sets (default: the
-configuration BASELINE.json's metric is quoted on, N=1000, B=256, 3DMatch snapshot).  Batches shard
-across ranks with no data-path collective (weak scaling: B sets per GPU); NCCL only reduces the timing.
+A "step" is one testing-mode forward over one batch of B synthetic correspondence sets (default: the configuration
+BASELINE.json's metric is quoted on, N=1000, B=256 per GPU, 3DMatch snapshot, inlier ratios 0.05/0.1/0.3/0.5 of SURVEY.md §8d).
+Batches shard across ranks with no data-path collective (weak scaling: B sets per GPU); NCCL only reduces the timing.
 
-value   : sets/s with inputs resident in HBM (CUDA events around exactly K steps, max over ranks)
-e2e     : sets/s through the reference-facing module call with pinned HOST tensors — the H2D copy of the
-          step's inputs and the D2H copy of (final_trans, final_labels) are inside the timed region
-roofline: the dominant kernel (per-layer SC-weighted attention) — algorithmic FLOPs per launch / its mean
-          launch duration measured live with CUDA events on the launch stream (pdsc_profile_*)
-cpu_baseline: the CPU oracle (a torch-CPU restatement of the reference, "port") on the box's host cores,
-          bounded sample, rank 0 at N=1 only.  `--impl reference` times that same CPU path as its own arm.
+value        : sets/s with inputs resident in HBM (CUDA events around exactly K steps, max over ranks, profiling events OFF)
+e2e          : sets/s through the reference-facing module call with pinned HOST tensors — the H2D copy of the step's inputs
+               and the D2H copy of (final_trans, final_labels) are inside the timed region
+roofline     : the dominant kernel (per-layer SC-weighted attention): algorithmic FLOPs per launch / its mean launch duration
+               measured live with CUDA events on the launch stream (pdsc_profile_*, a separate profiled pass of K steps)
+roofline_stages : every stage of the path against the roofline that bounds it (SURVEY.md §8d formulas)
+determinism  : the K timed steps process identical data; their outputs must be bit-identical (asserted)
+cpu_baseline : the reference's CPU path on the box's host cores, bounded sample, rank 0 at N=1 only: the UNMODIFIED reference
+               module from baseline/_ref when that install is present (kind "reference"), else the torch-CPU restatement in
+               oracle/ (kind "port").  `--impl reference` times the same CPU path as its own arm.
+extras       : bs=1 latency (the evaluation loops' batch size), BASELINE config D sweep (N in 500..5000, 128 sets per GPU),
+               strong scaling of the global B=256 batch when N > 1.
 """
 import argparse
 import json
@@ -27,15 +32,20 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+SNAP_DIRS = {"3dmatch": "PointDSC_3DMatch_release", "kitti": "PointDSC_KITTI_release"}
+CTOR = {"3dmatch": dict(inlier_threshold=0.10, sigma_d=0.10, nms_radius=0.10),      # evaluation/test_3DMatch.py:215-224
+        "kitti": dict(inlier_threshold=0.6, sigma_d=1.2, nms_radius=0.6)}            # evaluation/test_KITTI.py:166-191
+RATIOS = [0.05, 0.1, 0.3, 0.5]     # inlier ratios of the synthetic sets, cycled over the global set index
 
 METRIC = "correspondence-sets/sec (PointDSC.forward, N=1000, B=256)"   # BASELINE.json's metric (the default configuration)
+UNIT = "sets/s"
 
 
 def metric_of(args):
-    """The metric label of this run: BASELINE.json's string at the default configuration, the same label with the actual
-    N and B otherwise (parity-test sized runs must not carry the headline label)."""
+    """BASELINE.json's label at the default configuration, the same label with the actual N and B otherwise (parity-test
+    sized runs must not carry the headline label)."""
     return METRIC if (args.n == 1000 and args.batch == 256) else f"correspondence-sets/sec (PointDSC.forward, N={args.n}, B={args.batch})"
-UNIT = "sets/s"
 
 
 def parse():
@@ -46,20 +56,25 @@ def parse():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--n", type=int, default=1000)
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--k", type=int, default=40)
     ap.add_argument("--dataset", default="3dmatch", choices=["3dmatch", "kitti"])
     ap.add_argument("--precision", default=os.environ.get("POINTDSC_PRECISION", "fp16x3"))
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip bs=1 latency / config-D sweep / strong scaling")
     return ap.parse_args()
 
 
 def config_of(args, world):
     return {"workload": f"{args.dataset}-like synthetic correspondences, N={args.n}, B={args.batch} sets per GPU per step, "
-                        f"k=40, S={int(args.n * 0.1)} seeds, 12 SCNonlocal layers, released {args.dataset} snapshot",
-            "n": args.n, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+                        f"k={args.k}, S={int(args.n * 0.1)} seeds, 12 SCNonlocal layers, released {args.dataset} snapshot, "
+                        f"inlier ratios {RATIOS} cycled over the global set index",
+            "n": args.n, "batch_per_gpu": args.batch, "global_batch": args.batch * world, "k": args.k,
             "precision": args.precision, "parallelism": f"dp{world} (sets sharded, no data-path collective)",
             "l2": "per-step working set exceeds L2 (SC matrix alone is 4*N*NS*B bytes = "
-                  f"{4 * args.n * ((args.n + 63) // 64 * 64) * args.batch / 1e6:.0f} MB vs 126 MB L2); no flush needed"}
+                  f"{4 * args.n * ((args.n + 63) // 64 * 64) * args.batch / 1e6:.0f} MB vs 126 MB L2); no flush needed",
+            "profiling": "stage events are OFF in the timed loops of value / e2e; stage shares and rooflines come from a "
+                         "separate profiled pass of the same K steps"}
 
 
 def load_snapshot(dataset):
@@ -69,15 +84,14 @@ def load_snapshot(dataset):
     return {k: torch.from_numpy(z[k]) for k in z.files}
 
 
-def make_inputs(args, rank, world=1):
-    """This rank's shard of the global batch (B sets per GPU, weak scaling): global set g has seed g and an inlier
-    ratio cycling through 0.5 / 0.3 / 0.2 / 0.4, so any sharding of the same global batch sees the same sets."""
+def make_inputs(n, batch, dataset, rank, world=1):
+    """This rank's shard of a global batch of batch*world sets: global set g has seed g and inlier ratio RATIOS[g % 4], so any
+    sharding of the same global batch sees the same sets."""
     import torch
     from pointdsc_b200.shard import shard_bounds
     from pointdsc_b200.synth import make_pair
-    ratios = [0.5, 0.3, 0.2, 0.4]
-    lo, hi = shard_bounds(args.batch * world, rank, world)
-    pairs = [make_pair(g, args.n, args.dataset, ratios[g % 4]) for g in range(lo, hi)]
+    lo, hi = shard_bounds(batch * world, rank, world)
+    pairs = [make_pair(g, n, dataset, RATIOS[g % 4]) for g in range(lo, hi)]
     return {k: torch.stack([p[k] for p in pairs], 0).contiguous() for k in pairs[0]}
 
 
@@ -125,22 +139,60 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def pick_cpu_threads(args, sets):
-    """torch's CPU ops on small tensors slow down badly when oversubscribed (128 threads: 26 s per N=1000 forward,
-    8 threads: 0.17 s), so "all the host threads it can use" is found by timing one forward per candidate count
-    (bounded: a candidate that takes > 4x the best so far ends the search) and keeping the fastest."""
+# --------------------------------------------------------------------------------------------------------------------
+# the CPU arm: the unmodified reference (baseline/_ref) when installed, else the oracle port
+# --------------------------------------------------------------------------------------------------------------------
+class CpuPath:
+    """One bs=1 testing-mode forward of the reference's CPU implementation per call."""
+
+    def __init__(self, dataset, k=40):
+        import torch
+        self.torch = torch
+        self.kind = None
+        ref_model = os.path.join(REF_DIR, "models", "PointDSC.py")
+        pkl = os.path.join(REF_DIR, "snapshot", SNAP_DIRS[dataset], "models", "model_best.pkl")
+        if os.path.exists(ref_model) and os.path.exists(pkl):
+            sys.dont_write_bytecode = True
+            if REF_DIR not in sys.path:
+                sys.path.insert(0, REF_DIR)
+            import models.PointDSC as ref_mod       # the UNMODIFIED reference module (installed copy, see __graft_entry__.install_reference)
+            cfg = json.load(open(os.path.join(REF_DIR, "snapshot", SNAP_DIRS[dataset], "config.json")))
+            self.model = ref_mod.PointDSC(in_dim=cfg["in_dim"], num_layers=cfg["num_layers"], num_channels=cfg["num_channels"],
+                                          num_iterations=cfg["num_iterations"], ratio=cfg["ratio"], k=k, **CTOR[dataset])
+            res = self.model.load_state_dict(torch.load(pkl, map_location="cpu"), strict=False)
+            assert res.missing_keys == [], res
+            self.model.eval()
+            self.kind = "reference"
+            self.what = "unmodified reference module (baseline/_ref/models/PointDSC.py), released snapshot, eval(), no_grad, fp32"
+        else:
+            from oracle import pointdsc_oracle as O
+            self.O, self.sd = O, load_snapshot(dataset)
+            self.cfg = O.default_config(dataset)
+            self.cfg["k"] = k
+            self.kind = "port"
+            self.what = "torch-CPU restatement of the reference (oracle/pointdsc_oracle.py: baseline/_ref is not installed), fp32"
+
+    def forward(self, corr_pos, src, tgt):
+        if self.kind == "reference":
+            with self.torch.no_grad():
+                return self.model({"corr_pos": corr_pos[None], "src_keypts": src[None], "tgt_keypts": tgt[None], "testing": True})
+        return self.O.forward_testing(self.sd, self.cfg, corr_pos, src, tgt)
+
+
+def pick_cpu_threads(cpu, sets):
+    """torch's CPU ops on small tensors slow down badly when oversubscribed (128 threads: 26 s per N=1000 forward, 8 threads:
+    0.17 s), so "all the host threads it can use" is found by timing one forward per candidate count (bounded: a candidate that
+    takes > 4x the best so far ends the search) and keeping the fastest."""
     import torch
-    from oracle import pointdsc_oracle as O
-    sd = load_snapshot(args.dataset)
-    cfg = O.default_config(args.dataset)
     ncpu = os.cpu_count() or 1
     cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
     best, best_t = cands[0], None
+    one = (sets["corr_pos"][0], sets["src_keypts"][0], sets["tgt_keypts"][0])
     for c in cands:
         torch.set_num_threads(c)
-        O.forward_testing(sd, cfg, sets["corr_pos"][0], sets["src_keypts"][0], sets["tgt_keypts"][0])  # warm this pool size
+        cpu.forward(*one)                     # warm this pool size
         t0 = time.perf_counter()
-        O.forward_testing(sd, cfg, sets["corr_pos"][0], sets["src_keypts"][0], sets["tgt_keypts"][0])
+        cpu.forward(*one)
         dt = time.perf_counter() - t0
         if best_t is None or dt < best_t:
             best, best_t = c, dt
@@ -149,48 +201,42 @@ def pick_cpu_threads(args, sets):
     return best
 
 
-def cpu_oracle_rate(args, sets, budget_s, threads):
-    """sets/s of the CPU oracle on a bounded sample of the same workload."""
+def cpu_rate(cpu, sets, budget_s, threads):
+    """sets/s of the CPU path on a bounded sample of the same workload."""
     import torch
-    from oracle import pointdsc_oracle as O
     torch.set_num_threads(threads)
-    sd = load_snapshot(args.dataset)
-    cfg = O.default_config(args.dataset)
-    O.forward_testing(sd, cfg, sets["corr_pos"][0], sets["src_keypts"][0], sets["tgt_keypts"][0])  # warm-up
+    cpu.forward(sets["corr_pos"][0], sets["src_keypts"][0], sets["tgt_keypts"][0])  # warm-up
     done, t0 = 0, time.perf_counter()
     while done < sets["corr_pos"].shape[0] and (time.perf_counter() - t0 < budget_s or done < 2):
-        O.forward_testing(sd, cfg, sets["corr_pos"][done], sets["src_keypts"][done], sets["tgt_keypts"][done])
+        cpu.forward(sets["corr_pos"][done], sets["src_keypts"][done], sets["tgt_keypts"][done])
         done += 1
     dt = time.perf_counter() - t0
     return done / dt, done, dt
 
 
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path, as restated by the oracle (the reference is Python and
-    cannot travel to the GPU box), all host threads, loop of bs=1 testing forwards."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores, loop of bs=1 testing
+    forwards (the reference asserts bs == 1 in testing mode), every step a bounded sample of the workload."""
     if rank != 0:
         return
     import torch
-    from oracle import pointdsc_oracle as O
-    sd = load_snapshot(args.dataset)
-    cfg = O.default_config(args.dataset)
-    probe = make_inputs(argparse.Namespace(**{**vars(args), "batch": 4}), 0)
-    threads = pick_cpu_threads(args, probe)
+    cpu = CpuPath(args.dataset, args.k)
+    probe = make_inputs(args.n, 4, args.dataset, 0)
+    threads = pick_cpu_threads(cpu, probe)
     torch.set_num_threads(threads)
     t0 = time.perf_counter()
-    O.forward_testing(sd, cfg, probe["corr_pos"][1], probe["src_keypts"][1], probe["tgt_keypts"][1])
+    cpu.forward(probe["corr_pos"][1], probe["src_keypts"][1], probe["tgt_keypts"][1])
     one = max(time.perf_counter() - t0, 1e-3)
     # a step = a bounded sample of the batch, sized so that steps + warmup stay within ~2 minutes
     per_step = int(max(1, min(args.batch, 120.0 / (one * (args.steps + args.warmup)))))
     need = per_step * (args.steps + args.warmup)
-    small = argparse.Namespace(**{**vars(args), "batch": min(args.batch, need)})
-    sets = make_inputs(small, 0)
+    sets = make_inputs(args.n, min(args.batch, need), args.dataset, 0)
     nsets = sets["corr_pos"].shape[0]
 
     def step(i):
         for j in range(per_step):
             b = (i * per_step + j) % nsets
-            O.forward_testing(sd, cfg, sets["corr_pos"][b], sets["src_keypts"][b], sets["tgt_keypts"][b])
+            cpu.forward(sets["corr_pos"][b], sets["src_keypts"][b], sets["tgt_keypts"][b])
     for i in range(args.warmup):
         step(i)
     t0 = time.perf_counter()
@@ -198,75 +244,137 @@ def run_reference(args, rank, world):
         step(args.warmup + i)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    sample = (f"{per_step} sets per step (loop of bs=1 testing forwards) x {args.steps} steps of the N={args.n} workload, "
-              f"{threads} host threads (fastest of the candidate counts on {os.cpu_count()} cores)")
+    sample = (f"{per_step} sets per step (loop of bs=1 testing forwards; the engine's step is {args.batch} sets, rates are per set) "
+              f"x {args.steps} steps of the N={args.n} workload, {threads} host threads (fastest of the candidate counts on "
+              f"{os.cpu_count()} cores); {cpu.what}")
+    cfg = config_of(args, world)
+    cfg["reference_sets_per_step"] = per_step
     print(json.dumps({
         "impl": "reference", "metric": metric_of(args), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_of(args, world),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": cpu.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# per-stage rooflines (SURVEY.md §8d formulas; per rank and per step)
+# --------------------------------------------------------------------------------------------------------------------
+def stage_rooflines(prof, steps, B, N, k, peaks, sm_count, sm_max_mhz):
+    """{stage: {bound, algorithmic work, achieved, peak, frac, ms_per_step}}.  HBM bytes are ALGORITHMIC bytes of the stage as
+    designed (what it must read and write once), FLOPs are algorithmic (the fp16x3 format executes 3x the tensor FLOPs)."""
+    S, L, C = int(N * 0.1), 12, 128
+    KT, QT = (N + 63) // 64, (N + 127) // 128
+    hbm = float(peaks.get("hbm_gbs", 6568.4))                 # GB/s, measured copy bandwidth
+    tens = float(peaks.get("bf16_tflops_sustained", 1440.5))  # TFLOP/s, measured sustained cuBLAS bf16
+    fp32 = sm_count * 128 * 2 * (sm_max_mhz or 1965.0) * 1e6 / 1e12   # TFLOP/s, FFMA lanes x max clock (nominal: no measured fp32 peak)
+    T = 10
+    rows = {
+        "sc": ("hbm", float(B) * KT * QT * 32768, None),                                      # tiled SC write (a1)
+        "linear": ("hbm", float(B) * N * (512 + L * 5120), float(B) * N * L * 172032.0),          # layer0 out + per layer: feat in, feat1 out+2 in, Q/K/V images, msg in, feat out
+        "attention": ("tensor", float(B) * L * (KT * QT * 32768 + 4.0 * N * 512), float(B) * L * 4.0 * C * N * N),
+        "head": ("hbm", float(B) * N * (512 + 512 + 4), float(B) * N * 2.0 * (128 * 32 + 32 * 32 + 32)),
+        "seeds": ("fp32", None, float(B) * N * N * 8.0),                                         # N^2 pair tests, ~8 FLOP each
+        "knn": ("hbm", float(B) * (N * 512 + 2.0 * S * N * 4), float(B) * 2.0 * S * N * C),      # normed read, S x N distances write + read
+        "nsm": ("hbm", float(B) * S * (k * 536 + T * k * 4), float(B) * S * (k * k * C + T * 2.0 * k * k)),   # gather k rows + points, iterates out
+        "hypotheses": ("fp32", None, float(B) * S * N * 30.0),
+        "refine": ("latency", None, None),
+    }
+    out = {}
+    for name, (bound, nbytes, flops) in rows.items():
+        ms = prof[name][0] / steps
+        e = {"bound": bound, "ms_per_step": ms, "algorithmic_bytes": nbytes, "algorithmic_flops": flops}
+        if ms > 0:
+            if nbytes:
+                e["achieved_gbs"] = nbytes / (ms * 1e-3) / 1e9
+                e["frac_of_hbm_peak"] = e["achieved_gbs"] / hbm
+            if flops:
+                e["achieved_tflops"] = flops / (ms * 1e-3) / 1e12
+                e["frac_of_tensor_peak" if bound in ("tensor", "hbm") else "frac_of_fp32_peak"] = e["achieved_tflops"] / (tens if bound in ("tensor", "hbm") else fp32)
+            e["frac"] = {"hbm": e.get("frac_of_hbm_peak"), "tensor": e.get("frac_of_tensor_peak"), "fp32": e.get("frac_of_fp32_peak"),
+                         "latency": None}[bound]
+        out[name] = e
+    out["_peaks"] = {"hbm_gbs": hbm, "tensor_tflops": tens, "fp32_tflops_nominal": fp32,
+                     "source": "MEASURED_PEAKS.json (hbm_gbs, bf16_tflops_sustained)" if peaks else "B200_PROFILING.md fallback"}
+    return out
+
+
+def time_steps(model, d, steps, keep=False):
+    """CUDA events around exactly `steps` device-resident forwards; returns (ms, outputs of every step if keep)."""
+    import torch
+    outs = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        o = model.run(d["corr_pos"], d["src_keypts"], d["tgt_keypts"])
+        if keep:
+            outs.append(o)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), outs
 
 
 def run_engine(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from pointdsc_b200 import PointDSC
+    from pointdsc_b200.shard import gather_counters, output_checksum
+    from pointdsc_b200.shard import max_over_ranks as _max_over_ranks
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfgd = {"3dmatch": dict(inlier_threshold=0.10, sigma_d=0.10, nms_radius=0.10),
-            "kitti": dict(inlier_threshold=0.6, sigma_d=1.2, nms_radius=0.6)}[args.dataset]
-    model = PointDSC(in_dim=6, num_layers=12, num_channels=128, num_iterations=10, ratio=0.1, k=40,
-                     precision=args.precision, **cfgd)
+    model = PointDSC(in_dim=6, num_layers=12, num_channels=128, num_iterations=10, ratio=0.1, k=args.k,
+                     precision=args.precision, **CTOR[args.dataset])
     res = model.load_state_dict(load_snapshot(args.dataset), strict=False)
     assert res.missing_keys == [], res
     model = model.to(dev).eval()
-    host = make_inputs(args, rank, world)
+    B, N = args.batch, args.n
+    host = make_inputs(N, B, args.dataset, rank, world)
     pinned = {k: host[k].pin_memory() for k in ("corr_pos", "src_keypts", "tgt_keypts")}
     d = {k: host[k].to(dev) for k in ("corr_pos", "src_keypts", "tgt_keypts")}
-    B, N = args.batch, args.n
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    from pointdsc_b200.shard import gather_counters, output_checksum
-    from pointdsc_b200.shard import max_over_ranks as _max_over_ranks
-
     def max_over_ranks(x):
         return _max_over_ranks(x, dev)
 
-    # ---- device-resident throughput ----------------------------------------------------------------------
+    # ---- device-resident throughput (profiling events off) -------------------------------------------------------------
     for _ in range(args.warmup):
-        out = model.run(d["corr_pos"], d["src_keypts"], d["tgt_keypts"])
-    model.profile(True)
+        model.run(d["corr_pos"], d["src_keypts"], d["tgt_keypts"])
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        out = model.run(d["corr_pos"], d["src_keypts"], d["tgt_keypts"])
-    e1.record()
+    ms_local, outs = time_steps(model, d, args.steps, keep=True)
     barrier()
     t1 = time.perf_counter()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    prof = model.profile_read()
-    model.profile(False)
+    ms = max_over_ranks(ms_local)
     clocks = sampler.stop(t0, t1)
     value = B * world * args.steps / (ms * 1e-3)
+    out = outs[-1]
+    # the timed steps process identical data: a race or a read of stale memory would show up as a differing step
+    identical = all(torch.equal(o["final_trans"], outs[0]["final_trans"]) and torch.equal(o["final_labels"], outs[0]["final_labels"])
+                    for o in outs[1:])
+    assert identical, "outputs of the timed steps differ although their inputs are identical"
 
     # sanity: the timed work produced registrations (not a skipped / cached forward)
     err = (out["final_trans"].cpu() - host["gt_trans"]).abs().amax(dim=(1, 2))
     scale = 0.05 if args.dataset == "3dmatch" else 0.5
     registered = float((err < scale).float().mean())
+    del outs
 
-    # ---- end to end: pinned host tensors in, host tensors out, copies inside the timed region -------------
+    # ---- the same K steps with the engine's stage events on: stage shares, per-launch time of the dominant kernel ---------
+    model.profile(True)
+    time_steps(model, d, args.steps)
+    prof = model.profile_read()
+    model.profile(False)
+
+    # ---- end to end: pinned host tensors in, host tensors out, copies inside the timed region --------------------------
     for _ in range(min(2, args.warmup)):
         model.run(pinned["corr_pos"], pinned["src_keypts"], pinned["tgt_keypts"])
     barrier()
@@ -279,11 +387,19 @@ def run_engine(args, rank, world, local_rank):
     e2e_value = B * world * args.steps / e2e_s
     h2d = sum(pinned[k].numel() * 4 for k in pinned)
     d2h = ho["final_trans"].numel() * 4 + ho["final_labels"].numel() * 4
+    assert torch.equal(ho["final_trans"], out["final_trans"].cpu()), "host path and device path disagree"
+
+    # ---- extras: bs=1 latency, BASELINE config D sweep, strong scaling -------------------------------------------------
+    extras = None
+    if not args.no_extras:
+        extras = measure_extras(args, model, rank, world, dev, barrier, max_over_ranks)
 
     counters = output_checksum(out["final_trans"].cpu(), out["final_labels"].cpu())
     counters["registered"] = registered
     per_rank = gather_counters(counters)     # NCCL is used for timing / counters only: there is no data-path collective
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     registered = sum(c["registered"] * c["sets"] for c in per_rank) / max(1.0, sum(c["sets"] for c in per_rank))
     # ---- roofline of the dominant kernel --------------------------------------------------------------------
@@ -303,8 +419,7 @@ def run_engine(args, rank, world, local_rank):
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "attention_traffic.json")))
-        key = f"{args.precision}_N{N}_B{B}"
-        traffic = tj.get(key, {}).get("dram_bytes_per_launch")
+        traffic = tj.get(f"{args.precision}_N{N}_B{B}", {}).get("dram_bytes_per_launch")
     except Exception:
         pass
     executed = {"bf16x3": 3, "fp16x3": 3, "bf16": 1, "fp32": 1}[args.precision]
@@ -320,14 +435,17 @@ def run_engine(args, rank, world, local_rank):
     total_ms = prof["total"][0]
     stages = {k: {"ms_per_step": v[0] / args.steps, "share": (v[0] / total_ms if total_ms > 0 else None)}
               for k, v in prof.items() if k != "total"}
+    props = torch.cuda.get_device_properties(dev)
+    rstages = stage_rooflines(prof, args.steps, B, N, min(args.k, N - 1), peaks, props.multi_processor_count, clocks.get("sm_max_mhz"))
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = pick_cpu_threads(args, host)
-        rate, done, dt = cpu_oracle_rate(args, host, args.cpu_seconds, threads)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+        cpath = CpuPath(args.dataset, args.k)
+        threads = pick_cpu_threads(cpath, host)
+        rate, done, dt = cpu_rate(cpath, host, args.cpu_seconds, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": cpath.kind,
                "sample": f"first {done} sets of the step's batch, loop of bs=1 testing forwards, {dt:.1f} s on {threads} host threads "
-                         f"(fastest of the candidate thread counts on {os.cpu_count()} cores; torch {torch.__version__} CPU fp32)"}
+                         f"(fastest of the candidate thread counts on {os.cpu_count()} cores; torch {torch.__version__} CPU); {cpath.what}"}
     launches = model.launches_per_forward(B, N) * args.steps
     print(json.dumps({
         "metric": metric_of(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -336,11 +454,72 @@ def run_engine(args, rank, world, local_rank):
                   "fp16x3": "fp16 hi/lo split (3 products) with f32 accumulate", "fp32": "f32"}[args.precision],
         "data": "synthetic", "config": config_of(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "stages": stages,
-        "registered_fraction": registered,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_stages": rstages, "cpu_baseline": cpu,
+        "stages": stages, "registered_fraction": registered,
+        "determinism": {"timed_steps_bit_identical": identical, "steps_compared": args.steps},
+        "extras": extras,
         "rank_checksums": [{k: c[k] for k in ("sets", "trans_abs", "inliers")} for c in per_rank]}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_extras(args, model, rank, world, dev, barrier, max_over_ranks):
+    """Bounded extra measurements with the same module (all ranks take part so that barriers match)."""
+    import torch
+    out = {}
+    # (1) bs = 1 latency: the batch size every caller of the reference uses (evaluation/test_3DMatch.py:133, test_KITTI.py:126);
+    #     device-resident = pdsc_forward_graph replay, e2e = module call with host tensors (H2D + forward + D2H + sync)
+    lat = {}
+    for n in (1000, 5000):
+        one = make_inputs(n, 1, args.dataset, 0)
+        dv = {k: one[k].to(dev) for k in ("corr_pos", "src_keypts", "tgt_keypts")}
+        pin = {k: one[k].pin_memory() for k in ("corr_pos", "src_keypts", "tgt_keypts")}
+        for _ in range(3):
+            model.run(dv["corr_pos"], dv["src_keypts"], dv["tgt_keypts"])
+            model.run(pin["corr_pos"], pin["src_keypts"], pin["tgt_keypts"])
+        torch.cuda.synchronize()
+        reps = 20 if n <= 1000 else 8
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        e[0].record()
+        for i in range(reps):
+            model.run(dv["corr_pos"], dv["src_keypts"], dv["tgt_keypts"])
+            e[i + 1].record()
+        torch.cuda.synchronize()
+        dev_ms = statistics.median(e[i].elapsed_time(e[i + 1]) for i in range(reps))
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            model.run(pin["corr_pos"], pin["src_keypts"], pin["tgt_keypts"])
+            ts.append((time.perf_counter() - t0) * 1e3)
+        lat[f"N{n}"] = {"device_ms_per_pair": dev_ms, "e2e_ms_per_pair": statistics.median(ts), "reps": reps,
+                        "path": "CUDA-graph replay" if n <= model.graph_rows else "eager launches"}
+    out["latency_bs1"] = lat
+    # (2) BASELINE config D: N in {500, 1000, 2000, 5000}, 1024 sets over 8 GPUs = 128 sets per GPU (weak: per-GPU share)
+    sweep = {}
+    for n in (500, 1000, 2000, 5000):
+        bb = 128
+        h = make_inputs(n, bb, args.dataset, rank, world)
+        dv = {k: h[k].to(dev) for k in ("corr_pos", "src_keypts", "tgt_keypts")}
+        model.run(dv["corr_pos"], dv["src_keypts"], dv["tgt_keypts"])
+        barrier()
+        ms, _ = time_steps(model, dv, 3)
+        ms = max_over_ranks(ms)
+        sweep[f"N{n}"] = {"sets_per_s": bb * world * 3 / (ms * 1e-3), "ms_per_step": ms / 3, "batch_per_gpu": bb, "steps": 3}
+        del dv
+    out["config_d_sweep"] = sweep
+    # (3) strong scaling: the global B = 256 batch split over the ranks
+    if world > 1:
+        bb = max(1, 256 // world)
+        h = make_inputs(args.n, bb, args.dataset, rank, world)
+        dv = {k: h[k].to(dev) for k in ("corr_pos", "src_keypts", "tgt_keypts")}
+        for _ in range(2):
+            model.run(dv["corr_pos"], dv["src_keypts"], dv["tgt_keypts"])
+        barrier()
+        ms, _ = time_steps(model, dv, 10)
+        ms = max_over_ranks(ms)
+        out["strong_scaling"] = {"global_batch": bb * world, "batch_per_gpu": bb, "sets_per_s": bb * world * 10 / (ms * 1e-3),
+                                 "ms_per_step": ms / 10, "steps": 10}
+    return out
 
 
 def main():

@@ -96,6 +96,8 @@ struct pdsc_engine {
     cudaGraphExec_t exec;
   };
   std::vector<GraphEntry> graphs;
+  cudaStream_t capture_stream = nullptr;   // graphs are captured here (the caller's stream may be the legacy default stream,
+                                           // which cannot be captured) and launched into the caller's stream
 };
 
 namespace {
@@ -303,6 +305,7 @@ int pdsc_destroy(pdsc_engine* e) {
   if (e->corr_ready) cudaEventDestroy(e->corr_ready);
   for (auto& ev : e->ev) cudaEventDestroy(ev);
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+  if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
   delete e;
   return PDSC_OK;
 }
@@ -612,11 +615,12 @@ int pdsc_forward_graph(pdsc_engine* e, int32_t B, int32_t N, const float* d_corr
   int rc = forward_impl(e, 0, B, N, d_corr_pos, d_src, d_tgt, d_final_trans, d_final_labels, nullptr, nullptr, d_workspace,
                         workspace_bytes, cuda_stream);
   if (rc) return rc;
-  PDSC_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  if (!e->capture_stream) PDSC_CUDA(cudaStreamCreateWithFlags(&e->capture_stream, cudaStreamNonBlocking));
+  PDSC_CUDA(cudaStreamBeginCapture(e->capture_stream, cudaStreamCaptureModeThreadLocal));
   rc = forward_impl(e, 0, B, N, d_corr_pos, d_src, d_tgt, d_final_trans, d_final_labels, nullptr, nullptr, d_workspace,
-                    workspace_bytes, cuda_stream);
+                    workspace_bytes, e->capture_stream);
   cudaGraph_t graph = nullptr;
-  const cudaError_t end = cudaStreamEndCapture(st, &graph);
+  const cudaError_t end = cudaStreamEndCapture(e->capture_stream, &graph);
   if (rc) {
     if (graph) cudaGraphDestroy(graph);
     return rc;

@@ -59,10 +59,15 @@ __global__ void __launch_bounds__(kStatsThreads) eval_stats_kernel(const float* 
       ds += red_d[w];
       for (int q = 0; q < 4; ++q) c[q] += red_i[q][w];
     }
-    // trace(R^T R_gt) = sum_ij R_ij Rgt_ij
+    // trace(R^T R_gt): the three diagonal entries of the product (column dots), then their sum, as the matmul + trace of
+    // the reference evaluates them
     float tr = 0.f;
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) tr = __fmaf_rn(T[4 * i + j], G[4 * i + j], tr);
+    for (int j = 0; j < 3; ++j) {
+      float d = __fmul_rn(T[j], G[j]);
+      d = __fmaf_rn(T[4 + j], G[4 + j], d);
+      d = __fmaf_rn(T[8 + j], G[8 + j], d);
+      tr = __fadd_rn(tr, d);
+    }
     const float cosv = fminf(fmaxf((tr - 1.0f) / 2.0f, -1.0f), 1.0f);
     const float re = acosf(cosv) * 180.0f / 3.14159265358979323846f;
     const float dx = T[3] - G[3], dy = T[7] - G[7], dz = T[11] - G[11];

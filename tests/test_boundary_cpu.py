@@ -113,6 +113,9 @@ def test_bench_reference_arm_contract():
                 "cpu_baseline", "e2e", "gpu_launches"):
         assert key in d, key
     assert d["value"] > 0 and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    # "reference": the unmodified module from baseline/_ref (installed by __graft_entry__.build() where /root/reference exists);
+    # "port": the oracle restatement, when that install is absent
+    assert d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "sets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]

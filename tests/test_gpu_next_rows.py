@@ -41,10 +41,13 @@ def test_eval_stats_vs_reference_fixtures():
         ref = z[f"c{i}_row"]
         assert row[0] == ref[0], i                                       # success flag: exact
         assert row[3] == ref[3] and row[5] == ref[5], i                  # counts: exact
-        # RE / TE / ratios / RMSE: fp32 on both sides; acos is ill-conditioned near 0 degrees (the reference's own value there
-        # is round-off of the trace), hence the wider absolute bar for RE below 0.1 degree
-        np.testing.assert_allclose(np.concatenate([row[1:3], row[4:5], row[6:]]), np.concatenate([ref[1:3], ref[4:5], ref[6:]]),
-                                   rtol=1e-4, atol=2e-2 if ref[1] < 0.1 else 1e-4)
+        # TE / ratios / RMSE: fp32 on both sides, 1e-4.  RE = acos((trace - 1) / 2) is ill-conditioned near 0 degrees: a
+        # summation-order difference of a few ulps of the trace (3 x 6e-8) moves it by that over sin(RE); below 0.1 degree the
+        # reference's own value is round-off
+        np.testing.assert_allclose(np.concatenate([row[2:3], row[4:5], row[6:]]), np.concatenate([ref[2:3], ref[4:5], ref[6:]]),
+                                   rtol=1e-4, atol=1e-4)
+        re_tol = 5e-2 if ref[1] < 0.1 else 1e-4 * ref[1] + np.degrees(2e-7 / max(np.sin(np.radians(ref[1])), 1e-3))
+        assert abs(row[1] - ref[1]) <= re_tol, (i, row[1], ref[1])
 
 
 def test_eval_stats_batched_equals_single():
@@ -125,7 +128,9 @@ def test_validation_forward_vs_reference(precision):
     out = m(data)                                   # no 'testing' key, eval mode
     assert out["M"].shape == (3, 256, 256)
     assert np.abs(out["final_labels"].cpu().numpy() - z["final_labels"]).max() < 5e-3      # confidence logits
-    assert np.abs(out["M"].cpu().numpy() - z["M"]).max() < 2e-4
+    # M = 1 - (1 - f.f) / sigma^2 amplifies feature differences by 1 / sigma^2 = 10.5: the exact-arithmetic encoder stays
+    # inside 2e-4, the tensor-core encoder (fp16 hi/lo operands, different summation order) inside 2e-3
+    assert np.abs(out["M"].cpu().numpy() - z["M"]).max() < (2e-4 if precision == "fp32" else 2e-3)
     assert float(torch.diagonal(out["M"], dim1=1, dim2=2).abs().max()) == 0.0
     assert np.abs(out["final_trans"].cpu().numpy() - z["final_trans"]).max() < 1e-4
     taps = m.run_eval(data["corr_pos"], data["src_keypts"], data["tgt_keypts"], taps=["seeds", "power_iters"])
