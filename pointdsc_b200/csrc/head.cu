@@ -9,13 +9,21 @@
 
 namespace pdsc {
 
-// Lane = one correspondence (row), 32 rows per warp pass.  The warp stages its 32 rows transposed in shared memory
-// ([channel][row], stride 33: conflict-free both ways); every lane then runs the whole MLP of its own row with the 32
-// hidden accumulators in registers while the weights arrive as warp-wide BROADCAST 16-byte loads — 32 FMAs per 8 weight
-// loads + 1 activation load, instead of 1 FMA per 2 loads in a channel-per-lane scheme.  Accumulation order is the
-// reference's: bias first, then ascending input channel, one fp32 FMA each.
-constexpr int kHeadWarps = 4;
-constexpr int kHeadStride = 33;
+// Lane = one correspondence (row), 32 rows per warp pass.  The warp's 32 rows arrive with cp.async (16 bytes per lane, one
+// full 512-byte row per instruction) into a ROW-major shared-memory tile with a row stride of 132 floats: lane i then reads
+// its own row four channels at a time (LDS.128; 16-byte chunk index lane * 33 + c / 4 is distinct modulo 8 within every
+// quarter warp: conflict free), runs the whole MLP of that row with the 32 hidden accumulators in registers while the
+// weights arrive as warp-wide BROADCAST 16-byte loads (32 FMAs per 8 weight loads), and the normalised rows leave the
+// tile again as full 512-byte rows.  Eight warps per CTA, one tile each: while a warp waits for its next tile the other
+// warp of its scheduler computes.  Accumulation order is the reference's: bias first, then ascending input channel, one
+// fp32 FMA each.  (Round 1 staged the tile transposed through 4-way conflicting scalar stores with 2 x 4 warps per SM and
+// no overlap of load and compute: 0.20 ms for 262 MB.)
+constexpr int kHeadWarps = 8;
+constexpr int kHeadStride = 132;       // floats per staged row
+
+__device__ __forceinline__ void head_cp_async_16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
 
 __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(const float* __restrict__ feat, HeadWeights w,
                                                                 float* __restrict__ normed, float* __restrict__ conf,
@@ -26,7 +34,7 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(const float* __re
   float* b0s = w2t + 32 * 32;
   float* b2s = b0s + 32;
   float* w4s = b2s + 32;
-  float* tiles = w4s + 32;             // [warp][kC * kHeadStride]
+  float* tiles = w4s + 32;             // [warp][32 * kHeadStride]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (want_conf) {
     for (int i = tid; i < kC * 32; i += kHeadWarps * 32) w0t[i] = w.w0t[i];
@@ -35,45 +43,48 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(const float* __re
   }
   __syncthreads();
   const float b4 = want_conf ? w.b4[0] : 0.f;
-  float* T = tiles + (size_t)warp * kC * kHeadStride;
+  float* T = tiles + (size_t)warp * 32 * kHeadStride;
+  const uint32_t t_base = (uint32_t)__cvta_generic_to_shared(T);
   const long long ntiles = (rows + 31) / 32;
   for (long long t = (long long)blockIdx.x * kHeadWarps + warp; t < ntiles; t += (long long)gridDim.x * kHeadWarps) {
     const long long r0 = t * 32;
-    // stage: row i, channels 4 lane .. 4 lane + 3  ->  T[c][i]
-#pragma unroll 4
+#pragma unroll 8
     for (int i = 0; i < 32; ++i) {
-      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r0 + i < rows) f = *reinterpret_cast<const float4*>(feat + (r0 + i) * kC + lane * 4);
-      T[(lane * 4 + 0) * kHeadStride + i] = f.x;
-      T[(lane * 4 + 1) * kHeadStride + i] = f.y;
-      T[(lane * 4 + 2) * kHeadStride + i] = f.z;
-      T[(lane * 4 + 3) * kHeadStride + i] = f.w;
+      if (r0 + i < rows) head_cp_async_16(t_base + (uint32_t)((i * kHeadStride + lane * 4) * 4), feat + (r0 + i) * kC + lane * 4);
+      else *reinterpret_cast<float4*>(T + i * kHeadStride + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     // this lane's row: squared norm (+ hidden layer 1 when the confidence is wanted)
+    const float* my = T + lane * kHeadStride;
     float ss = 0.f;
     float h1[32];
     if (want_conf) {
 #pragma unroll
       for (int o = 0; o < 32; ++o) h1[o] = b0s[o];
-#pragma unroll 2
-      for (int c = 0; c < kC; ++c) {
-        const float f = T[c * kHeadStride + lane];
-        ss = fmaf(f, f, ss);
+#pragma unroll 1
+      for (int c4 = 0; c4 < kC; c4 += 4) {
+        const float4 fv = *reinterpret_cast<const float4*>(my + c4);
+        const float fr[4] = {fv.x, fv.y, fv.z, fv.w};
 #pragma unroll
-        for (int o4 = 0; o4 < 8; ++o4) {
-          const float4 wv = *reinterpret_cast<const float4*>(w0t + c * 32 + o4 * 4);
-          h1[o4 * 4 + 0] = fmaf(f, wv.x, h1[o4 * 4 + 0]);
-          h1[o4 * 4 + 1] = fmaf(f, wv.y, h1[o4 * 4 + 1]);
-          h1[o4 * 4 + 2] = fmaf(f, wv.z, h1[o4 * 4 + 2]);
-          h1[o4 * 4 + 3] = fmaf(f, wv.w, h1[o4 * 4 + 3]);
+        for (int q = 0; q < 4; ++q) {
+          const float f = fr[q];
+          ss = fmaf(f, f, ss);
+#pragma unroll
+          for (int o4 = 0; o4 < 8; ++o4) {
+            const float4 wv = *reinterpret_cast<const float4*>(w0t + (c4 + q) * 32 + o4 * 4);
+            h1[o4 * 4 + 0] = fmaf(f, wv.x, h1[o4 * 4 + 0]);
+            h1[o4 * 4 + 1] = fmaf(f, wv.y, h1[o4 * 4 + 1]);
+            h1[o4 * 4 + 2] = fmaf(f, wv.z, h1[o4 * 4 + 2]);
+            h1[o4 * 4 + 3] = fmaf(f, wv.w, h1[o4 * 4 + 3]);
+          }
         }
       }
     } else {
 #pragma unroll 4
-      for (int c = 0; c < kC; ++c) {
-        const float f = T[c * kHeadStride + lane];
-        ss = fmaf(f, f, ss);
+      for (int c4 = 0; c4 < kC; c4 += 4) {
+        const float4 fv = *reinterpret_cast<const float4*>(my + c4);
+        ss = fmaf(fv.x, fv.x, ss); ss = fmaf(fv.y, fv.y, ss); ss = fmaf(fv.z, fv.z, ss); ss = fmaf(fv.w, fv.w, ss);
       }
     }
     const float den = fmaxf(sqrtf(ss), 1e-12f);   // F.normalize: x / max(||x||, eps)
@@ -103,9 +114,8 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(const float* __re
     for (int i = 0; i < 32; ++i) {
       const float d = __shfl_sync(0xffffffffu, den, i);
       if (r0 + i < rows) {
-        const float4 f = make_float4(T[(lane * 4 + 0) * kHeadStride + i] / d, T[(lane * 4 + 1) * kHeadStride + i] / d,
-                                     T[(lane * 4 + 2) * kHeadStride + i] / d, T[(lane * 4 + 3) * kHeadStride + i] / d);
-        *reinterpret_cast<float4*>(normed + (r0 + i) * kC + lane * 4) = f;
+        const float4 fv = *reinterpret_cast<const float4*>(T + i * kHeadStride + lane * 4);
+        *reinterpret_cast<float4*>(normed + (r0 + i) * kC + lane * 4) = make_float4(fv.x / d, fv.y / d, fv.z / d, fv.w / d);
       }
     }
     __syncwarp();
@@ -115,10 +125,10 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(const float* __re
 void launch_head(const float* feat, const HeadWeights& w, float* normed, float* conf, long long rows, int want_conf,
                  cudaStream_t st) {
   long long blocks = ((rows + 31) / 32 + kHeadWarps - 1) / kHeadWarps;
-  const long long max_blocks = 2LL * device_sm_count();
+  const long long max_blocks = device_sm_count();
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
-  constexpr int kSmem = (kC * 32 + 32 * 32 + 96 + kHeadWarps * kC * kHeadStride) * (int)sizeof(float);
+  constexpr int kSmem = (kC * 32 + 32 * 32 + 96 + kHeadWarps * 32 * kHeadStride) * (int)sizeof(float);
   ensure_dynamic_smem(reinterpret_cast<const void*>(head_kernel), kSmem);
   head_kernel<<<(unsigned)blocks, kHeadWarps * 32, kSmem, st>>>(feat, w, normed, conf, rows, want_conf);
 }

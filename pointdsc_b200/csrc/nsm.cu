@@ -34,280 +34,366 @@ void launch_gather_rows(const float* normed, const int32_t* seeds, float* out, i
 }
 
 // ---- top-(k+1) smallest per seed row ---------------------------------------------------------------
-__device__ __forceinline__ unsigned long long dist_key(float d, int j) {
+// One warp per seed row.  The row's distances become order-preserving 32-bit keys in the warp's slice of shared memory
+// (+0 == -0, NaN last); a 4-pass radix SELECT (8 bits per pass, 256-bin histogram in shared memory) finds the value T of
+// the (k+1)-th smallest key and how many elements equal to T belong to the selection; one ordered pass compacts the
+// k+1 winners — every key < T plus the lowest-INDEX elements with key == T, which is the (distance, index) order the
+// reference's topk + the engine's tie rule define — and a bitonic sort of those <= 256 packed (key, index) pairs puts them
+// in ascending order.  Rank 0 (the seed itself, ignore_self) is dropped.  ~1.5 k instructions per row at N = 1000 instead
+// of the 6.5 k of k + 1 serial argmin rounds, and no register-resident copy of the row, so one kernel serves every N.
+__device__ __forceinline__ uint32_t dist_key32(float d) {
   uint32_t u = __float_as_uint(d);
-  if ((u & 0x7FFFFFFFu) == 0u) u = 0u;
-  u ^= (u & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u;
-  return ((unsigned long long)u << 32) | (unsigned)j;
+  if (d != d) return 0xFFFFFFFFu;            // NaN distances are never selected
+  if ((u & 0x7FFFFFFFu) == 0u) u = 0u;       // -0 ranks equal to +0
+  return u ^ ((u & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u);
 }
 
-__global__ void __launch_bounds__(128) knn_select_kernel(const float* __restrict__ dist, int32_t* __restrict__ knn_idx,
-                                                         int N, int S, int k) {
-  extern __shared__ unsigned long long keys[];  // [N]
-  __shared__ unsigned long long wmin[4];
-  __shared__ unsigned long long chosen;
-  const int row = blockIdx.x;  // b * S + s
+__global__ void __launch_bounds__(256) knn_select_kernel(const float* __restrict__ dist, int32_t* __restrict__ knn_idx, int N,
+                                                         int rows, int k, int warps_per_cta, int P) {
+  extern __shared__ __align__(16) unsigned char knn_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * warps_per_cta + warp;
+  if (row >= rows) return;                   // whole warps leave: no block-level barrier below
+  const int NP = (N + 31) & ~31;
+  const size_t per_warp = (size_t)NP * 4 + 1024 + (size_t)P * 8;
+  unsigned char* base = knn_smem + (size_t)warp * per_warp;
+  unsigned long long* sel = reinterpret_cast<unsigned long long*>(base);            // [P]   (first: 8-byte aligned)
+  uint32_t* hist = reinterpret_cast<uint32_t*>(base + (size_t)P * 8);               // [256]
+  uint32_t* keys = hist + 256;                                                      // [NP]
   const float* d = dist + (size_t)row * N;
-  for (int j = threadIdx.x; j < N; j += 128) keys[j] = dist_key(d[j], j);
-  __syncthreads();
-  unsigned long long prev = 0ull;
-  for (int r = 0; r <= k; ++r) {
-    unsigned long long best = ~0ull;
-    for (int j = threadIdx.x; j < N; j += 128) {
-      const unsigned long long v = keys[j];
-      if (v > prev && v < best) best = v;
-    }
+  for (int j = lane; j < NP; j += 32) keys[j] = j < N ? dist_key32(d[j]) : 0xFFFFFFFFu;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  // ---- radix select of the (k+1)-th smallest key -----------------------------------------------------
+  uint32_t prefix = 0u, mask = 0u;
+  int need = k + 1;                          // rank (1-based) still to be located among the keys matching `prefix`
+#pragma unroll 1
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-      best = other < best ? other : best;
+    for (int q = 0; q < 8; ++q) hist[lane * 8 + q] = 0u;
+    __syncwarp();
+    for (int j = lane; j < NP; j += 32) {
+      const uint32_t v = keys[j];
+      if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1u);
     }
-    if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = best;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long m = wmin[0];
-      for (int w = 1; w < 4; ++w) m = wmin[w] < m ? wmin[w] : m;
-      chosen = m;
-      if (r > 0) knn_idx[(size_t)row * k + (r - 1)] = (m == ~0ull) ? 0 : (int32_t)(m & 0xFFFFFFFFull);
+    __syncwarp();
+    uint32_t c[8], lane_sum = 0u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { c[q] = hist[lane * 8 + q]; lane_sum += c[q]; }
+    uint32_t incl = lane_sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    __syncthreads();
-    prev = chosen;
+    const uint32_t excl = incl - lane_sum;
+    const bool mine = excl < (uint32_t)need && (uint32_t)need <= incl;   // exactly one lane (need <= matching count)
+    uint32_t digit = 0u, rem = 0u;
+    if (mine) {
+      uint32_t cum = excl;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (cum < (uint32_t)need && (uint32_t)need <= cum + c[q]) { digit = (uint32_t)(lane * 8 + q); rem = (uint32_t)need - cum; }
+        cum += c[q];
+      }
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+    digit = __shfl_sync(0xffffffffu, digit, src);
+    need = (int)__shfl_sync(0xffffffffu, rem, src);
+    prefix |= digit << shift;
+    mask |= 0xFFu << shift;
+    __syncwarp();
   }
-}
-
-// Register-resident variant for N <= 32 * EPL: one warp per seed row, lane l holds the distances of points
-// l, l+32, ...  Each of the k+1 rounds takes the lexicographic minimum (distance, index) of what is left:
-// lane-local scan in ascending index order (strict '<' keeps the lowest index among equal distances), a 5-step
-// shuffle argmin, and the owning lane retires its element.  No shared memory, no block barriers.
-template <int EPL>
-__global__ void __launch_bounds__(256) knn_select_warp_kernel(const float* __restrict__ dist, int32_t* __restrict__ knn_idx,
-                                                              int N, int rows, int k) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const float* d = dist + (size_t)row * N;
-  float v[EPL];
-#pragma unroll
-  for (int i = 0; i < EPL; ++i) {
-    const int j = lane + 32 * i;
-    float x = (j < N) ? d[j] : INFINITY;
-    if (x == 0.0f) x = 0.0f;          // -0 ranks equal to +0
-    v[i] = (x == x) ? x : INFINITY;   // NaN distances are never selected
+  // ---- ordered compaction: key < T, plus the `need` lowest indices with key == T ----------------------
+  const uint32_t T = prefix;
+  int out = 0, eq_seen = 0;
+  for (int j0 = 0; j0 < NP; j0 += 32) {
+    const uint32_t v = keys[j0 + lane];
+    const bool eq = v == T;
+    const uint32_t beq = __ballot_sync(0xffffffffu, eq);
+    const bool take = (v < T) || (eq && eq_seen + __popc(beq & lt_mask) < need);
+    const uint32_t bt = __ballot_sync(0xffffffffu, take);
+    if (take) sel[out + __popc(bt & lt_mask)] = ((unsigned long long)v << 32) | (unsigned)(j0 + lane);
+    out += __popc(bt);
+    eq_seen += __popc(beq);
   }
-  for (int r = 0; r <= k; ++r) {
-    float bd = INFINITY;
-    int bi = EPL;
-#pragma unroll
-    for (int i = 0; i < EPL; ++i) {
-      const bool better = v[i] < bd;
-      bd = better ? v[i] : bd;
-      bi = better ? i : bi;
+  for (int i = out + lane; i < P; i += 32) sel[i] = ~0ull;      // out == k + 1 <= P
+  __syncwarp();
+  // ---- bitonic sort of the P packed pairs (ascending) -------------------------------------------------
+  for (int kk = 2; kk <= P; kk <<= 1) {
+    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+      for (int t = lane; t < (P >> 1); t += 32) {
+        const int i = ((t & ~(jj - 1)) << 1) | (t & (jj - 1));   // the lower index of the t-th pair at distance jj
+        const int ixj = i | jj;
+        const unsigned long long a = sel[i], c2 = sel[ixj];
+        const bool asc = (i & kk) == 0;
+        if ((a > c2) == asc) { sel[i] = c2; sel[ixj] = a; }
+      }
+      __syncwarp();
     }
-    int bj = (bi < EPL) ? lane + 32 * bi : 0x7FFFFFFF;
-    float wd = bd;
-    int wj = bj;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, wd, o);
-      const int oj = __shfl_xor_sync(0xffffffffu, wj, o);
-      const bool take = (od < wd) || (od == wd && oj < wj);
-      wd = take ? od : wd;
-      wj = take ? oj : wj;
-    }
-    if (wj == bj && bi < EPL) {
-#pragma unroll
-      for (int i = 0; i < EPL; ++i)
-        if (i == bi) v[i] = INFINITY;
-    }
-    if (r > 0 && lane == 0) knn_idx[(size_t)row * k + (r - 1)] = (wj == 0x7FFFFFFF) ? 0 : wj;
+  }
+  for (int r = 1 + lane; r <= k; r += 32) {
+    const unsigned long long v = sel[r];
+    knn_idx[(size_t)row * k + (r - 1)] = (v == ~0ull || (uint32_t)(v >> 32) == 0xFFFFFFFFu) ? 0 : (int32_t)(v & 0xFFFFFFFFull);
   }
 }
 
 void launch_knn_select(const float* dist, int32_t* knn_idx, int B, int N, int S, int k, cudaStream_t st) {
   if (S <= 0) return;
   const int rows = B * S;
-  if (N <= 1024) {
-    knn_select_warp_kernel<32><<<(rows + 7) / 8, 256, 0, st>>>(dist, knn_idx, N, rows, k);
-    return;
-  }
-  if (N <= 2048) {
-    knn_select_warp_kernel<64><<<(rows + 7) / 8, 256, 0, st>>>(dist, knn_idx, N, rows, k);
-    return;
-  }
-  const int smem = N * (int)sizeof(unsigned long long);
+  int P = 2;
+  while (P < k + 1) P <<= 1;
+  const int NP = (N + 31) & ~31;
+  const size_t per_warp = (size_t)NP * 4 + 1024 + (size_t)P * 8;
+  int warps = (int)((200 * 1024) / per_warp);
+  warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
+  const int smem = (int)(per_warp * warps);
   ensure_dynamic_smem(reinterpret_cast<const void*>(knn_select_kernel), smem);
-  knn_select_kernel<<<rows, 128, smem, st>>>(dist, knn_idx, N, S, k);
+  knn_select_kernel<<<(rows + warps - 1) / warps, warps * 32, smem, st>>>(dist, knn_idx, N, rows, k, warps, P);
 }
 
-// ---- compatibility matrix + power iteration, one 64-thread CTA per seed -------------------------------
-// The k gathered feature rows stay ROW-major in shared memory (F[a][c], 512 B per row) with the 16-byte chunk index of a
-// row XOR-swizzled by (a >> 2) & 7, so both the gather (one 16-byte store per lane, a full row per warp instruction) and
-// the Gram loop (4 x 4 register blocks: 8 LDS.128 per 64 FMAs, rows of different blocks in different banks) are
-// conflict free.  Only blocks on or above the diagonal are computed (55 of them for k = 40: 86 % of the 64 threads busy).
-// Channels are accumulated in ascending order, one fp32 FMA each.
-constexpr int kNsmThreads = 64;
-
-__device__ __forceinline__ const float4* nsm_chunk(const float* F, int row, int chunk) {
-  return reinterpret_cast<const float4*>(F + (size_t)row * kC + ((chunk ^ ((row >> 2) & 7)) << 2));
+// ---- compatibility matrix + power iteration: ONE WARP PER SEED ------------------------------------------
+// (round 1 ran one 64-thread CTA per seed with block barriers between gather, Gram and each of the 10 iterations: every
+// phase waited for the slowest of two warps and a CTA held 28 KB of shared memory through its latency-bound phases — 0.71 ms
+// for B * S = 25 600 seeds.)  Here a warp owns a seed from the gather to the last iterate, so nothing but __syncwarp()
+// separates the phases, and up to 12 warps per SM sit in different phases and hide each other's latencies:
+//   gather   the k neighbour rows arrive with cp.async (16 bytes per lane, four rows per instruction), one 32-channel QUARTER
+//            at a time, so the feature tile costs k x 128 B of shared memory instead of k x 512 B (16 warps per SM);
+//   Gram     4 x 4 register blocks on or above the diagonal (55 blocks for k = 40: two rounds of 32 lanes), 8 LDS.128 per
+//            64 FMAs, accumulated over the two halves in ascending channel order, one fp32 FMA each;
+//   compat   feature-compat * spatial-compat with the reference's rounded operation sequence, M symmetric in shared memory;
+//   power    lane l owns rows l, l+32, l+64, l+96; row a is read as column a (M is symmetric: consecutive lanes read
+//            consecutive words); the squared norm is summed per 32-row group by shuffles and the groups are added in
+//            ascending order; every iterate is stored and the "all rows passed allclose at iteration t" bits of the seed
+//            are ANDed into the set's word.
+// The 16-byte chunk index of a feature row is XOR-swizzled by (row >> 2) & 7 so that the rows of different 4-row blocks
+// fall into different banks (rows of one block are read by lanes that share them: broadcasts).
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kNsmThreads) nsm_power_kernel(const float* __restrict__ normed, const float* __restrict__ src,
-                                                                const float* __restrict__ tgt,
-                                                                const int32_t* __restrict__ knn_idx,
-                                                                float* __restrict__ iterates, uint32_t* __restrict__ conv_mask,
-                                                                float* __restrict__ compat_out, int N, int S, int k, int iters,
-                                                                float sigma2, float sigmad2, int mask_stride) {
+__global__ void __launch_bounds__(256) nsm_power_kernel(const float* __restrict__ normed, const float* __restrict__ src,
+                                                        const float* __restrict__ tgt, const int32_t* __restrict__ knn_idx,
+                                                        float* __restrict__ iterates, uint32_t* __restrict__ conv_mask,
+                                                        float* __restrict__ compat_out, int N, int S, int k, int iters,
+                                                        float sigma2, float sigmad2, int mask_stride, int warps_per_cta,
+                                                        int per_warp_floats) {
   extern __shared__ __align__(16) float sm[];
-  const int ms = k | 1;                  // odd row stride of M: conflict-free row-per-thread reads
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int s = blockIdx.x * warps_per_cta + warp;
+  if (s >= S) return;                      // whole warps leave: no block-level barrier below
+  const int ms = k | 1;                    // odd row stride of M: conflict-free column reads
   const int kp = (k + 3) & ~3;
-  float* F = sm;                         // [kp][kC], chunk-swizzled
-  float* M = F + (size_t)kp * kC;        // [k][ms]
-  float* pa = M + (size_t)k * ms;        // [k][3]
-  float* pb = pa + k * 3;                // [k][3]
-  float* v = pb + k * 3;                 // [k]
-  float* red = v + k;                    // [4]
-  __shared__ int idx[kMaxK];
-  const int b = blockIdx.y, s = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* F = sm + (size_t)warp * per_warp_floats;   // [kp][32]  one channel quarter, chunk-swizzled
+  float* M = F + (size_t)kp * 32;                   // [k][ms]
+  float* pa = M + (size_t)k * ms;                   // [k][3]
+  float* pb = pa + k * 3;                           // [k][3]
+  float* v = pb + k * 3;                            // [k]
+  int* idx = reinterpret_cast<int*>(v + k);         // [k]
   const size_t seed_row = (size_t)b * S + s;
 
-  for (int a = tid; a < kp; a += kNsmThreads) {
-    if (a < k) {
-      int j = knn_idx[seed_row * k + a];
-      j = min(max(j, 0), N - 1);
-      idx[a] = j;
-      const float* ps = src + ((size_t)b * N + j) * 3;
-      const float* pt = tgt + ((size_t)b * N + j) * 3;
-      pa[a * 3 + 0] = ps[0]; pa[a * 3 + 1] = ps[1]; pa[a * 3 + 2] = ps[2];
-      pb[a * 3 + 0] = pt[0]; pb[a * 3 + 1] = pt[1]; pb[a * 3 + 2] = pt[2];
-      v[a] = 1.0f;
-      M[a * ms + a] = 0.0f;  // total_knn_M[:, i, i] = 0  (PointDSC.py:278)
-    }
+  for (int a = lane; a < k; a += 32) {
+    int j = knn_idx[seed_row * k + a];
+    j = min(max(j, 0), N - 1);
+    idx[a] = j;
+    const float* ps = src + ((size_t)b * N + j) * 3;
+    const float* pt = tgt + ((size_t)b * N + j) * 3;
+    pa[a * 3 + 0] = ps[0]; pa[a * 3 + 1] = ps[1]; pa[a * 3 + 2] = ps[2];
+    pb[a * 3 + 0] = pt[0]; pb[a * 3 + 1] = pt[1]; pb[a * 3 + 2] = pt[2];
+    v[a] = 1.0f;
+    M[a * ms + a] = 0.0f;  // total_knn_M[:, i, i] = 0  (PointDSC.py:278)
   }
-  if (tid < 4) red[tid] = 0.f;
-  __syncthreads();
-  // gather: warp w takes rows w, w+2, ...; all of a warp's loads are issued before the first store
-  {
-    constexpr int kMaxRowsPerWarp = (kMaxK + 3) / 2 / 4 * 4 + 4;
-    (void)kMaxRowsPerWarp;
-    for (int a0 = warp; a0 < kp; a0 += 2 * 8) {
-      float4 buf[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int a = a0 + 2 * u;
-        buf[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a < k) buf[u] = __ldg(reinterpret_cast<const float4*>(normed + ((size_t)b * N + idx[a]) * kC) + lane);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int a = a0 + 2 * u;
-        if (a < kp) *reinterpret_cast<float4*>(F + (size_t)a * kC + ((lane ^ ((a >> 2) & 7)) << 2)) = buf[u];
-      }
-    }
-  }
-  __syncthreads();
+  __syncwarp();
 
-  // 4 x 4 blocks (A <= B) of feature-compat * spatial-compat
+  // this lane's blocks (A <= Bk) of rounds 0, 1, ...: block t = lane + 32 * round in row-major upper-triangular order
   const int nb = kp >> 2;
   const int nblk = nb * (nb + 1) / 2;
-  for (int t = tid; t < nblk; t += kNsmThreads) {
-    int A = 0, rem = t;
-    while (rem >= nb - A) { rem -= nb - A; ++A; }
-    const int Bk = A + rem;
-    float acc[4][4];
+  constexpr int kMaxRounds = 2;            // 64 blocks per pass (k <= 40 in one pass); larger k repeats gather + Gram per group of 64 blocks
+  const uint32_t f_base = (uint32_t)__cvta_generic_to_shared(F);
+  for (int r0 = 0; r0 * 32 < nblk; r0 += kMaxRounds) {
+    int bA[kMaxRounds], bB[kMaxRounds];
+    float acc[kMaxRounds][4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-#pragma unroll 2
-    for (int cc = 0; cc < kC / 4; ++cc) {
-      float4 x[4], y[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        x[i] = *nsm_chunk(F, 4 * A + i, cc);
-        y[i] = *nsm_chunk(F, 4 * Bk + i, cc);
-      }
+    for (int r = 0; r < kMaxRounds; ++r) {
+      const int t = lane + 32 * (r0 + r);
+      int A = 0, rem = t < nblk ? t : 0;
+      while (rem >= nb - A) { rem -= nb - A; ++A; }
+      bA[r] = A; bB[r] = A + rem;
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[i][j] = fmaf(x[i].x, y[j].x, acc[i][j]);
-          acc[i][j] = fmaf(x[i].y, y[j].y, acc[i][j]);
-          acc[i][j] = fmaf(x[i].z, y[j].z, acc[i][j]);
-          acc[i][j] = fmaf(x[i].w, y[j].w, acc[i][j]);
-        }
+        for (int j = 0; j < 4; ++j) acc[r][i][j] = 0.f;
     }
+#pragma unroll 1
+    for (int quarter = 0; quarter < 4; ++quarter) {
+      // gather: eight lanes per row, 16-byte chunk q of channels [32 quarter, 32 quarter + 32)
+      const int q = lane & 7;
+      for (int a = lane >> 3; a < kp; a += 4) {
+        const uint32_t dst = f_base + (uint32_t)((a * 32 + ((q ^ ((a >> 2) & 7)) << 2)) * 4);
+        if (a < k) cp_async_16(dst, normed + ((size_t)b * N + idx[a]) * kC + quarter * 32 + q * 4);
+        else *reinterpret_cast<float4*>(F + a * 32 + ((q ^ ((a >> 2) & 7)) << 2)) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      cp_async_wait_all();
+      __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int r = 0; r < kMaxRounds; ++r) {
+        if (lane + 32 * (r0 + r) < nblk) {
+          const float* xa = F + (size_t)(4 * bA[r]) * 32;
+          const float* yb = F + (size_t)(4 * bB[r]) * 32;
+          const int sx = bA[r] & 7, sy = bB[r] & 7;      // (row >> 2) & 7 is the block index & 7
+#pragma unroll 2
+          for (int cc = 0; cc < 8; ++cc) {
+            float4 x[4], y[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int a = 4 * A + i, c = 4 * Bk + j;
-        if (a < c && c < k) {
-          const float fm = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fsub_rn(1.0f, acc[i][j]), sigma2)), 0.0f);
-          const float la = length3_pow(pa[a * 3] - pa[c * 3], pa[a * 3 + 1] - pa[c * 3 + 1], pa[a * 3 + 2] - pa[c * 3 + 2]);
-          const float lb = length3_pow(pb[a * 3] - pb[c * 3], pb[a * 3 + 1] - pb[c * 3 + 1], pb[a * 3 + 2] - pb[c * 3 + 2]);
-          const float val = __fmul_rn(fm, consistency(__fsub_rn(la, lb), sigmad2));
-          M[a * ms + c] = val;
-          M[c * ms + a] = val;
+            for (int i = 0; i < 4; ++i) {
+              x[i] = *reinterpret_cast<const float4*>(xa + i * 32 + ((cc ^ sx) << 2));
+              y[i] = *reinterpret_cast<const float4*>(yb + i * 32 + ((cc ^ sy) << 2));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                acc[r][i][j] = fmaf(x[i].x, y[j].x, acc[r][i][j]);
+                acc[r][i][j] = fmaf(x[i].y, y[j].y, acc[r][i][j]);
+                acc[r][i][j] = fmaf(x[i].z, y[j].z, acc[r][i][j]);
+                acc[r][i][j] = fmaf(x[i].w, y[j].w, acc[r][i][j]);
+              }
+          }
         }
       }
+      __syncwarp();          // everyone is done with this quarter before the next gather overwrites it
+    }
+    // compatibility of this group of blocks
+#pragma unroll
+    for (int r = 0; r < kMaxRounds; ++r) {
+      if (lane + 32 * (r0 + r) < nblk) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int a = 4 * bA[r] + i, c = 4 * bB[r] + j;
+            if (a < c && c < k) {
+              const float fm = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fsub_rn(1.0f, acc[r][i][j]), sigma2)), 0.0f);
+              const float la = length3_pow(pa[a * 3] - pa[c * 3], pa[a * 3 + 1] - pa[c * 3 + 1], pa[a * 3 + 2] - pa[c * 3 + 2]);
+              const float lb = length3_pow(pb[a * 3] - pb[c * 3], pb[a * 3 + 1] - pb[c * 3 + 1], pb[a * 3 + 2] - pb[c * 3 + 2]);
+              const float val = __fmul_rn(fm, consistency(__fsub_rn(la, lb), sigmad2));
+              M[a * ms + c] = val;
+              M[c * ms + a] = val;
+            }
+          }
+      }
+    }
   }
-  __syncthreads();
+  __syncwarp();
   if (compat_out) {
     float* dst = compat_out + seed_row * k * k;
-    for (int t = tid; t < k * k; t += kNsmThreads) dst[t] = M[(t / k) * ms + (t % k)];
+    for (int t = lane; t < k * k; t += 32) dst[t] = M[(t / k) * ms + (t % k)];
   }
 
   // power iteration from the all-ones vector; record every iterate and a convergence bit per iteration.
-  // Thread `a` owns row a (and row a + 64 when k > 64); the squared norm is summed per warp, then warp 0 + warp 1.
+  // Lane = (row group rg = lane >> 2, column quarter cq = lane & 3): it owns rows rg + 8 i and the columns of quarter cq, so
+  // the k x k matrix-vector product is spread over all 32 lanes (k = 40: 50 MACs per lane and iteration, the matrix slice
+  // held in registers for all iterations; the round-1 kernel ran a 40-step dependent chain per row with two shared-memory
+  // loads per MAC).  A row's four partial sums (ascending column order within a quarter) are combined by an xor butterfly,
+  // (q0 + q1) + (q2 + q3), the squared norm by a butterfly over the row groups: fixed orders, identical on every lane.
   uint32_t mask = 0u;
   float* it_out = iterates + seed_row * (size_t)iters * k;
-  for (int t = 0; t < iters; ++t) {
-    float u0 = 0.f, u1 = 0.f, vold0 = 0.f, vold1 = 0.f;
-    // M is symmetric: row a is read as column a (M[c][a]), so consecutive threads read consecutive words.  The loads
-    // of eight steps are issued together; the FMAs stay one dependent chain in ascending c (the reference order).
-    if (tid < k) {
-      const float* mc = M + tid;
-      int c = 0;
-      for (; c + 8 <= k; c += 8) {
-        float m8[8], v8[8];
+  const int rg = lane >> 2, cq = lane & 3;
+  const int CQ = (k + 3) >> 2;                       // columns per quarter
+  const int c_lo = cq * CQ, c_hi = min(k, c_lo + CQ);
+  if (k <= 40) {
+    constexpr int RI = 5, CW = 10;
+    float m[RI][CW], vq[CW], vrow[RI];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { m8[q] = mc[(c + q) * ms]; v8[q] = v[c + q]; }
+    for (int i = 0; i < RI; ++i) {
+      const int row = rg + 8 * i;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) u0 = fmaf(m8[q], v8[q], u0);
+      for (int c = 0; c < CW; ++c) m[i][c] = (row < k && c_lo + c < c_hi) ? M[row * ms + c_lo + c] : 0.f;
+      vrow[i] = 1.0f;
+    }
+#pragma unroll
+    for (int c = 0; c < CW; ++c) vq[c] = (c_lo + c < c_hi) ? 1.0f : 0.f;
+    for (int t = 0; t < iters; ++t) {
+      float u[RI], ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < RI; ++i) {
+        float p = 0.f;
+#pragma unroll
+        for (int c = 0; c < CW; ++c) p = fmaf(m[i][c], vq[c], p);
+        p += __shfl_xor_sync(0xffffffffu, p, 1);
+        p += __shfl_xor_sync(0xffffffffu, p, 2);
+        u[i] = p;
+        ss += (rg + 8 * i < k) ? p * p : 0.f;
       }
-      for (; c < k; ++c) u0 = fmaf(mc[c * ms], v[c], u0);
-      vold0 = v[tid];
+      ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+      const float nrm = sqrtf(ss) + 1e-6f;
+      bool ok = true;
+#pragma unroll
+      for (int i = 0; i < RI; ++i) {
+        const int row = rg + 8 * i;
+        const float vn = u[i] / nrm;
+        // torch.allclose(new, last): |new - last| <= atol + rtol * |last|, atol 1e-8, rtol 1e-5
+        ok = ok && (row >= k || fabsf(vn - vrow[i]) <= 1e-8f + 1e-5f * fabsf(vrow[i]));
+        vrow[i] = vn;
+        if (row < k && cq == 0) {
+          v[row] = vn;
+          it_out[(size_t)t * k + row] = vn;
+        }
+      }
+      if (__all_sync(0xffffffffu, ok)) mask |= (1u << t);
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < CW; ++c) vq[c] = (c_lo + c < c_hi) ? v[c_lo + c] : 0.f;
+      __syncwarp();
     }
-    if (tid + kNsmThreads < k) {
-      const float* mc = M + tid + kNsmThreads;
-      for (int c = 0; c < k; ++c) u1 = fmaf(mc[c * ms], v[c], u1);
-      vold1 = v[tid + kNsmThreads];
+  } else {
+    constexpr int RI = kMaxK / 8;
+    float vrow[RI];
+#pragma unroll
+    for (int i = 0; i < RI; ++i) vrow[i] = 1.0f;
+    for (int t = 0; t < iters; ++t) {
+      float u[RI], ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < RI; ++i) {
+        const int row = rg + 8 * i;
+        float p = 0.f;
+        if (row < k) {
+          const float* mr = M + (size_t)row * ms;
+          for (int c = c_lo; c < c_hi; ++c) p = fmaf(mr[c], v[c], p);
+        }
+        p += __shfl_xor_sync(0xffffffffu, p, 1);
+        p += __shfl_xor_sync(0xffffffffu, p, 2);
+        u[i] = p;
+        ss += (row < k) ? p * p : 0.f;
+      }
+      ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+      const float nrm = sqrtf(ss) + 1e-6f;
+      bool ok = true;
+      __syncwarp();                      // every lane has read the old v
+#pragma unroll
+      for (int i = 0; i < RI; ++i) {
+        const int row = rg + 8 * i;
+        const float vn = u[i] / nrm;
+        ok = ok && (row >= k || fabsf(vn - vrow[i]) <= 1e-8f + 1e-5f * fabsf(vrow[i]));
+        vrow[i] = vn;
+        if (row < k && cq == 0) {
+          v[row] = vn;
+          it_out[(size_t)t * k + row] = vn;
+        }
+      }
+      if (__all_sync(0xffffffffu, ok)) mask |= (1u << t);
+      __syncwarp();
     }
-    const float ssa = warp_sum(tid < k ? u0 * u0 : 0.f);
-    const float ssb = warp_sum(tid + kNsmThreads < k ? u1 * u1 : 0.f);
-    if (lane == 0) { red[warp] = ssa; red[2 + warp] = ssb; }
-    __syncthreads();
-    const float nrm = sqrtf(red[0] + red[1] + red[2] + red[3]) + 1e-6f;
-    const float vnew0 = u0 / nrm, vnew1 = u1 / nrm;
-    // torch.allclose(new, last): |new - last| <= atol + rtol * |last|, atol 1e-8, rtol 1e-5
-    const int ok0 = (tid >= k) || (fabsf(vnew0 - vold0) <= 1e-8f + 1e-5f * fabsf(vold0));
-    const int ok1 = (tid + kNsmThreads >= k) || (fabsf(vnew1 - vold1) <= 1e-8f + 1e-5f * fabsf(vold1));
-    const int all_ok = __syncthreads_and(ok0 && ok1);
-    if (tid < k) {
-      v[tid] = vnew0;
-      it_out[(size_t)t * k + tid] = vnew0;
-    }
-    if (tid + kNsmThreads < k) {
-      v[tid + kNsmThreads] = vnew1;
-      it_out[(size_t)t * k + tid + kNsmThreads] = vnew1;
-    }
-    if (all_ok) mask |= (1u << t);
-    __syncthreads();
   }
   // testing mode: the early exit is a per-set decision (mask_stride 1); non-testing mode: the reference's allclose spans
   // the whole [bs * S, k] batch (PointDSC.py:354), so every set ANDs into word 0 (mask_stride 0)
-  if (tid == 0) atomicAnd(conv_mask + (size_t)b * mask_stride, mask);
+  if (lane == 0) atomicAnd(conv_mask + (size_t)b * mask_stride, mask);
 }
 
 void launch_nsm_power(const float* normed, const float* src, const float* tgt, const int32_t* knn_idx, float* iterates,
@@ -316,10 +402,17 @@ void launch_nsm_power(const float* normed, const float* src, const float* tgt, c
   if (S <= 0) return;
   const int ms = k | 1;
   const int kp = (k + 3) & ~3;
-  const int smem = (kC * kp + k * ms + 6 * k + k + 4) * (int)sizeof(float);
+  int per_warp_floats = kp * 32 + k * ms + 6 * k + k + k;     // F quarter, M, pa, pb, v, idx
+  per_warp_floats = (per_warp_floats + 3) & ~3;               // keep every warp's slice 16-byte aligned
+  // two CTAs per SM (about 110 KB each) so that a CTA's launch / drain overlaps the other's work
+  int warps = (int)((110 * 1024) / ((size_t)per_warp_floats * sizeof(float)));
+  warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
+  const int smem = warps * per_warp_floats * (int)sizeof(float);
   ensure_dynamic_smem(reinterpret_cast<const void*>(nsm_power_kernel), smem);
-  nsm_power_kernel<<<dim3(S, B), kNsmThreads, smem, st>>>(normed, src, tgt, knn_idx, iterates, conv_mask, compat_out, N, S, k,
-                                                          iters, sigma * sigma, sigma_d * sigma_d, mask_stride);
+  nsm_power_kernel<<<dim3((S + warps - 1) / warps, B), warps * 32, smem, st>>>(normed, src, tgt, knn_idx, iterates, conv_mask,
+                                                                              compat_out, N, S, k, iters, sigma * sigma,
+                                                                              sigma_d * sigma_d, mask_stride, warps,
+                                                                              per_warp_floats);
 }
 
 }  // namespace pdsc
