@@ -184,6 +184,17 @@ int pdsc_match(pdsc_engine* e, int32_t Ns, int32_t Nt, int32_t D, const void* d_
                int32_t* d_corr, int32_t* d_count, float* d_corr_pos, float* d_out_src, float* d_out_tgt, void* d_scratch,
                size_t scratch_bytes, void* cuda_stream);
 
+/* f4: leading eigenvector of N x N compatibility matrices by power iteration, replacing cal_leading_eigenvector(M, 'power')
+ * (models/PointDSC.py:338-358) in its N x N uses: the learned feature-similarity matrix of the non-testing forward (:170) and
+ * the classical spectral-matching baseline (baseline_scripts/baseline_3DMatch.py:40-44, ten fixed iterations = early_exit 0).
+ * d_M [B,N,N] row-major; start vector all ones; v <- M v / (||M v|| + 1e-6); with early_exit the iteration of a set stops
+ * when allclose(v, v_prev, rtol 1e-5, atol 1e-8) holds (per set, decided on the device).  d_eigenvector [B,N],
+ * d_iterations_run [B]; d_scratch holds pdsc_leading_eigenvector_scratch_bytes(B, N) bytes, 16-byte aligned. */
+size_t pdsc_leading_eigenvector_scratch_bytes(int32_t B, int32_t N);
+int pdsc_leading_eigenvector(pdsc_engine* e, int32_t B, int32_t N, const float* d_M, int32_t num_iterations, int32_t early_exit,
+                             float* d_eigenvector, int32_t* d_iterations_run, void* d_scratch, size_t scratch_bytes,
+                             void* cuda_stream);
+
 /* ---- live profiling with CUDA events on the caller's stream ------------------------------------------
  * When enabled, pdsc_forward() records an event pair around each stage below (and around EVERY launch of
  * the dominant kernel, the per-layer attention).  pdsc_profile_read() waits for the last forward's events

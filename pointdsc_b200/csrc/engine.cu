@@ -660,6 +660,28 @@ int pdsc_eval_stats(pdsc_engine* e, int32_t B, int32_t N, const float* d_pred_tr
   return PDSC_OK;
 }
 
+size_t pdsc_leading_eigenvector_scratch_bytes(int32_t B, int32_t N) {
+  return (B > 0 && N > 0) ? pdsc::eig_scratch_bytes(B, N) : 0;
+}
+
+int pdsc_leading_eigenvector(pdsc_engine* e, int32_t B, int32_t N, const float* d_M, int32_t num_iterations, int32_t early_exit,
+                             float* d_eigenvector, int32_t* d_iterations_run, void* d_scratch, size_t scratch_bytes,
+                             void* cuda_stream) {
+  if (!e) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine");
+  if (B <= 0 || N <= 0) return fail(PDSC_ERR_SHAPE, "need B >= 1 and N >= 1 (got B=%d N=%d)", B, N);
+  if (num_iterations < 1 || num_iterations > 1000) return fail(PDSC_ERR_INVALID_ARGUMENT, "num_iterations %d out of range", num_iterations);
+  if (N > 24576) return fail(PDSC_ERR_UNSUPPORTED, "N=%d exceeds the supported maximum 24576", N);
+  if (!d_M || !d_eigenvector || !d_iterations_run) return fail(PDSC_ERR_INVALID_ARGUMENT, "pdsc_leading_eigenvector: null tensor pointer");
+  if (!d_scratch || scratch_bytes < pdsc::eig_scratch_bytes(B, N) || reinterpret_cast<uintptr_t>(d_scratch) % 16)
+    return fail(PDSC_ERR_WORKSPACE, "pdsc_leading_eigenvector: scratch too small or not 16-byte aligned (%zu bytes given, %zu needed)",
+                scratch_bytes, pdsc::eig_scratch_bytes(B, N));
+  DeviceGuard g(e->cfg.device);
+  const int rc = pdsc::launch_leading_eigenvector(d_M, d_eigenvector, d_iterations_run, B, N, num_iterations, early_exit, d_scratch,
+                                                  static_cast<cudaStream_t>(cuda_stream));
+  if (rc) return fail(PDSC_ERR_CUDA, "power iteration launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  return PDSC_OK;
+}
+
 size_t pdsc_match_scratch_bytes(int32_t Ns, int32_t Nt) {
   return (Ns > 0 && Nt > 0) ? pdsc::match_scratch_bytes(Ns, Nt) : 0;
 }

@@ -87,6 +87,11 @@ void launch_match(const void* src_desc, const void* tgt_desc, int desc_is_fp64, 
                   int Ns, int Nt, int D, int mutual, void* scratch, int32_t* corr, int32_t* count, float* corr_pos,
                   float* out_src, float* out_tgt, cudaStream_t st);
 
+// ---- f4: N x N power iteration (eig_power.cu) -----------------------------------------------------------------
+size_t eig_scratch_bytes(int B, int N);
+int launch_leading_eigenvector(const float* M, float* v, int* iters_run, int B, int N, int iters, int early_exit, void* scratch,
+                               cudaStream_t st);   // returns cudaError_t
+
 // ---- per-device launch configuration (device_state.cu) ----------------------------------------------------
 // opt `kernel` in to `bytes` of dynamic shared memory on the CURRENT device (no-op if already granted there)
 cudaError_t ensure_dynamic_smem(const void* kernel, int bytes);

@@ -40,11 +40,13 @@ def main():
     with torch.no_grad():
         out = model(data)             # no 'testing' key
     model.cal_seed_trans = orig
+    with torch.no_grad():      # the N x N use of the power iteration (PointDSC.py:170, disabled in the released forward)
+        m_eig = model.cal_leading_eigenvector(out["M"], method="power")
     np.savez_compressed(os.path.join(HERE, "eval_3dmatch_n256_b3.npz"), corr_pos=data["corr_pos"].numpy(),
                         src_keypts=data["src_keypts"].numpy(), tgt_keypts=data["tgt_keypts"].numpy(),
                         gt_trans=torch.stack([p["gt_trans"] for p in pairs], 0).numpy(),
                         final_trans=out["final_trans"].numpy(), final_labels=out["final_labels"].numpy(), M=out["M"].numpy(),
-                        seeds=seen["seeds"].numpy().astype(np.int32))
+                        seeds=seen["seeds"].numpy().astype(np.int32), M_eig=m_eig.numpy())
     err = (out["final_trans"] - torch.stack([p["gt_trans"] for p in pairs], 0)).abs().amax(dim=(1, 2))
     print("eval fixture: |T - gt| per set", err.tolist(), "M nonzero fraction", float((out["M"] > 0).float().mean()))
 

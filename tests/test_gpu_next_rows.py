@@ -208,3 +208,40 @@ def test_engines_on_two_devices_in_one_process():
         outs.append(m.run(*x, taps=["best"])["final_trans"][0].cpu().numpy())
     assert np.abs(outs[0] - c["final_trans"]).max() < 1e-4 and np.abs(outs[1] - c["final_trans"]).max() < 1e-4
     assert np.array_equal(outs[0], outs[1])
+
+
+# ---------------------------------------------------------------------------------------------------
+# f4: N x N power iteration (TMA-tiled GEMV)
+# ---------------------------------------------------------------------------------------------------
+def test_leading_eigenvector_vs_reference_on_its_own_M():
+    """cal_leading_eigenvector(M, 'power') of the reference on the M its non-testing forward returned (one allclose over the
+    batch there; per matrix here: every matrix of the fixture needs all 10 iterations, so the two rules coincide)."""
+    from pointdsc_b200.spectral import leading_eigenvector
+    z = np.load(os.path.join(GOLDEN, "eval_3dmatch_n256_b3.npz"))
+    v, iters = leading_eigenvector(torch.from_numpy(z["M"]).cuda(), num_iterations=10, early_exit=True)
+    ref = O.leading_eigenvector(torch.from_numpy(z["M"]), 10)[0].numpy()
+    assert np.abs(ref - z["M_eig"]).max() < 1e-6                                   # oracle == reference
+    assert np.abs(v.cpu().numpy() - z["M_eig"]).max() < 1e-5
+    assert iters.cpu().tolist() == [O.leading_eigenvector(torch.from_numpy(z["M"][b:b + 1]), 10)[1] for b in range(3)]
+
+
+@pytest.mark.parametrize("n", [1000, 1003, 5000])       # 16-byte aligned rows: bulk async copies; 1003: plain loads
+def test_leading_eigenvector_spectral_matching_matrix(n):
+    """The classical baseline's matrix (baseline_scripts/baseline_3DMatch.py:19-39: polynomial kernel of the length
+    differences, zero diagonal), ten fixed iterations, against the oracle's power iteration."""
+    from pointdsc_b200.spectral import leading_eigenvector
+    from pointdsc_b200.synth import make_pair
+    p = make_pair(3, n, "3dmatch", 0.3)
+    ds = torch.cdist(p["src_keypts"], p["src_keypts"]) - torch.cdist(p["tgt_keypts"], p["tgt_keypts"])
+    sigma = 0.1 / 3
+    m = torch.clamp(4.5 - ds ** 2 / 2 / sigma ** 2, min=0)
+    m.fill_diagonal_(0)
+    v, iters = leading_eigenvector(m[None].cuda(), num_iterations=10, early_exit=False)
+    x = torch.ones(n, 1)
+    for _ in range(10):
+        x = m @ x
+        x = x / (x.norm() + 1e-6)
+    assert int(iters[0]) == 10
+    assert float((v[0].cpu() - x[:, 0]).abs().max()) < 2e-5 * float(x.abs().max())
+    top = set(torch.argsort(v[0].cpu(), descending=True)[: n // 10].tolist())
+    assert len(top & set(range(int(0.3 * n)))) > 0.9 * len(top)                   # the leading eigenvector marks the inliers
