@@ -507,6 +507,34 @@ def measure_extras(args, model, rank, world, dev, barrier, max_over_ranks):
         sweep[f"N{n}"] = {"sets_per_s": bb * world * 3 / (ms * 1e-3), "ms_per_step": ms / 3, "batch_per_gpu": bb, "steps": 3}
         del dv
     out["config_d_sweep"] = sweep
+    # (2b) BASELINE.json configs A / B / C as named there (per GPU): A 3DMatch N=1000 B=64; B KITTI N=5000 B=32 (sigma_d 1.2);
+    #      C N=2000 with k=80 neighbours, B=256.  B needs the KITTI snapshot: a second module.
+    named = {}
+    for name, (ds, n, bb, kk) in {"A_3dmatch_N1000_B64": ("3dmatch", 1000, 64, 40), "B_kitti_N5000_B32": ("kitti", 5000, 32, 40),
+                                   "C_3dmatch_N2000_k80_B256": ("3dmatch", 2000, 256, 80)}.items():
+        if ds == args.dataset:
+            mod = model
+            mod.k = kk
+        else:
+            from pointdsc_b200 import PointDSC
+            mod = PointDSC(in_dim=6, num_layers=12, num_channels=128, num_iterations=10, ratio=0.1, k=kk, precision=args.precision,
+                           **CTOR[ds])
+            mod.load_state_dict(load_snapshot(ds), strict=False)
+            mod = mod.to(dev).eval()
+        h = make_inputs(n, bb, ds, rank, world)
+        dv = {k: h[k].to(dev) for k in ("corr_pos", "src_keypts", "tgt_keypts")}
+        mod.run(dv["corr_pos"], dv["src_keypts"], dv["tgt_keypts"])
+        barrier()
+        ms, outs = time_steps(mod, dv, 3, keep=True)
+        ms = max_over_ranks(ms)
+        err = (outs[-1]["final_trans"].cpu() - h["gt_trans"]).abs().amax(dim=(1, 2))
+        named[name] = {"sets_per_s": bb * world * 3 / (ms * 1e-3), "ms_per_step": ms / 3, "batch_per_gpu": bb, "k": kk, "steps": 3,
+                       "registered_fraction": float((err < (0.05 if ds == "3dmatch" else 0.5)).float().mean())}
+        del dv, outs
+        if mod is not model:
+            del mod
+    model.k = args.k
+    out["baseline_configs"] = named
     # (3) strong scaling: the global B = 256 batch split over the ranks
     if world > 1:
         bb = max(1, 256 // world)

@@ -71,6 +71,10 @@ CASES = [
     ("3dmatch", 1000, 13, 0.1, "io", 80),
     ("kitti", 1000, 6, 0.05, "io"),
     ("3dmatch", 1000, 14, 0.3, "full1k"),
+    # sizes that are a multiple of no tile size (the same sets tests/test_gpu_parity.py::test_ragged_sizes_vs_oracle runs
+    # against the oracle: here the REFERENCE is the authority)
+    ("3dmatch", 257, 357, 0.6, "io"),
+    ("3dmatch", 1003, 1103, 0.6, "io"),
 ]
 
 
