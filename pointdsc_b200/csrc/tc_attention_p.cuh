@@ -313,7 +313,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
           if (a.split) tmem_st16(tS + 32 + 16 * hf, lo);
         }
         // rare: the reference advanced, O (accumulated under the old reference) must be rescaled before PV_j
+#ifdef PDSC_EXP_NO_RESCALE          // timing experiment only (tools/build_variant.py): results are wrong
+        if (false) {
+#else
         if (__any_sync(0xffffffffu, advance && j > 0)) {
+#endif
           const int gp = gvb + j - 1;
           mbar_wait(pv_done + 8 * (gp & 1), (uint32_t)((gp >> 1) & 1));   // PV_{j-1} complete: O quiescent
           tc_fence_after();

@@ -111,7 +111,11 @@ __device__ __forceinline__ void stage_store64(uint8_t* stage, int lane, const ui
     const int rr = (lane >> 2) + 8 * i;
     const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
     void* p = dst(i, piece);
+#ifdef PDSC_EXP_NO_CHAIN_STORES      // timing experiment only (tools/build_variant.py): results are wrong
+    if (p && val.x == 0x7fc12345u) st_global_v4(p, val);
+#else
     if (p) st_global_v4(p, val);
+#endif
   }
 }
 
