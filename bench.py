@@ -535,6 +535,8 @@ def measure_extras(args, model, rank, world, dev, barrier, max_over_ranks):
             del mod
     model.k = args.k
     out["baseline_configs"] = named
+    # (2c) the rows beside the path, each timed with CUDA events on rank 0's device (every rank runs them)
+    out["next_rows"] = measure_next_rows(model, dev)
     # (3) strong scaling: the global B = 256 batch split over the ranks
     if world > 1:
         bb = max(1, 256 // world)
@@ -548,6 +550,60 @@ def measure_extras(args, model, rank, world, dev, barrier, max_over_ranks):
         out["strong_scaling"] = {"global_batch": bb * world, "batch_per_gpu": bb, "sets_per_s": bb * world * 10 / (ms * 1e-3),
                                  "ms_per_step": ms / 10, "steps": 10}
     return out
+
+
+def measure_next_rows(model, dev):
+    """f1 (front end), f3 (evaluation statistics), f4 (non-testing forward with M, N x N power iteration): milliseconds per call
+    and the achieved rate against the bound that applies (algorithmic bytes or FLOPs)."""
+    import torch
+    from pointdsc_b200.frontend import match
+    from pointdsc_b200.metrics import eval_stats
+    from pointdsc_b200.spectral import leading_eigenvector
+    from pointdsc_b200.synth import make_batch
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    res = {}
+    g = torch.Generator().manual_seed(0)
+    ns = nt = 5000
+    sd = torch.nn.functional.normalize(torch.randn(ns, 32, generator=g), dim=1).to(dev)
+    td = torch.nn.functional.normalize(torch.randn(nt, 32, generator=g), dim=1).to(dev)
+    sk, tk = torch.rand(ns, 3, generator=g).to(dev), torch.rand(nt, 3, generator=g).to(dev)
+    for mutual in (False, True):
+        ms = timed(lambda: match(sd, td, sk, tk, use_mutual=mutual))
+        flops = 2.0 * ns * nt * 32 * (2 if mutual else 1)
+        res[f"f1_match_fcgf32_Ns5000_Nt5000_mutual{int(mutual)}"] = {"ms": ms, "bound": "fp32", "achieved_tflops": flops / (ms * 1e-3) / 1e12,
+                                                                     "note": "includes the 4-byte device->host read of the correspondence count"}
+    b = make_batch(range(8), 1000, "3dmatch", 0.3)
+    B = 256
+    rep = {k: b[k].repeat(B // 8, *([1] * (b[k].dim() - 1))).to(dev) for k in ("src_keypts", "tgt_keypts", "gt_trans", "gt_labels")}
+    lab = (torch.rand(B, 1000, generator=g) < 0.3).float().to(dev)
+    ms = timed(lambda: eval_stats(rep["gt_trans"], rep["gt_trans"], rep["src_keypts"], rep["tgt_keypts"], lab, rep["gt_labels"]))
+    res["f3_eval_stats_B256_N1000"] = {"ms": ms, "bound": "hbm", "achieved_gbs": B * 1000 * 32.0 / (ms * 1e-3) / 1e9,
+                                       "note": "8 MB of inputs: launch-latency bound"}
+    n = 5000
+    pts = torch.rand(n, 3, generator=g) * 3
+    ds = torch.cdist(pts, pts)
+    m = torch.clamp(1 - (ds - ds.t().roll(1, 0)) ** 2, min=0)[None].contiguous().to(dev)
+    ms = timed(lambda: leading_eigenvector(m, num_iterations=10, early_exit=False), reps=3)
+    res["f4_leading_eigenvector_N5000_10iters"] = {"ms": ms, "bound": "hbm (L2-resident: 100 MB matrix re-read by every iteration)",
+                                                   "achieved_gbs": 10 * 4.0 * n * n / (ms * 1e-3) / 1e9}
+    bb = make_batch(range(16), 1000, "3dmatch", 0.3)
+    dv = [bb[k].to(dev) for k in ("corr_pos", "src_keypts", "tgt_keypts")]
+    was = model.training
+    model.eval()
+    ms = timed(lambda: model.run_eval(*dv, want_M=True), reps=3)
+    res["f4_forward_without_testing_key_B16_N1000_with_M"] = {"ms": ms, "sets_per_s": 16 / (ms * 1e-3)}
+    model.train(was)
+    return res
 
 
 def main():
