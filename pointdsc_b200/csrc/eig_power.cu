@@ -8,11 +8,12 @@
 // N x N form the north star describes: a memory-bound GEMV whose matrix tiles stream from HBM (or L2: M is re-read by every
 // iteration and 4 N^2 bytes fit the 126 MB L2 up to N ~ 5000) into shared memory through the TMA engine.
 //
-// gemv kernel   CTA = 32 rows of one set.  Column tiles of 32 rows x 512 columns (64 KB) arrive as 32 bulk async copies
-//               (cp.async.bulk, one contiguous 2 KB row segment each, mbarrier complete_tx) into a two-stage ring; the
-//               eight warps take four rows each, lane l reading columns 4 l + 128 i of the staged tile and of the vector as
+// gemv kernel   CTA = R <= 32 rows of one set (R chosen on the host so that a small problem is ONE wave of two CTAs per SM: with
+//               32 rows, N = 5000 is 157 CTAs on 148 SMs, i.e. two waves).  Column tiles of R rows x 512 columns arrive as R bulk
+//               async copies (cp.async.bulk, one contiguous 2 KB row segment each, mbarrier complete_tx) into a two-stage ring;
+//               warp w takes rows w, w + 8, ..., lane l reading columns 4 l + 128 i of the staged tile and of the vector as
 //               128-bit shared-memory loads; a row's 32 lane partials are combined by an xor-shuffle tree.  Every CTA also
-//               leaves the sum of squares of its 32 outputs (fixed order) for the normalisation.
+//               leaves the sum of squares of its outputs (fixed order) for the normalisation.
 // norm kernel   one CTA per set: adds the per-CTA partial sums in ascending order, scales, tests allclose against the
 //               previous iterate and latches a per-set `done` flag — later iterations of a finished set are no-ops, which is
 //               how the data-dependent early exit runs without a host synchronisation.
@@ -24,19 +25,18 @@
 namespace pdsc {
 using namespace ptx;
 
-constexpr int kEigRows = 32, kEigCols = 512, kEigThreads = 256;
-constexpr int kEigTileBytes = kEigRows * kEigCols * 4;                 // 64 KB
-constexpr int kEigSmem = 2 * kEigTileBytes + 64;                        // two stages + barriers (+ the vector, appended)
+constexpr int kEigRows = 32, kEigCols = 512, kEigThreads = 256;       // kEigRows: the maximum; R = rows_per_cta at run time
 
 __global__ void __launch_bounds__(kEigThreads) eig_gemv_kernel(const float* __restrict__ M, const float* __restrict__ v,
                                                                float* __restrict__ u, float* __restrict__ partial_ss,
-                                                               const int* __restrict__ done, int N, int use_tma) {
+                                                               const int* __restrict__ done, int N, int use_tma, int R) {
   extern __shared__ __align__(128) uint8_t esm[];
-  const int b = blockIdx.y, r0 = blockIdx.x * kEigRows;
+  const int b = blockIdx.y, r0 = blockIdx.x * R;
   if (done[b]) return;                                // the set converged in an earlier iteration
+  const int tile_bytes = R * kEigCols * 4;            // one stage: R rows x 2 KB
   float* tiles = reinterpret_cast<float*>(esm);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(esm + 2 * kEigTileBytes);
-  float* vs = reinterpret_cast<float*>(esm + kEigSmem);                 // [round_up(N, kEigCols)]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(esm + 2 * tile_bytes);
+  float* vs = reinterpret_cast<float*>(esm + 2 * tile_bytes + 64);      // [round_up(N, kEigCols)]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* Mb = M + (size_t)b * N * N;
   const float* vb = v + (size_t)b * N;
@@ -50,14 +50,14 @@ __global__ void __launch_bounds__(kEigThreads) eig_gemv_kernel(const float* __re
     fence_barrier_init();
   }
   __syncthreads();
-  const int rows_here = min(kEigRows, N - r0);
+  const int rows_here = min(R, N - r0);
 
   auto issue = [&](int t) {      // one elected thread: 2 KB per row, complete_tx on the stage's barrier
     const int st = t & 1, c0 = t * kEigCols;
     const int cols = min(kEigCols, N - c0);
     mbar_expect_tx(bar0 + 8 * st, (uint32_t)(rows_here * cols * 4));
     for (int r = 0; r < rows_here; ++r)
-      bulk_g2s(t_base + (uint32_t)(st * kEigTileBytes + r * kEigCols * 4), Mb + (size_t)(r0 + r) * N + c0, (uint32_t)(cols * 4),
+      bulk_g2s(t_base + (uint32_t)(st * tile_bytes + r * kEigCols * 4), Mb + (size_t)(r0 + r) * N + c0, (uint32_t)(cols * 4),
                bar0 + 8 * st);
   };
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -70,10 +70,10 @@ __global__ void __launch_bounds__(kEigThreads) eig_gemv_kernel(const float* __re
       const int st = t & 1;
       mbar_wait(bar0 + 8 * st, (uint32_t)((t >> 1) & 1));
       const int cols = min(kEigCols, N - t * kEigCols);
-      const float* T = tiles + (size_t)st * (kEigTileBytes / 4);
+      const float* T = tiles + (size_t)st * (tile_bytes / 4);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int r = warp * 4 + q;
+        const int r = warp + 8 * q;
         if (r < rows_here) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kEigThreads) eig_gemv_kernel(const float* __re
     }
   } else {
     for (int q = 0; q < 4; ++q) {
-      const int r = warp * 4 + q;
+      const int r = warp + 8 * q;
       if (r < rows_here) {
         const float* row = Mb + (size_t)(r0 + r) * N;
         for (int c = lane; c < N; c += 32) acc[q] = fmaf(row[c], vs[c], acc[q]);
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kEigThreads) eig_gemv_kernel(const float* __re
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float s = warp_sum(acc[q]);
-    const int r = warp * 4 + q;
+    const int r = warp + 8 * q;
     if (lane == 0) {
       usq[r] = (r < rows_here) ? s * s : 0.f;
       if (r < rows_here) u[(size_t)b * N + r0 + r] = s;
@@ -154,26 +154,33 @@ __global__ void eig_init_kernel(float* v, int* done, int* iters_run, int B, int 
 }
 
 size_t eig_scratch_bytes(int B, int N) {
-  const int nparts = (N + kEigRows - 1) / kEigRows;
+  const int nparts = (N + 7) / 8;                     // upper bound: the smallest rows-per-CTA is 8
   return (size_t)B * N * 4 + (size_t)B * nparts * 4 + (size_t)B * 4 + 256;
 }
 
 // v [B,N] receives the eigenvector, iters_run [B] the iterations executed per set.  scratch: u [B,N] | partial [B,nparts] | done [B]
 int launch_leading_eigenvector(const float* M, float* v, int* iters_run, int B, int N, int iters, int early_exit, void* scratch,
                                cudaStream_t st) {
-  const int nparts = (N + kEigRows - 1) / kEigRows;
+  // rows per CTA: 32 when the grid is many waves anyway, else what makes it one wave of two CTAs per SM
+  const int sms = device_sm_count();
+  int R = kEigRows;
+  if ((long long)B * ((N + R - 1) / R) < 4LL * sms) {
+    R = (int)(((long long)B * N + 2LL * sms - 1) / (2LL * sms));
+    R = R < 8 ? 8 : (R > kEigRows ? kEigRows : R);
+  }
+  const int nparts = (N + R - 1) / R;
   float* u = static_cast<float*>(scratch);
   float* partial = u + (size_t)B * N;
-  int* done = reinterpret_cast<int*>(partial + (size_t)B * nparts);
+  int* done = reinterpret_cast<int*>(partial + (size_t)B * ((N + 7) / 8));
   const int NP = (N + kEigCols - 1) / kEigCols * kEigCols;
-  const int smem = kEigSmem + NP * 4;
+  const int smem = 2 * R * kEigCols * 4 + 64 + NP * 4;
   if (smem > 227 * 1024) return (int)cudaErrorInvalidValue;
   const cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(eig_gemv_kernel), smem);
   if (e != cudaSuccess) return (int)e;
   const int use_tma = (N % 4 == 0) && (reinterpret_cast<uintptr_t>(M) % 16 == 0);
   eig_init_kernel<<<(unsigned)(((long long)B * N + 255) / 256), 256, 0, st>>>(v, done, iters_run, B, N);
   for (int t = 0; t < iters; ++t) {
-    eig_gemv_kernel<<<dim3(nparts, B), kEigThreads, smem, st>>>(M, v, u, partial, done, N, use_tma);
+    eig_gemv_kernel<<<dim3(nparts, B), kEigThreads, smem, st>>>(M, v, u, partial, done, N, use_tma, R);
     eig_norm_kernel<<<B, 256, 0, st>>>(u, v, partial, done, iters_run, N, nparts, early_exit);
   }
   return (int)cudaGetLastError();

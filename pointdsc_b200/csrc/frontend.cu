@@ -8,18 +8,23 @@
 //     corr_pos   = concat(src_keypts[corr[:,0]], tgt_keypts[corr[:,1]]) - mean over the kept correspondences
 //
 // Kernels (one pair per call, Ns source and Nt target key points, descriptor dimension D <= 64):
-//   match_rows_kernel<T>   thread = source row (descriptor in registers-by-smem), target descriptors staged through shared
-//                          memory in tiles and read as broadcasts; the row keeps a running (distance, index) with a strict '<',
-//                          which is numpy's first-minimum rule.  The square root is applied BEFORE the comparison, as the
-//                          reference does (it merges distances that differ by less than an ulp of the root).  With the mutual
-//                          check, column minima are merged across CTAs with atomicMin on the distance's bit pattern
-//                          (distances are >= 0, so the IEEE bit patterns order like the values).
-//   match_cols_kernel<T>   second pass for the mutual check: the lowest source index among those that attain a column's minimum
-//                          (every distance is recomputed by the same instruction sequence, so equality is exact).
+//   match_rows_kernel<T>   nearest column of every row of a [rows x cols] problem over ONE chunk of the columns (grid.y chunks, so
+//                          that a 5000 x 5000 problem fills the GPU): thread = row, its descriptor cached 16 channels at a time in
+//                          registers; the chunk's descriptors are staged channel-major in shared memory, 64 columns (fp32) or 32
+//                          (fp64) per tile, and read as BROADCAST 128-bit loads of four (two) adjacent columns — 64 FMAs per 16
+//                          loads, every dot product one ascending-channel FMA chain in T.  The square root is applied BEFORE the
+//                          strict '<' comparison, as the reference does (it merges distances that differ by less than an ulp of
+//                          the root), which is numpy's first-minimum rule inside the chunk.  Result: (distance, index) per
+//                          (row, chunk).
+//   match_reduce_kernel<T> thread = row: scans its chunks in ascending column order with the same strict '<' — the first
+//                          minimum of the whole row.  No atomics anywhere.
+//   The mutual check needs argmin along the other axis: the SAME two kernels with the roles of the two descriptor sets
+//   swapped.  a*b == b*a exactly and the channel order is the same, so both launches see bit-identical distances — the
+//   consistency numpy gets from taking both argmins of one matrix.
 //   compact_center_kernel  one CTA: ordered compaction of the kept pairs (ascending source index), gather of the key points,
 //                          column means in fp64, centred corr_pos — written in the layout pdsc_forward consumes.
-// The dot product is accumulated in ascending channel order with one FMA per channel in T; the reference's BLAS fixes no
-// accumulation order, so indices are only comparable where the best and the second-best distance are separated (tests).
+// The reference's BLAS fixes no accumulation order, so indices are only comparable where the best and the second-best distance
+// are separated (tests); exact duplicates resolve to the first one, as in numpy.
 #include <cfloat>
 
 #include "common.cuh"
@@ -27,19 +32,9 @@
 
 namespace pdsc {
 
-constexpr int kMatchRows = 128;   // source rows per CTA (one per thread)
-constexpr int kMatchTile = 64;    // target rows per shared-memory tile
+constexpr int kMatchRows = 128;   // rows per CTA (one per thread)
 constexpr int kMatchMaxD = 64;
-
-template <typename T> struct BitsOf;
-template <> struct BitsOf<float> {
-  using type = unsigned int;
-  __device__ static unsigned int get(float x) { return __float_as_uint(x); }
-};
-template <> struct BitsOf<double> {
-  using type = unsigned long long;
-  __device__ static unsigned long long get(double x) { return (unsigned long long)__double_as_longlong(x); }
-};
+constexpr int kMatchMaxChunks = 32;
 
 template <typename T>
 __device__ __forceinline__ T feature_distance(T dot) {
@@ -47,59 +42,92 @@ __device__ __forceinline__ T feature_distance(T dot) {
   if (sizeof(T) == 4) return (T)__fsqrt_rn(__fadd_rn(__fsub_rn(2.0f, __fmul_rn(2.0f, (float)dot)), 1e-6f));
   return (T)__dsqrt_rn(__dadd_rn(__dsub_rn(2.0, __dmul_rn(2.0, (double)dot)), 1e-6));
 }
+template <typename T>
+__device__ __forceinline__ T fma_t(T a, T b, T c) {
+  if (sizeof(T) == 4) return (T)__fmaf_rn((float)a, (float)b, (float)c);
+  return (T)__fma_rn((double)a, (double)b, (double)c);
+}
 
-// PASS 0: row minima (+ column minimum VALUES when col_min != nullptr).   PASS 1: column argmin given the column minima.
-template <typename T, int PASS>
-__global__ void __launch_bounds__(kMatchRows) match_kernel(const T* __restrict__ src_desc, const T* __restrict__ tgt_desc, int Ns,
-                                                           int Nt, int D, int32_t* __restrict__ row_idx,
-                                                           typename BitsOf<T>::type* __restrict__ col_min,
-                                                           int32_t* __restrict__ col_idx) {
+template <typename T> struct MatchPartial { T dist; int idx; int pad; };
+
+template <typename T>
+__global__ void __launch_bounds__(kMatchRows) match_rows_kernel(const T* __restrict__ row_desc, const T* __restrict__ col_desc,
+                                                                int rows, int cols, int D, int cols_per_chunk,
+                                                                MatchPartial<T>* __restrict__ partial) {
+  constexpr int TT = sizeof(T) == 4 ? 64 : 32;        // columns per shared-memory tile
+  constexpr int VW = 16 / (int)sizeof(T);             // columns per 128-bit load
   extern __shared__ __align__(16) unsigned char match_smem[];
-  T* s_src = reinterpret_cast<T*>(match_smem);       // [D][kMatchRows]   (channel-major: conflict-free per-thread reads)
-  T* s_tgt = s_src + (size_t)D * kMatchRows;          // [kMatchTile][D]   (read as broadcasts)
+  T* s_row = reinterpret_cast<T*>(match_smem);        // [D][kMatchRows]  channel-major: conflict-free per-thread reads
+  T* s_col = s_row + (size_t)D * kMatchRows;          // [D][TT]          channel-major: broadcast vector reads
   const int tid = threadIdx.x;
   const int i = blockIdx.x * kMatchRows + tid;
+  const int c_begin = blockIdx.y * cols_per_chunk, c_end = min(cols, c_begin + cols_per_chunk);
   for (int e = tid; e < D * kMatchRows; e += kMatchRows) {
     const int r = e / D, d = e % D;                   // coalesced over the row-major descriptor block
     const int gi = blockIdx.x * kMatchRows + r;
-    s_src[(size_t)d * kMatchRows + r] = gi < Ns ? src_desc[(size_t)gi * D + d] : (T)0;
+    s_row[(size_t)d * kMatchRows + r] = gi < rows ? row_desc[(size_t)gi * D + d] : (T)0;
   }
   T best = (T)0;
   int best_j = -1;
-  for (int j0 = 0; j0 < Nt; j0 += kMatchTile) {
+  for (int j0 = c_begin; j0 < c_end; j0 += TT) {
     __syncthreads();
-    const int cnt = min(kMatchTile, Nt - j0);
-    for (int e = tid; e < cnt * D; e += kMatchRows) s_tgt[e] = tgt_desc[(size_t)j0 * D + e];
+    const int cnt = min(TT, c_end - j0);
+    for (int e = tid; e < TT * D; e += kMatchRows) {
+      const int t = e / D, d = e % D;
+      s_col[(size_t)d * TT + t] = t < cnt ? col_desc[(size_t)(j0 + t) * D + d] : (T)0;
+    }
     __syncthreads();
-    if (i < Ns) {
-      for (int t = 0; t < cnt; ++t) {
-        T acc = (T)0;
-        const T* tg = s_tgt + (size_t)t * D;
-        for (int d = 0; d < D; ++d) {
-          if (sizeof(T) == 4) acc = (T)__fmaf_rn((float)s_src[(size_t)d * kMatchRows + tid], (float)tg[d], (float)acc);
-          else acc = (T)__fma_rn((double)s_src[(size_t)d * kMatchRows + tid], (double)tg[d], (double)acc);
-        }
-        const T dist = feature_distance<T>(acc);
-        const int j = j0 + t;
-        if (PASS == 0) {
-          if (best_j < 0 || dist < best) { best = dist; best_j = j; }    // strict '<': the first minimum wins
-          if (col_min) atomicMin(col_min + j, BitsOf<T>::get(dist));
-        } else {
-          if (BitsOf<T>::get(dist) == col_min[j]) atomicMin(col_idx + j, i);
+    T acc[TT];
+#pragma unroll
+    for (int t = 0; t < TT; ++t) acc[t] = (T)0;
+    for (int d0 = 0; d0 < D; d0 += 16) {
+      T sv[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) sv[q] = (d0 + q < D) ? s_row[(size_t)(d0 + q) * kMatchRows + tid] : (T)0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        if (d0 + q < D) {                            // warp-uniform
+          const T* cv = s_col + (size_t)(d0 + q) * TT;
+#pragma unroll
+          for (int t = 0; t < TT; t += VW) {
+            if (sizeof(T) == 4) {
+              const float4 v = *reinterpret_cast<const float4*>(cv + t);
+              acc[t] = fma_t<T>(sv[q], (T)v.x, acc[t]); acc[t + 1] = fma_t<T>(sv[q], (T)v.y, acc[t + 1]);
+              acc[t + 2] = fma_t<T>(sv[q], (T)v.z, acc[t + 2]); acc[t + 3] = fma_t<T>(sv[q], (T)v.w, acc[t + 3]);
+            } else {
+              const double2 v = *reinterpret_cast<const double2*>(cv + t);
+              acc[t] = fma_t<T>(sv[q], (T)v.x, acc[t]); acc[t + 1] = fma_t<T>(sv[q], (T)v.y, acc[t + 1]);
+            }
+          }
         }
       }
     }
+#pragma unroll
+    for (int t = 0; t < TT; ++t) {
+      if (t < cnt) {
+        const T dist = feature_distance<T>(acc[t]);
+        if (best_j < 0 || dist < best) { best = dist; best_j = j0 + t; }      // strict '<': the first minimum wins
+      }
+    }
   }
-  if (PASS == 0 && i < Ns) row_idx[i] = best_j;
+  if (i < rows) {
+    MatchPartial<T>& o = partial[(size_t)i * gridDim.y + blockIdx.y];
+    o.dist = best;
+    o.idx = best_j;
+  }
 }
 
-template <typename Bits>
-__global__ void match_init_kernel(Bits* col_min, int32_t* col_idx, int Nt) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < Nt) {
-    col_min[j] = ~(Bits)0;
-    col_idx[j] = 0x7FFFFFFF;
+template <typename T>
+__global__ void match_reduce_kernel(const MatchPartial<T>* __restrict__ partial, int rows, int chunks, int32_t* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  T best = (T)0;
+  int best_j = -1;
+  for (int c = 0; c < chunks; ++c) {                  // ascending column ranges: strict '<' keeps the first minimum
+    const MatchPartial<T> p = partial[(size_t)i * chunks + c];
+    if (p.idx >= 0 && (best_j < 0 || p.dist < best)) { best = p.dist; best_j = p.idx; }
   }
+  idx[i] = best_j;
 }
 
 // One CTA.  keep[i] = !mutual || col_idx[row_idx[i]] == i ; ordered compaction ; gather ; centre.
@@ -174,27 +202,45 @@ __global__ void __launch_bounds__(kCompactThreads) compact_center_kernel(const i
   }
 }
 
+static int match_chunks(int rows) {
+  const int row_ctas = (rows + kMatchRows - 1) / kMatchRows;
+  int chunks = (4 * device_sm_count() + row_ctas - 1) / row_ctas;      // about four CTAs per SM
+  return chunks < 1 ? 1 : (chunks > kMatchMaxChunks ? kMatchMaxChunks : chunks);
+}
+
+template <typename T>
+static void nearest_columns(const T* row_desc, const T* col_desc, int rows, int cols, int D, MatchPartial<T>* partial, int32_t* idx,
+                            cudaStream_t st) {
+  constexpr int TT = sizeof(T) == 4 ? 64 : 32;
+  int chunks = match_chunks(rows);
+  int per = (cols + chunks - 1) / chunks;
+  per = (per + TT - 1) / TT * TT;                      // whole tiles per chunk
+  chunks = (cols + per - 1) / per;
+  const int smem = (int)sizeof(T) * D * (kMatchRows + TT);
+  ensure_dynamic_smem(reinterpret_cast<const void*>(match_rows_kernel<T>), smem);
+  match_rows_kernel<T><<<dim3((rows + kMatchRows - 1) / kMatchRows, chunks), kMatchRows, smem, st>>>(row_desc, col_desc, rows, cols,
+                                                                                                    D, per, partial);
+  match_reduce_kernel<T><<<(rows + 255) / 256, 256, 0, st>>>(partial, rows, chunks, idx);
+}
+
 template <typename T>
 static void launch_match_t(const T* src_desc, const T* tgt_desc, const float* src_keypts, const float* tgt_keypts, int Ns, int Nt,
                            int D, int mutual, void* scratch, int32_t* corr, int32_t* count, float* corr_pos, float* out_src,
                            float* out_tgt, cudaStream_t st) {
-  using Bits = typename BitsOf<T>::type;
-  // scratch: row_idx [Ns] int32 | col_idx [Nt] int32 | col_min [Nt] Bits (8-byte aligned)
+  // scratch: row_idx [Ns] int32 | col_idx [Nt] int32 | partial [max(Ns, Nt)][kMatchMaxChunks] (16-byte aligned)
   int32_t* row_idx = static_cast<int32_t*>(scratch);
   int32_t* col_idx = row_idx + Ns;
-  Bits* col_min = reinterpret_cast<Bits*>((reinterpret_cast<uintptr_t>(col_idx + Nt) + 7) & ~uintptr_t(7));
-  const int smem = (int)sizeof(T) * D * (kMatchRows + kMatchTile);
-  const int grid = (Ns + kMatchRows - 1) / kMatchRows;
-  ensure_dynamic_smem(reinterpret_cast<const void*>(match_kernel<T, 0>), smem);
-  ensure_dynamic_smem(reinterpret_cast<const void*>(match_kernel<T, 1>), smem);
-  if (mutual) match_init_kernel<Bits><<<(Nt + 255) / 256, 256, 0, st>>>(col_min, col_idx, Nt);
-  match_kernel<T, 0><<<grid, kMatchRows, smem, st>>>(src_desc, tgt_desc, Ns, Nt, D, row_idx, mutual ? col_min : nullptr, col_idx);
-  if (mutual) match_kernel<T, 1><<<grid, kMatchRows, smem, st>>>(src_desc, tgt_desc, Ns, Nt, D, row_idx, col_min, col_idx);
+  auto* partial = reinterpret_cast<MatchPartial<T>*>((reinterpret_cast<uintptr_t>(col_idx + Nt) + 15) & ~uintptr_t(15));
+  nearest_columns<T>(src_desc, tgt_desc, Ns, Nt, D, partial, row_idx, st);
+  if (mutual) nearest_columns<T>(tgt_desc, src_desc, Nt, Ns, D, partial, col_idx, st);   // argmin along the other axis
   compact_center_kernel<<<1, kCompactThreads, 0, st>>>(row_idx, col_idx, src_keypts, tgt_keypts, Ns, mutual, corr, count, corr_pos,
                                                        out_src, out_tgt);
 }
 
-size_t match_scratch_bytes(int Ns, int Nt) { return (size_t)(Ns + Nt) * sizeof(int32_t) + (size_t)Nt * 8 + 16; }
+size_t match_scratch_bytes(int Ns, int Nt) {
+  const size_t rows = (size_t)(Ns > Nt ? Ns : Nt);
+  return (size_t)(Ns + Nt) * sizeof(int32_t) + rows * kMatchMaxChunks * sizeof(MatchPartial<double>) + 32;
+}
 int match_max_dim() { return kMatchMaxD; }
 
 void launch_match(const void* src_desc, const void* tgt_desc, int desc_is_fp64, const float* src_keypts, const float* tgt_keypts,
