@@ -1,28 +1,30 @@
-// Stage ii on the 5th-generation tensor cores (tcgen05 + TMEM), precisions PDSC_BF16X3 / PDSC_BF16.
+// Stage ii on the 5th-generation tensor cores (tcgen05 + TMEM), precisions PDSC_FP16X3 (default) / PDSC_BF16X3 / PDSC_BF16.
 //
 // Reference: models/PointDSC.py:9-77 — per layer  PointCN (conv+BN+ReLU) -> Q,K,V 1x1 convs ->
 //   P = softmax_j(SC_ij * q_i.k_j / sqrt(C)), msg = P V -> fc_message (128->64->64->128) -> residual.
 //
-// Numerics.  The stack is chaotic (|logit| reaches ~2.6e3, softmax is near-argmax): tools/numerics_probe.py
-// shows single bf16 / fp16 / tf32 operands move the final R/t by up to 7e-4, above the 1e-4 bar, while a
-// bf16 hi/lo split of BOTH operands of every contraction (x ~= hi + lo, products hi*hi + hi*lo + lo*hi,
-// fp32 accumulation in TMEM) stays at the fp32 noise floor (2e-6).  PDSC_BF16X3 issues those three
-// kind::f16 MMAs per k-step; PDSC_BF16 issues only hi*hi (3x less tensor work, throughput mode).
+// Numerics.  The stack is chaotic (|logit| reaches ~2.6e3, softmax is near-argmax): tools/numerics_probe.py shows single
+// bf16 / fp16 / tf32 operands move the final R/t by up to 7e-4, above the 1e-4 bar, while a 16-bit hi/lo split of BOTH
+// operands of every contraction (x ~= hi + lo, products hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) stays at the fp32
+// noise floor (fp16 split: 22 significant bits, 2.4e-6; bf16 split: 16 bits).  The x3 modes issue those three kind::f16 MMAs per
+// k-step; PDSC_BF16 issues only hi*hi (3x less tensor work, throughput mode).
 //
-// Operand images.  Every MMA operand is a K-major bf16 "panel": rows x 64 elements = rows x 128 B in the
-// canonical SWIZZLE_128B layout (8-row atoms of 1024 B; 16-byte chunk c of row r stored at chunk c ^ (r & 7)).
-// A 128-channel operand is two panels; "hi" panels come first, "lo" panels second.  Producers write Q / K / V
-// straight into this image layout in HBM, so a consumer stages a whole operand tile with ONE bulk async copy
-// (cp.async.bulk -> TMA engine, mbarrier complete_tx) and no tensor map.  Per set b:
+// Operand images.  Every MMA operand read from shared memory is a K-major 16-bit "panel": rows x 64 elements = rows x 128 B in
+// the canonical SWIZZLE_128B layout (8-row atoms of 1024 B; 16-byte chunk c of row r stored at chunk c ^ (r & 7)).  A
+// 128-channel operand is two panels; "hi" panels come first, "lo" panels second.  Producers write Q / K / V straight into this
+// image layout in HBM, so a consumer stages a whole operand tile with ONE bulk async copy (cp.async.bulk -> TMA engine, mbarrier
+// complete_tx) and no tensor map.  Per set b:
 //     Qimg[b][qt]   qt = 128-query tile : [Qhi 32K][Qlo 32K]                       (Q pre-scaled by log2e/sqrt(C))
-//     KVimg[b][kt]  kt = 64-key tile    : [Khi 16K][Klo 16K][Vhi 16K][Vlo 16K]   (V in the K format, read MN-major)
+//     KVimg[b][kt]  kt = 64-key tile    : [Khi 16K][Klo 16K][Vhi 16K][Vlo 16K]   (V in the K format, read as an MN-major B operand)
 //
-// Kernels per layer (all warp-specialised, one CTA per SM, mbarrier pipelines):
-//   tc_chain<PCQ>   feat  -> PointCN -> feat1 (fp32, HBM) -> Q image                 weights resident in smem
+// Kernels per layer (all warp-specialised, persistent: one CTA per SM, mbarrier pipelines):
+//   tc_chain<PCQ>   feat  -> PointCN -> feat1 (fp32, HBM; and as a hi|lo operand in TENSOR MEMORY) -> Q image    tc_chain.cuh
 //   tc_chain<KV>    feat1 -> K image, V image (K format)
-//   tc_attention    flash-style: S = Q K^T into TMEM, SC-weighted online softmax by 128 row-owner threads,
-//                   P (bf16 hi/lo) through smem, O += P V in TMEM; lazy rescale; msg (fp32, HBM)
-//   tc_chain<MSG>   msg -> fc_message chain -> + feat1 -> feat (fp32, HBM)
+//   tc_attention_persistent   flash-style over (set, 128-query tile) items: Q and P are A operands IN TENSOR MEMORY (P is written
+//                   over its own S tile), S = Q K^T per 64-key tile, SC-weighted online softmax by two groups of 128 row-owner
+//                   threads on alternate tiles, O += P V in TMEM, lazy rescale; msg (fp32, HBM)                   tc_attention_p.cuh
+//   tc_chain<MSG>   msg -> fc_message chain (hidden activations stay in tensor memory) -> + feat1 -> feat (fp32, HBM)
+// Synchronisation rules of these kernels (counted barriers, tensor-memory write-after-read): tc_common.cuh.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>

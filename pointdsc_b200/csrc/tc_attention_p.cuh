@@ -373,7 +373,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
       // group g drains columns [64 g, 64 g + 64) of every row, 32 columns at a time, through its 16 KB half of the Q
       // staging buffer ([128 rows][128 B], 16-byte chunks XOR-swizzled by row) so that every store instruction writes
       // four full 128-byte lines.  The buffer is free here: both halves of the next Q have already gone through it.
-      if (it + 1 < my_items && a.split && g == 0) mbar_wait(ql_used, (uint32_t)((it + 1) & 1));
+      // (split formats: group 1 moves the lo image, which fills the whole buffer, so group 0 waits for it; single formats: only
+      // group 0 moves an image - the hi one, also the whole buffer - so group 1 waits for that)
+      if (it + 1 < my_items) {
+        if (a.split && g == 0) mbar_wait(ql_used, (uint32_t)((it + 1) & 1));
+        if (!a.split && g == 1) mbar_wait(qh_used, (uint32_t)((it + 1) & 1));
+      }
       uint8_t* ost = smem + kAttnPQ + g * 16384;
       float* dst = a.msg + ((size_t)b * a.N + qt * 128) * kC + 64 * g;
       const int rsub = gt >> 3, piece = gt & 7;   // read-out: rows rsub + 16 i, 16-byte piece of the 128-byte segment
