@@ -61,57 +61,96 @@ __global__ void __launch_bounds__(256) knn_select_kernel(const float* __restrict
   uint32_t* hist = reinterpret_cast<uint32_t*>(base + (size_t)P * 8);               // [256]
   uint32_t* keys = hist + 256;                                                      // [NP]
   const float* d = dist + (size_t)row * N;
-  for (int j = lane; j < NP; j += 32) keys[j] = j < N ? dist_key32(d[j]) : 0xFFFFFFFFu;
+  // the row arrives with ALL of its loads in flight at once: 16-byte cp.async when the row is 16-byte aligned (N % 4 == 0),
+  // else scalar loads in batches of eight — a plain `keys[j] = f(d[j])` loop waits one memory latency per iteration, which at
+  // N = 5000 (157 iterations, 8 warps per SM) was nearly all of this kernel's 1.6 ms in the KITTI configuration
+  if ((N & 3) == 0) {
+    const uint32_t kbase = (uint32_t)__cvta_generic_to_shared(keys);
+    for (int j4 = lane; j4 < (N >> 2); j4 += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kbase + (uint32_t)j4 * 16u), "l"(d + 4 * j4) : "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else {
+    for (int j0 = lane; j0 < N; j0 += 256) {
+      float t[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t[q] = (j0 + 32 * q < N) ? d[j0 + 32 * q] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (j0 + 32 * q < N) keys[j0 + 32 * q] = __float_as_uint(t[q]);
+    }
+  }
+  __syncwarp();
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+  for (int j = lane; j < NP; j += 32) {
+    const uint32_t key = j < N ? dist_key32(__uint_as_float(keys[j])) : 0xFFFFFFFFu;
+    keys[j] = key;
+    if (j < N) { kmin = min(kmin, key); kmax = max(kmax, key); }
+  }
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
   const uint32_t lt_mask = (1u << lane) - 1u;
   // ---- radix select of the (k+1)-th smallest key -----------------------------------------------------
-  uint32_t prefix = 0u, mask = 0u;
+  // Distances of unit vectors share sign and most exponent bits: the digits START at the highest bit in which the row's keys
+  // differ (everything above it is common), so the first histogram already spreads over its 256 bins.  Starting at bit 31 the
+  // first two passes put nearly every key of a row into one or two bins — 32-way serialised shared-memory atomics, which made
+  // this kernel 1.6 ms of the KITTI N = 5000 configuration.
+  uint32_t prefix = 0u, T;
   int need = k + 1;                          // rank (1-based) still to be located among the keys matching `prefix`
+  if (kmin == kmax) {
+    T = kmin;                                // every distance equal: the k + 1 lowest indices
+  } else {
+    int hi_bit = 31 - __clz(kmin ^ kmax);    // highest differing bit
+    prefix = (hi_bit == 31) ? 0u : (kmin >> (hi_bit + 1)) << (hi_bit + 1);
 #pragma unroll 1
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
+    while (hi_bit >= 0) {
+      const int width = hi_bit + 1 < 8 ? hi_bit + 1 : 8;
+      const int shift = hi_bit + 1 - width;
+      const uint32_t dmask = (1u << width) - 1u;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) hist[lane * 8 + q] = 0u;
-    __syncwarp();
-    for (int j = lane; j < NP; j += 32) {
-      const uint32_t v = keys[j];
-      if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1u);
-    }
-    __syncwarp();
-    uint32_t c[8], lane_sum = 0u;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { c[q] = hist[lane * 8 + q]; lane_sum += c[q]; }
-    uint32_t incl = lane_sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    const uint32_t excl = incl - lane_sum;
-    const bool mine = excl < (uint32_t)need && (uint32_t)need <= incl;   // exactly one lane (need <= matching count)
-    uint32_t digit = 0u, rem = 0u;
-    if (mine) {
-      uint32_t cum = excl;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (cum < (uint32_t)need && (uint32_t)need <= cum + c[q]) { digit = (uint32_t)(lane * 8 + q); rem = (uint32_t)need - cum; }
-        cum += c[q];
+      for (int q = 0; q < 8; ++q) hist[lane * 8 + q] = 0u;
+      __syncwarp();
+      for (int j = lane; j < NP; j += 32) {
+        const uint32_t v = keys[j];
+        const bool in = (hi_bit == 31) || ((v >> (hi_bit + 1)) == (prefix >> (hi_bit + 1)));
+        if (in && j < N) atomicAdd(&hist[(v >> shift) & dmask], 1u);
       }
+      __syncwarp();
+      uint32_t c[8], lane_sum = 0u;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { c[q] = hist[lane * 8 + q]; lane_sum += c[q]; }
+      uint32_t incl = lane_sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t excl = incl - lane_sum;
+      const bool mine = excl < (uint32_t)need && (uint32_t)need <= incl;   // exactly one lane (need <= matching count)
+      uint32_t digit = 0u, rem = 0u;
+      if (mine) {
+        uint32_t cum = excl;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (cum < (uint32_t)need && (uint32_t)need <= cum + c[q]) { digit = (uint32_t)(lane * 8 + q); rem = (uint32_t)need - cum; }
+          cum += c[q];
+        }
+      }
+      const int srcl = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+      digit = __shfl_sync(0xffffffffu, digit, srcl);
+      need = (int)__shfl_sync(0xffffffffu, rem, srcl);
+      prefix |= digit << shift;
+      hi_bit = shift - 1;
+      __syncwarp();
     }
-    const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
-    digit = __shfl_sync(0xffffffffu, digit, src);
-    need = (int)__shfl_sync(0xffffffffu, rem, src);
-    prefix |= digit << shift;
-    mask |= 0xFFu << shift;
-    __syncwarp();
+    T = prefix;
   }
   // ---- ordered compaction: key < T, plus the `need` lowest indices with key == T ----------------------
-  const uint32_t T = prefix;
   int out = 0, eq_seen = 0;
   for (int j0 = 0; j0 < NP; j0 += 32) {
     const uint32_t v = keys[j0 + lane];
-    const bool eq = v == T;
+    const bool eq = v == T && (j0 + lane < N);
     const uint32_t beq = __ballot_sync(0xffffffffu, eq);
-    const bool take = (v < T) || (eq && eq_seen + __popc(beq & lt_mask) < need);
+    const bool take = (j0 + lane < N) && ((v < T) || (eq && eq_seen + __popc(beq & lt_mask) < need));
     const uint32_t bt = __ballot_sync(0xffffffffu, take);
     if (take) sel[out + __popc(bt & lt_mask)] = ((unsigned long long)v << 32) | (unsigned)(j0 + lane);
     out += __popc(bt);
@@ -152,20 +191,25 @@ void launch_knn_select(const float* dist, int32_t* knn_idx, int B, int N, int S,
   knn_select_kernel<<<(rows + warps - 1) / warps, warps * 32, smem, st>>>(dist, knn_idx, N, rows, k, warps, P);
 }
 
-// ---- compatibility matrix + power iteration: ONE WARP PER SEED ------------------------------------------
+// ---- compatibility matrix + power iteration: one warp (k <= 40) or one 4-warp CTA (k > 40) per seed ----------------------
 // (round 1 ran one 64-thread CTA per seed with block barriers between gather, Gram and each of the 10 iterations: every
 // phase waited for the slowest of two warps and a CTA held 28 KB of shared memory through its latency-bound phases — 0.71 ms
-// for B * S = 25 600 seeds.)  Here a warp owns a seed from the gather to the last iterate, so nothing but __syncwarp()
-// separates the phases, and up to 12 warps per SM sit in different phases and hide each other's latencies:
-//   gather   the k neighbour rows arrive with cp.async (16 bytes per lane, four rows per instruction), one 32-channel QUARTER
-//            at a time, so the feature tile costs k x 128 B of shared memory instead of k x 512 B (16 warps per SM);
-//   Gram     4 x 4 register blocks on or above the diagonal (55 blocks for k = 40: two rounds of 32 lanes), 8 LDS.128 per
-//            64 FMAs, accumulated over the two halves in ascending channel order, one fp32 FMA each;
+// for B * S = 25 600 seeds.)  A seed is owned by a GROUP of WPS warps from the gather to the last iterate:
+//   WPS = 1 (k <= 40, the released configuration): nothing but __syncwarp() separates the phases, and 16 warps per SM sit in
+//           different phases and hide each other's latencies;
+//   WPS = 4 (k > 40, e.g. BASELINE config C with k = 80): the 210 register blocks of an 80 x 80 Gram are two rounds of 128
+//           threads (one warp would need seven rounds and four passes over the gathered features), five CTAs per SM.
+// Phases:
+//   gather   the k neighbour rows arrive with cp.async (16 bytes per lane, eight lanes per row), one 32-channel QUARTER at a
+//            time, so the feature tile costs k x 128 B of shared memory instead of k x 512 B;
+//   Gram     4 x 4 register blocks on or above the diagonal (55 blocks for k = 40), 8 LDS.128 per 64 FMAs, accumulated over the
+//            four quarters in ascending channel order, one fp32 FMA each;
 //   compat   feature-compat * spatial-compat with the reference's rounded operation sequence, M symmetric in shared memory;
-//   power    lane l owns rows l, l+32, l+64, l+96; row a is read as column a (M is symmetric: consecutive lanes read
-//            consecutive words); the squared norm is summed per 32-row group by shuffles and the groups are added in
-//            ascending order; every iterate is stored and the "all rows passed allclose at iteration t" bits of the seed
-//            are ANDed into the set's word.
+//   power    thread = (row group, column quarter): the k x k matrix-vector product is spread over all threads of the group; a
+//            row's four partial sums (ascending column order within a quarter) are combined by an xor butterfly,
+//            (q0 + q1) + (q2 + q3), the squared norm by a butterfly over the row groups (and, for WPS = 4, the four warps'
+//            sums in ascending order): fixed orders, identical on every thread.  Every iterate is stored and the "all rows
+//            passed allclose at iteration t" bits of the seed are ANDed into the set's word.
 // The 16-byte chunk index of a feature row is XOR-swizzled by (row >> 2) & 7 so that the rows of different 4-row blocks
 // fall into different banks (rows of one block are read by lanes that share them: broadcasts).
 __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src) {
@@ -173,28 +217,38 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__global__ void __launch_bounds__(256) nsm_power_kernel(const float* __restrict__ normed, const float* __restrict__ src,
-                                                        const float* __restrict__ tgt, const int32_t* __restrict__ knn_idx,
-                                                        float* __restrict__ iterates, uint32_t* __restrict__ conv_mask,
-                                                        float* __restrict__ compat_out, int N, int S, int k, int iters,
-                                                        float sigma2, float sigmad2, int mask_stride, int warps_per_cta,
-                                                        int per_warp_floats) {
+template <int WPS>
+__device__ __forceinline__ void seed_group_sync() {
+  if (WPS == 1) __syncwarp();
+  else __syncthreads();        // WPS == 4: the CTA is exactly one seed group
+}
+
+template <int WPS>
+__global__ void __launch_bounds__(WPS == 1 ? 256 : 128) nsm_power_kernel(
+    const float* __restrict__ normed, const float* __restrict__ src, const float* __restrict__ tgt,
+    const int32_t* __restrict__ knn_idx, float* __restrict__ iterates, uint32_t* __restrict__ conv_mask,
+    float* __restrict__ compat_out, int N, int S, int k, int iters, float sigma2, float sigmad2, int mask_stride,
+    int groups_per_cta, int per_group_floats) {
   extern __shared__ __align__(16) float sm[];
+  constexpr int TS = 32 * WPS;             // threads per seed
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int group = (WPS == 1) ? warp : 0;
+  const int tg = (WPS == 1) ? lane : (int)threadIdx.x;      // thread index within the seed's group
   const int b = blockIdx.y;
-  const int s = blockIdx.x * warps_per_cta + warp;
-  if (s >= S) return;                      // whole warps leave: no block-level barrier below
+  const int s = blockIdx.x * groups_per_cta + group;
+  if (s >= S) return;                      // WPS == 1: whole warps leave (no block barrier below); WPS == 4: never true
   const int ms = k | 1;                    // odd row stride of M: conflict-free column reads
   const int kp = (k + 3) & ~3;
-  float* F = sm + (size_t)warp * per_warp_floats;   // [kp][32]  one channel quarter, chunk-swizzled
-  float* M = F + (size_t)kp * 32;                   // [k][ms]
-  float* pa = M + (size_t)k * ms;                   // [k][3]
-  float* pb = pa + k * 3;                           // [k][3]
-  float* v = pb + k * 3;                            // [k]
-  int* idx = reinterpret_cast<int*>(v + k);         // [k]
+  float* F = sm + (size_t)group * per_group_floats;   // [kp][32]  one channel quarter, chunk-swizzled
+  float* M = F + (size_t)kp * 32;                      // [k][ms]
+  float* pa = M + (size_t)k * ms;                      // [k][3]
+  float* pb = pa + k * 3;                              // [k][3]
+  float* v = pb + k * 3;                               // [k]
+  int* idx = reinterpret_cast<int*>(v + k);            // [k]
+  float* red = reinterpret_cast<float*>(idx + k);      // [8]: WPS == 4 cross-warp reductions
   const size_t seed_row = (size_t)b * S + s;
 
-  for (int a = lane; a < k; a += 32) {
+  for (int a = tg; a < k; a += TS) {
     int j = knn_idx[seed_row * k + a];
     j = min(max(j, 0), N - 1);
     idx[a] = j;
@@ -205,19 +259,19 @@ __global__ void __launch_bounds__(256) nsm_power_kernel(const float* __restrict_
     v[a] = 1.0f;
     M[a * ms + a] = 0.0f;  // total_knn_M[:, i, i] = 0  (PointDSC.py:278)
   }
-  __syncwarp();
+  seed_group_sync<WPS>();
 
-  // this lane's blocks (A <= Bk) of rounds 0, 1, ...: block t = lane + 32 * round in row-major upper-triangular order
+  // this thread's blocks (A <= Bk) of rounds 0, 1: block t = tg + TS * round in row-major upper-triangular order
   const int nb = kp >> 2;
   const int nblk = nb * (nb + 1) / 2;
-  constexpr int kMaxRounds = 2;            // 64 blocks per pass (k <= 40 in one pass); larger k repeats gather + Gram per group of 64 blocks
+  constexpr int kMaxRounds = 2;            // 2 TS blocks per pass (k <= 40 for one warp, k <= 88 for four); larger k repeats gather + Gram
   const uint32_t f_base = (uint32_t)__cvta_generic_to_shared(F);
-  for (int r0 = 0; r0 * 32 < nblk; r0 += kMaxRounds) {
+  for (int r0 = 0; r0 * TS < nblk; r0 += kMaxRounds) {
     int bA[kMaxRounds], bB[kMaxRounds];
     float acc[kMaxRounds][4][4];
 #pragma unroll
     for (int r = 0; r < kMaxRounds; ++r) {
-      const int t = lane + 32 * (r0 + r);
+      const int t = tg + TS * (r0 + r);
       int A = 0, rem = t < nblk ? t : 0;
       while (rem >= nb - A) { rem -= nb - A; ++A; }
       bA[r] = A; bB[r] = A + rem;
@@ -229,17 +283,17 @@ __global__ void __launch_bounds__(256) nsm_power_kernel(const float* __restrict_
 #pragma unroll 1
     for (int quarter = 0; quarter < 4; ++quarter) {
       // gather: eight lanes per row, 16-byte chunk q of channels [32 quarter, 32 quarter + 32)
-      const int q = lane & 7;
-      for (int a = lane >> 3; a < kp; a += 4) {
+      const int q = tg & 7;
+      for (int a = tg >> 3; a < kp; a += TS / 8) {
         const uint32_t dst = f_base + (uint32_t)((a * 32 + ((q ^ ((a >> 2) & 7)) << 2)) * 4);
         if (a < k) cp_async_16(dst, normed + ((size_t)b * N + idx[a]) * kC + quarter * 32 + q * 4);
         else *reinterpret_cast<float4*>(F + a * 32 + ((q ^ ((a >> 2) & 7)) << 2)) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       cp_async_wait_all();
-      __syncwarp();
+      seed_group_sync<WPS>();
 #pragma unroll
       for (int r = 0; r < kMaxRounds; ++r) {
-        if (lane + 32 * (r0 + r) < nblk) {
+        if (tg + TS * (r0 + r) < nblk) {
           const float* xa = F + (size_t)(4 * bA[r]) * 32;
           const float* yb = F + (size_t)(4 * bB[r]) * 32;
           const int sx = bA[r] & 7, sy = bB[r] & 7;      // (row >> 2) & 7 is the block index & 7
@@ -263,12 +317,12 @@ __global__ void __launch_bounds__(256) nsm_power_kernel(const float* __restrict_
           }
         }
       }
-      __syncwarp();          // everyone is done with this quarter before the next gather overwrites it
+      seed_group_sync<WPS>();          // everyone is done with this quarter before the next gather overwrites it
     }
     // compatibility of this group of blocks
 #pragma unroll
     for (int r = 0; r < kMaxRounds; ++r) {
-      if (lane + 32 * (r0 + r) < nblk) {
+      if (tg + TS * (r0 + r) < nblk) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -286,24 +340,22 @@ __global__ void __launch_bounds__(256) nsm_power_kernel(const float* __restrict_
       }
     }
   }
-  __syncwarp();
+  seed_group_sync<WPS>();
   if (compat_out) {
     float* dst = compat_out + seed_row * k * k;
-    for (int t = lane; t < k * k; t += 32) dst[t] = M[(t / k) * ms + (t % k)];
+    for (int t = tg; t < k * k; t += TS) dst[t] = M[(t / k) * ms + (t % k)];
   }
 
   // power iteration from the all-ones vector; record every iterate and a convergence bit per iteration.
-  // Lane = (row group rg = lane >> 2, column quarter cq = lane & 3): it owns rows rg + 8 i and the columns of quarter cq, so
-  // the k x k matrix-vector product is spread over all 32 lanes (k = 40: 50 MACs per lane and iteration, the matrix slice
-  // held in registers for all iterations; the round-1 kernel ran a 40-step dependent chain per row with two shared-memory
-  // loads per MAC).  A row's four partial sums (ascending column order within a quarter) are combined by an xor butterfly,
-  // (q0 + q1) + (q2 + q3), the squared norm by a butterfly over the row groups: fixed orders, identical on every lane.
+  // Thread = (row group rg = tg >> 2, column quarter cq = tg & 3): rows rg + (TS / 4) i, the columns of quarter cq.
   uint32_t mask = 0u;
   float* it_out = iterates + seed_row * (size_t)iters * k;
-  const int rg = lane >> 2, cq = lane & 3;
+  constexpr int RG = TS / 4;                         // row groups: 8 (one warp) or 32 (four warps)
+  const int rg = tg >> 2, cq = tg & 3;
   const int CQ = (k + 3) >> 2;                       // columns per quarter
   const int c_lo = cq * CQ, c_hi = min(k, c_lo + CQ);
-  if (k <= 40) {
+  if (WPS == 1 && k <= 40) {
+    // k = 40: 50 MACs per lane and iteration, the matrix slice held in registers for all iterations
     constexpr int RI = 5, CW = 10;
     float m[RI][CW], vq[CW], vrow[RI];
 #pragma unroll
@@ -351,7 +403,8 @@ __global__ void __launch_bounds__(256) nsm_power_kernel(const float* __restrict_
       __syncwarp();
     }
   } else {
-    constexpr int RI = kMaxK / 8;
+    // general k: the matrix stays in shared memory, rows rg + RG i (i < RI)
+    constexpr int RI = kMaxK / RG;                   // 16 (one warp) or 4 (four warps)
     float vrow[RI];
 #pragma unroll
     for (int i = 0; i < RI; ++i) vrow[i] = 1.0f;
@@ -359,7 +412,7 @@ __global__ void __launch_bounds__(256) nsm_power_kernel(const float* __restrict_
       float u[RI], ss = 0.f;
 #pragma unroll
       for (int i = 0; i < RI; ++i) {
-        const int row = rg + 8 * i;
+        const int row = rg + RG * i;
         float p = 0.f;
         if (row < k) {
           const float* mr = M + (size_t)row * ms;
@@ -373,12 +426,17 @@ __global__ void __launch_bounds__(256) nsm_power_kernel(const float* __restrict_
       ss += __shfl_xor_sync(0xffffffffu, ss, 4);
       ss += __shfl_xor_sync(0xffffffffu, ss, 8);
       ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+      if (WPS > 1) {                                 // the four warps' sums, added in ascending warp order on every thread
+        if (lane == 0) red[warp] = ss;
+        __syncthreads();
+        ss = ((red[0] + red[1]) + red[2]) + red[3];
+      }
       const float nrm = sqrtf(ss) + 1e-6f;
       bool ok = true;
-      __syncwarp();                      // every lane has read the old v
+      seed_group_sync<WPS>();                        // every thread has read the old v (and red)
 #pragma unroll
       for (int i = 0; i < RI; ++i) {
-        const int row = rg + 8 * i;
+        const int row = rg + RG * i;
         const float vn = u[i] / nrm;
         ok = ok && (row >= k || fabsf(vn - vrow[i]) <= 1e-8f + 1e-5f * fabsf(vrow[i]));
         vrow[i] = vn;
@@ -387,13 +445,20 @@ __global__ void __launch_bounds__(256) nsm_power_kernel(const float* __restrict_
           it_out[(size_t)t * k + row] = vn;
         }
       }
-      if (__all_sync(0xffffffffu, ok)) mask |= (1u << t);
-      __syncwarp();
+      bool all_ok = __all_sync(0xffffffffu, ok);
+      if (WPS > 1) {
+        if (lane == 0) red[4 + warp] = all_ok ? 1.f : 0.f;
+        __syncthreads();
+        all_ok = (red[4] + red[5] + red[6] + red[7]) == 4.f;
+      } else {
+        __syncwarp();
+      }
+      if (all_ok) mask |= (1u << t);
     }
   }
   // testing mode: the early exit is a per-set decision (mask_stride 1); non-testing mode: the reference's allclose spans
   // the whole [bs * S, k] batch (PointDSC.py:354), so every set ANDs into word 0 (mask_stride 0)
-  if (lane == 0) atomicAnd(conv_mask + (size_t)b * mask_stride, mask);
+  if (tg == 0) atomicAnd(conv_mask + (size_t)b * mask_stride, mask);
 }
 
 void launch_nsm_power(const float* normed, const float* src, const float* tgt, const int32_t* knn_idx, float* iterates,
@@ -402,17 +467,25 @@ void launch_nsm_power(const float* normed, const float* src, const float* tgt, c
   if (S <= 0) return;
   const int ms = k | 1;
   const int kp = (k + 3) & ~3;
-  int per_warp_floats = kp * 32 + k * ms + 6 * k + k + k;     // F quarter, M, pa, pb, v, idx
-  per_warp_floats = (per_warp_floats + 3) & ~3;               // keep every warp's slice 16-byte aligned
-  // two CTAs per SM (about 110 KB each) so that a CTA's launch / drain overlaps the other's work
-  int warps = (int)((110 * 1024) / ((size_t)per_warp_floats * sizeof(float)));
-  warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
-  const int smem = warps * per_warp_floats * (int)sizeof(float);
-  ensure_dynamic_smem(reinterpret_cast<const void*>(nsm_power_kernel), smem);
-  nsm_power_kernel<<<dim3((S + warps - 1) / warps, B), warps * 32, smem, st>>>(normed, src, tgt, knn_idx, iterates, conv_mask,
-                                                                              compat_out, N, S, k, iters, sigma * sigma,
-                                                                              sigma_d * sigma_d, mask_stride, warps,
-                                                                              per_warp_floats);
+  int per_group_floats = kp * 32 + k * ms + 6 * k + k + k + 8;     // F quarter, M, pa, pb, v, idx, red
+  per_group_floats = (per_group_floats + 3) & ~3;                  // keep every group's slice 16-byte aligned
+  const size_t group_bytes = (size_t)per_group_floats * sizeof(float);
+  if (k <= 40) {
+    // one warp per seed, two CTAs per SM (about 110 KB each) so that a CTA's launch / drain overlaps the other's work
+    int warps = (int)((110 * 1024) / group_bytes);
+    warps = warps > 8 ? 8 : (warps < 1 ? 1 : warps);
+    const int smem = warps * (int)group_bytes;
+    ensure_dynamic_smem(reinterpret_cast<const void*>(nsm_power_kernel<1>), smem);
+    nsm_power_kernel<1><<<dim3((S + warps - 1) / warps, B), warps * 32, smem, st>>>(
+        normed, src, tgt, knn_idx, iterates, conv_mask, compat_out, N, S, k, iters, sigma * sigma, sigma_d * sigma_d, mask_stride,
+        warps, per_group_floats);
+  } else {
+    // four warps per seed, one seed per CTA
+    const int smem = (int)group_bytes;
+    ensure_dynamic_smem(reinterpret_cast<const void*>(nsm_power_kernel<4>), smem);
+    nsm_power_kernel<4><<<dim3(S, B), 128, smem, st>>>(normed, src, tgt, knn_idx, iterates, conv_mask, compat_out, N, S, k, iters,
+                                                        sigma * sigma, sigma_d * sigma_d, mask_stride, 1, per_group_floats);
+  }
 }
 
 }  // namespace pdsc
