@@ -26,7 +26,7 @@ constexpr int kKnnSmem = kKnnBars + 256;
 
 __global__ void __launch_bounds__(kKnnThreads, 1) knn_dist_tc_kernel(const float* __restrict__ normed,
                                                                      const int32_t* __restrict__ seeds,
-                                                                     float* __restrict__ dist, int N, int S) {
+                                                                     float* __restrict__ dist, int N, int S, int tiles_per_cta) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kKnnBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
@@ -36,7 +36,9 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_dist_tc_kernel(const float
   const uint32_t d_full = smem_u32(bars + 5), d_free = smem_u32(bars + 7);    // [2]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, s_base = blockIdx.x * 128;
-  const int T = (N + 63) / 64;
+  // key tiles [t0, t0 + T) of this CTA: blockIdx.z splits the keys when seed-row tiles x sets alone would leave SMs idle
+  const int t0 = blockIdx.z * tiles_per_cta;
+  const int T = min(tiles_per_cta, (N + 63) / 64 - t0);
   constexpr int FMT = kFmtF16;
 
   if (tid == 0) {
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_dist_tc_kernel(const float
       float4 v[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const int key = t * 64 + lw * 16 + i;
+        const int key = (t0 + t) * 64 + lw * 16 + i;
         v[i] = (key < N) ? __ldg(reinterpret_cast<const float4*>(rows + (size_t)key * kC) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (use > 0) mbar_wait(b_free + 8 * st, (uint32_t)((use - 1) & 1));
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_dist_tc_kernel(const float
         uint32_t raw[32];
         tmem_ld32(tmem + lane_base + 64 * st + 32 * hcol, raw);
         tmem_ld_wait();
-        const int j0 = t * 64 + 32 * hcol;
+        const int j0 = (t0 + t) * 64 + 32 * hcol;
         if (live) {
           if (vec_ok && j0 + 32 <= N) {
 #pragma unroll
@@ -188,7 +190,12 @@ __global__ void __launch_bounds__(kKnnThreads, 1) knn_dist_tc_kernel(const float
 void launch_knn_dist_tc(const float* normed, const int32_t* seeds, float* dist, int B, int N, int S, cudaStream_t st) {
   if (S <= 0) return;
   ensure_dynamic_smem(reinterpret_cast<const void*>(knn_dist_tc_kernel), kKnnSmem);
-  knn_dist_tc_kernel<<<dim3((S + 127) / 128, B), kKnnThreads, kKnnSmem, st>>>(normed, seeds, dist, N, S);
+  const int T = (N + 63) / 64, ctas = ((S + 127) / 128) * B, sms = device_sm_count();
+  int chunks = ctas >= sms ? 1 : (sms + ctas - 1) / ctas;
+  if (chunks > T) chunks = T;
+  const int per = (T + chunks - 1) / chunks;
+  chunks = (T + per - 1) / per;
+  knn_dist_tc_kernel<<<dim3((S + 127) / 128, B, chunks), kKnnThreads, kKnnSmem, st>>>(normed, seeds, dist, N, S, per);
 }
 
 }  // namespace pdsc

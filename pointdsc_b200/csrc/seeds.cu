@@ -21,8 +21,8 @@ constexpr int kSeedMaxN = 16384;
 // `d2_min` is the smallest fp32 squared length whose correctly rounded square root is >= R (found on the host by
 // stepping floats around R^2): sqrt is monotonic, so  length3(d) >= R  <=>  fma-chain(d) >= d2_min  exactly,
 // and the kernel needs no square root at all.
-constexpr int kNmsTile = 256;
-
+// TILE rows per CTA: 256 for big batches; 32 when the whole call is a handful of CTAs (bs = 1 at N = 1000 was 4 CTAs and 60 us)
+template <int kNmsTile>
 __global__ void __launch_bounds__(kNmsTile) nms_key_kernel(const float* __restrict__ src, const float* __restrict__ conf,
                                                            float* __restrict__ key, int N, float d2_min) {
   __shared__ float4 pts[kNmsTile];
@@ -110,8 +110,10 @@ void launch_pick_seeds(const float* src, const float* conf, int32_t* seeds, floa
   float d2_min = radius * radius;
   while (std::sqrt(d2_min) >= radius && d2_min > 0.f) d2_min = std::nextafter(d2_min, 0.0f);
   while (std::sqrt(d2_min) < radius) d2_min = std::nextafter(d2_min, INFINITY);
-  dim3 g1((N + kNmsTile - 1) / kNmsTile, B);
-  nms_key_kernel<<<g1, kNmsTile, 0, st>>>(src, conf, key_scratch, N, d2_min);
+  if ((long long)B * ((N + 255) / 256) >= 2LL * device_sm_count())
+    nms_key_kernel<256><<<dim3((N + 255) / 256, B), 256, 0, st>>>(src, conf, key_scratch, N, d2_min);
+  else
+    nms_key_kernel<32><<<dim3((N + 31) / 32, B), 32, 0, st>>>(src, conf, key_scratch, N, d2_min);
   launch_seed_sort(key_scratch, seeds, B, N, S, st);
 }
 
