@@ -114,11 +114,37 @@ void tc_free_weights(TcWeights* w) {
 static inline int q_tiles(int N) { return (N + 127) / 128; }
 static inline int k_tiles(int N) { return (N + 63) / 64; }
 
+// key split of the attention (small calls): at most this many work items, each with a 64 KB partial O and 1 KB of (m, l)
+constexpr int kAttnSplitMaxItems = 320;
+constexpr size_t kAttnSplitBytes = (size_t)kAttnSplitMaxItems * (65536 + 1024);
+
 size_t tc_scratch_bytes(int B, int N) {
-  return ((size_t)B * q_tiles(N) + (size_t)B * k_tiles(N)) * 65536 + 1024;
+  return ((size_t)B * q_tiles(N) + (size_t)B * k_tiles(N)) * 65536 + 1024 + kAttnSplitBytes;
 }
 
-int tc_launches(int num_layers) { return 2 + 4 * num_layers; }  // layer0 + pad clear + 4 per layer
+// Key split policy.  When a call's (set, query tile) items cover less than half of the SMs (the evaluation loops' bs = 1:
+// 8 items at N = 1000, 40 at N = 5000), every item is split along the keys into chunks of TS tiles, TS a function of N ONLY:
+// calls of the small regime therefore agree bit for bit whatever their batch size, and so do calls of the large regime
+// (no split); across the two regimes the softmax sums are associated differently (fp32 rounding, far inside the parity bar).
+static void attn_split_policy(int B, int N, int num_sms, int* splits, int* TS) {
+  const int QT = q_tiles(N), KT = k_tiles(N);
+  *splits = 1;
+  *TS = KT;
+  if (2 * B * QT > num_sms || KT < 4) return;
+  const int want = (num_sms + QT - 1) / QT;          // splits that would fill the SMs with ONE set
+  int ts = (KT + want - 1) / want;
+  if (ts < 2) ts = 2;
+  const int sp = (KT + ts - 1) / ts;
+  if (sp < 2 || B * QT * sp > kAttnSplitMaxItems) return;
+  *splits = sp;
+  *TS = ts;
+}
+
+int tc_launches(int num_layers, int B, int N) {   // layer0 + pad clear + 4 per layer (+ the merge of a key-split attention)
+  int splits, ts;
+  attn_split_policy(B, N, device_sm_count(), &splits, &ts);
+  return 2 + (splits > 1 ? 5 : 4) * num_layers;
+}
 
 // ---- zero the never-written pad rows/columns of the last key tile of every set ---------------------------
 __global__ void tc_clear_pads_kernel(uint8_t* kvimg, int N, int KT) {
@@ -177,6 +203,8 @@ static int tc_encoder_forward_fmt(const TcWeights& w, const TcForwardArgs& a, cu
   uint8_t* qimg = static_cast<uint8_t*>(a.scratch);
   qimg = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(qimg) + 1023) & ~uintptr_t(1023));
   uint8_t* kvimg = qimg + (size_t)a.B * QT * 65536;
+  float* part_o = reinterpret_cast<float*>(kvimg + (size_t)a.B * KT * 65536);
+  float* part_ml = part_o + (size_t)kAttnSplitMaxItems * 128 * kC;
   const long long tiles = (rows + 127) / 128;
   const int num_sms = device_sm_count();
   if (num_sms <= 0) return (int)cudaErrorInvalidDevice;
@@ -198,12 +226,15 @@ static int tc_encoder_forward_fmt(const TcWeights& w, const TcForwardArgs& a, cu
     c.in = a.feat1; c.out_f32 = nullptr; c.wimg = base + kWk; c.wbytes = 131072; c.dbg = nullptr;
     tc_chain_kernel<kKV, FMT><<<grid, kChainThreads, kChainSmem, st>>>(c);
     // attention
+    int splits, ts;
+    attn_split_policy(a.B, a.N, num_sms, &splits, &ts);
     AttnArgs at{a.N, a.NS, QT, KT, a.split, qimg, kvimg, a.sc, a.msg,
-                (a.timeline && a.debug_layer == l) ? a.timeline + 512 : nullptr, a.B * QT};
+                (a.timeline && a.debug_layer == l) ? a.timeline + 512 : nullptr, a.B * QT * splits, splits, ts, part_o, part_ml};
     if (a.attn_events) cudaEventRecord(a.attn_events[2 * l], st);
     {
-      const int items = a.B * QT;
+      const int items = at.items;
       tc_attention_persistent_kernel<FMT><<<items < num_sms ? items : num_sms, kAttnThreads, kAttnPSmem, st>>>(at);
+      if (splits > 1) tc_attention_merge_kernel<<<a.B * QT * 4, 256, 0, st>>>(part_o, part_ml, a.msg, a.N, QT, splits);
     }
     if (a.attn_events) cudaEventRecord(a.attn_events[2 * l + 1], st);
     if (a.debug_out && a.debug_layer == l) {

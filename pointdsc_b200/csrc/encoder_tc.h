@@ -40,7 +40,7 @@ struct TcForwardArgs {
 int tc_build_weights(const TcLayerHost* layers, int num_layers, TcWeights* out);  // returns cudaError_t
 void tc_free_weights(TcWeights* w);
 size_t tc_scratch_bytes(int B, int N);
-int tc_launches(int num_layers);
+int tc_launches(int num_layers, int B, int N);
 int tc_encoder_forward(const TcWeights& w, const TcForwardArgs& a, cudaStream_t st);  // returns cudaError_t
 
 }  // namespace pdsc

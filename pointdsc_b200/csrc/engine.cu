@@ -408,7 +408,7 @@ size_t pdsc_workspace_bytes(const pdsc_engine* e, int32_t B, int32_t N) {
 int32_t pdsc_launches_per_forward(const pdsc_engine* e, int32_t B, int32_t N) {
   if (!e) return 0;
   const int L = e->cfg.num_layers;
-  const int enc = (e->cfg.precision == PDSC_FP32_SIMT) ? (1 + 8 * L) : pdsc::tc_launches(L);
+  const int enc = (e->cfg.precision == PDSC_FP32_SIMT) ? (1 + 8 * L) : pdsc::tc_launches(L, B, N);
   // sc, encoder, head, nms, sort, (gather +) dist gemm, knn select, 2 fills, nsm, hypotheses, refine
   return 1 + enc + 1 + 2 + ((e->cfg.precision == PDSC_FP32_SIMT) ? 3 : 2) + 2 + 3;
 }

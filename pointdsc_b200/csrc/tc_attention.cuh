@@ -19,7 +19,12 @@ struct AttnArgs {
   const float* sc;    // tiled: [B][KT][QT][16 key groups][128 queries][4 keys]
   float* msg;
   long long* dbg;
-  int items;          // B * QT work items (persistent kernel)
+  int items;          // work items of the launch: B * QT * splits
+  // key split (small calls only, see encoder_tc.cu): a work item is (set, query tile, split) and covers key tiles
+  // [split * TS, split * TS + TS); tiles beyond KT are "virtual" (fully masked).  splits == 1: TS == KT, one item per query tile.
+  int splits, TS;
+  float* part_o;      // [items][128][128] unnormalised O of every work item           (splits > 1)
+  float* part_ml;     // [items][128][2]   its final reference maximum (log2 units) and row sum
 };
 
 constexpr int kAttnThreads = 320;

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
   const uint32_t stage_free = smem_u32(bars + 31);   // the item's output has left the staging buffer
   const uint32_t qk_done = smem_u32(bars + 32);      // the item's last QK has completed: the Q columns are free
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int T = a.KT;
+  const int T = a.TS;                                          // key tiles per work item (== a.KT unless the keys are split)
   const int TE = (T + 1) >> 1, TO = T >> 1;                   // tiles per item with even / odd index
   const int my_items = (a.items > (int)blockIdx.x) ? (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -100,8 +100,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
         bool progress = false;
         if (ki < my_items) {
           if (kuse == 0 || mbar_test(k_empty + 8 * kst, (uint32_t)((kuse - 1) & 1))) {
-            const int item = blockIdx.x + ki * gridDim.x;
-            const uint8_t* kv = a.kvimg + ((size_t)(item / a.QT) * a.KT + kj) * 65536;
+            const int witem = blockIdx.x + ki * gridDim.x;
+            const int item = witem / a.splits;                                       // (set, query tile)
+            const int kt = min((witem % a.splits) * T + kj, a.KT - 1);               // a virtual tile re-reads the last real one (it is masked)
+            const uint8_t* kv = a.kvimg + ((size_t)(item / a.QT) * a.KT + kt) * 65536;
             mbar_expect_tx(k_full + 8 * kst, tile_bytes);
             bulk_g2s(s0 + kAttnPK + kst * 32768, kv, tile_bytes, k_full + 8 * kst);
             if (++kst == kAttnRing) { kst = 0; ++kuse; }
@@ -111,8 +113,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
         }
         if (vi < my_items) {
           if (vuse == 0 || mbar_test(v_empty + 8 * vst, (uint32_t)((vuse - 1) & 1))) {
-            const int item = blockIdx.x + vi * gridDim.x;
-            const uint8_t* kv = a.kvimg + ((size_t)(item / a.QT) * a.KT + vj) * 65536 + 32768;
+            const int witem = blockIdx.x + vi * gridDim.x;
+            const int item = witem / a.splits;
+            const int kt = min((witem % a.splits) * T + vj, a.KT - 1);
+            const uint8_t* kv = a.kvimg + ((size_t)(item / a.QT) * a.KT + kt) * 65536 + 32768;
             mbar_expect_tx(v_full + 8 * vst, tile_bytes);
             bulk_g2s(s0 + kAttnPV + vst * 32768, kv, tile_bytes, v_full + 8 * vst);
             if (++vst == kAttnRing) { vst = 0; ++vuse; }
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
                                             (qi < 2 || mbar_test(stage_free, (uint32_t)((qi - 2) & 1))));
           else free = mbar_test(qh_used, (uint32_t)(qi & 1));
           if (free) {
-            const int item = blockIdx.x + qi * gridDim.x;
+            const int item = (blockIdx.x + qi * gridDim.x) / a.splits;
             const uint8_t* qsrc = a.qimg + (size_t)item * 65536 + qh * 32768;
             const uint32_t bar = qh ? ql_full : qh_full;
             mbar_expect_tx(bar, 32768u);
@@ -211,7 +215,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
     const int gt = (warp - 2 - 4 * g) * 32 + lane;   // thread index within the group
     const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
     const size_t tile_stride = (size_t)a.QT << 13;
-    const bool ragged = (a.N & 63) != 0;
     const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && gt == 0;
 
     // move one half of the staged Q image (this thread's row) into tensor memory: hi by group 0, lo by group 1
@@ -237,27 +240,30 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
     };
 
     float sc[64];
-    auto load_sc = [&](int item, int j) {   // this thread's 64 SC values of key tile j: 16 coalesced float4 loads
-      load_sc_tile(sc, a.sc + ((((size_t)(item / a.QT) * a.KT) * a.QT + (item % a.QT)) << 13) + (size_t)j * tile_stride, r);
+    auto load_sc = [&](int witem, int j) {   // this thread's 64 SC values of tile j of work item `witem`: 16 coalesced float4 loads
+      const int item = witem / a.splits;
+      const int kt = min((witem % a.splits) * T + j, a.KT - 1);
+      load_sc_tile(sc, a.sc + ((((size_t)(item / a.QT) * a.KT) * a.QT + (item % a.QT)) << 13) + (size_t)kt * tile_stride, r);
     };
     if (my_items > 0) {
       if (g < T) load_sc(blockIdx.x, g);
       convert_q(0);
     }
     for (int it = 0; it < my_items; ++it) {
-      const int item = blockIdx.x + it * gridDim.x;
+      const int witem = blockIdx.x + it * gridDim.x;
+      const int item = witem / a.splits, t0 = (witem % a.splits) * T;   // (set, query tile) and the split's first key tile
       const int b = item / a.QT, qt = item % a.QT;
       const int gvb = it * T;   // the CTA's running tile count at the item's first tile
       const float* sc_cta = a.sc + ((((size_t)b * a.KT) * a.QT + qt) << 13);
       const float* sc_line = sc_cta + gt * 32;   // two 128-byte lines of each 32 KB tile per thread (L2 prefetch)
       float my_ref = -INFINITY, l_sum = 0.f;
       if (stamp) PDSC_STAMP1(a.dbg, it, 1 + g, 0);
-      if (g + 2 < T) { prefetch_l2(sc_line + (size_t)(g + 2) * tile_stride); prefetch_l2(sc_line + (size_t)(g + 2) * tile_stride + 4096); }
+      if (g + 2 < T && t0 + g + 2 < a.KT) { prefetch_l2(sc_line + (size_t)(t0 + g + 2) * tile_stride); prefetch_l2(sc_line + (size_t)(t0 + g + 2) * tile_stride + 4096); }
       for (int j = g; j < T; j += 2) {
         const int tn = gvb + j;   // running tile count
         const int buf = tn & 3;
         const uint32_t tS = tmem + 64 * buf + lane_base;
-        if (j + 4 < T) { prefetch_l2(sc_line + (size_t)(j + 4) * tile_stride); prefetch_l2(sc_line + (size_t)(j + 4) * tile_stride + 4096); }
+        if (j + 4 < T && t0 + j + 4 < a.KT) { prefetch_l2(sc_line + (size_t)(t0 + j + 4) * tile_stride); prefetch_l2(sc_line + (size_t)(t0 + j + 4) * tile_stride + 4096); }
         mbar_wait(s_full + 8 * buf, (uint32_t)((tn >> 2) & 1));
         tc_fence_after();
         float l[64];
@@ -272,13 +278,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
 #pragma unroll
           for (int c = 0; c < 32; ++c) l[32 + c] = __uint_as_float(raw[c]) * sc[32 + c];
         }
-        if (ragged && j == T - 1) {
+        if ((t0 + j) * 64 + 63 >= a.N) {     // the set's last, ragged key tile - or a virtual tile behind it (all masked)
 #pragma unroll
-          for (int c = 0; c < 64; ++c) l[c] = (j * 64 + c < a.N) ? l[c] : -INFINITY;
+          for (int c = 0; c < 64; ++c) l[c] = ((t0 + j) * 64 + c < a.N) ? l[c] : -INFINITY;
         }
         // the SC registers are dead: refill them with this group's next tile (of this item or of the next one)
-        if (j + 2 < T) load_sc(item, j + 2);
-        else if (it + 1 < my_items && g < T) load_sc(item + gridDim.x, g);
+        if (j + 2 < T) load_sc(witem, j + 2);
+        else if (it + 1 < my_items && g < T) load_sc(witem + gridDim.x, g);
         float tmax = l[0];
 #pragma unroll
         for (int c = 1; c < 64; ++c) tmax = fmaxf(tmax, l[c]);
@@ -352,7 +358,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
       if (it + 1 < my_items) {
         mbar_wait(qk_done, (uint32_t)(it & 1));   // the item's last QK has completed: the Q columns are free
         tc_fence_after();
-        if (g >= T) load_sc(item + gridDim.x, g);   // (never true for T >= 2; keeps a one-tile item correct)
+        if (g >= T) load_sc(witem + gridDim.x, g);   // (never true for T >= 2; keeps a one-tile item correct)
         convert_q(it + 1);
       }
       if (stamp) PDSC_STAMP1(a.dbg, it, 1 + g, 3);
@@ -369,7 +375,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
       }
       softmax_all_sync();
       if (stamp) PDSC_STAMP1(a.dbg, it, 1 + g, 5);
-      const float inv_l = 1.0f / (lsum_s[r] + lsum_s[128 + r]);
+      // one query tile per item: msg = O / l.  Key split: the item's UNNORMALISED O, its reference maximum and its row sum go
+      // to the partial buffers; tc_attention_merge_kernel combines the splits of a query tile in ascending split order.
+      const bool partial = a.splits > 1;
+      const float l_tot = lsum_s[r] + lsum_s[128 + r];
+      const float inv_l = partial ? 1.0f : 1.0f / l_tot;
+      if (partial && g == 0) {
+        const int jlp = T - 1;
+        *reinterpret_cast<float2*>(a.part_ml + ((size_t)witem * 128 + r) * 2) = make_float2(ref_s[(jlp & 1) * 128 + r], l_tot);
+      }
       // group g drains columns [64 g, 64 g + 64) of every row, 32 columns at a time, through its 16 KB half of the Q
       // staging buffer ([128 rows][128 B], 16-byte chunks XOR-swizzled by row) so that every store instruction writes
       // four full 128-byte lines.  The buffer is free here: both halves of the next Q have already gone through it.
@@ -380,7 +394,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
         if (!a.split && g == 1) mbar_wait(qh_used, (uint32_t)((it + 1) & 1));
       }
       uint8_t* ost = smem + kAttnPQ + g * 16384;
-      float* dst = a.msg + ((size_t)b * a.N + qt * 128) * kC + 64 * g;
+      float* dst = partial ? a.part_o + (size_t)witem * (128 * kC) + 64 * g : a.msg + ((size_t)b * a.N + qt * 128) * kC + 64 * g;
       const int rsub = gt >> 3, piece = gt & 7;   // read-out: rows rsub + 16 i, 16-byte piece of the 128-byte segment
 #pragma unroll
       for (int sr = 0; sr < 2; ++sr) {
@@ -401,7 +415,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
         for (int i = 0; i < 8; ++i) {
           const int rr = rsub + 16 * i;
           const float4 val = *reinterpret_cast<const float4*>(ost + rr * 128 + ((piece ^ (rr & 7)) << 4));
-          if (qt * 128 + rr < a.N) *reinterpret_cast<float4*>(dst + (size_t)rr * kC + 32 * sr + piece * 4) = val;
+          if (partial || qt * 128 + rr < a.N) *reinterpret_cast<float4*>(dst + (size_t)rr * kC + 32 * sr + piece * 4) = val;
         }
         group_sync(g);
       }
@@ -425,6 +439,41 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
       a.dbg[(15 * 4 + 1) * 8 + 1] = dt;
     }
   }
+}
+
+// ---- key split: combine the partial results of one query tile -------------------------------------------------------------
+// msg_i = sum_s O_s[i] 2^(m_s - m*) / sum_s l_s 2^(m_s - m*),  m* = max_s m_s, splits added in ascending order (deterministic).
+// One CTA per (query tile, 32-row quarter), thread = (row, 16-byte column piece stride).
+__global__ void __launch_bounds__(256) tc_attention_merge_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
+                                                                 float* __restrict__ msg, int N, int QT, int splits) {
+  const int item = blockIdx.x >> 2, quarter = blockIdx.x & 3;
+  const int b = item / QT, qt = item % QT;
+  const int row = quarter * 32 + (threadIdx.x >> 3);
+  if (qt * 128 + row >= N) return;
+  float mstar = -INFINITY;
+  for (int s = 0; s < splits; ++s) mstar = fmaxf(mstar, part_ml[(((size_t)item * splits + s) * 128 + row) * 2]);
+  float L = 0.f;
+  float4 acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const size_t w = (size_t)item * splits + s;
+    const float2 ml = *reinterpret_cast<const float2*>(part_ml + (w * 128 + row) * 2);
+    const float wgt = ex2_approx(ml.x - mstar);
+    L = fmaf(ml.y, wgt, L);
+    const float* o = part_o + (w * 128 + row) * kC;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = *reinterpret_cast<const float4*>(o + ((threadIdx.x & 7) + 8 * i) * 4);
+      acc[i].x = fmaf(v.x, wgt, acc[i].x); acc[i].y = fmaf(v.y, wgt, acc[i].y);
+      acc[i].z = fmaf(v.z, wgt, acc[i].z); acc[i].w = fmaf(v.w, wgt, acc[i].w);
+    }
+  }
+  const float inv = 1.0f / L;
+  float* dst = msg + ((size_t)b * N + qt * 128 + row) * kC;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(dst + ((threadIdx.x & 7) + 8 * i) * 4) = make_float4(acc[i].x * inv, acc[i].y * inv, acc[i].z * inv, acc[i].w * inv);
 }
 
 }  // namespace pdsc
