@@ -29,7 +29,7 @@ constexpr int kChainThreads = 512;
 constexpr int kChLoaderWarps = 7, kChLoaderRows = 19;   // rows lw + 7 i, i < 19 (the last one only for lw < 2)
 constexpr int kChA = 0;                          // A image: [hi p0 16K][hi p1 16K][lo p0 16K][lo p1 16K]
 constexpr int kChW = 65536;                      // weight images (128 KB for PCQ / KV, 80 KB for MSG)
-constexpr int kChStage = 65536 + 131072;         // PCQ / KV: 8 x 2 KB store staging
+constexpr int kChStage = 65536 + 131072;         // PCQ / KV: 8 x 4 KB store staging (one 32-column chunk of 32 rows per warp)
 constexpr int kChRes = 65536 + 81920;            // MSG: 64 KB residual tile (also the fp32 store staging)
 constexpr int kChBias = kChStage + 32768;        // 256 floats: this mode's biases
 constexpr int kChBars = kChBias + 1024;
@@ -93,29 +93,66 @@ __device__ __forceinline__ void locate_row(int b0, int n0, int rr, int N, int& b
   }
 }
 
-// One warp stores 32 rows x 64 B (16 words per thread, thread = row `lane`) through its 2 KB staging buffer: 16-byte
-// chunk q of row r is parked at chunk q ^ ((r >> 1) & 3) of the row's 64-byte slot (conflict-free both ways); in the
-// read-out lane l takes piece (l & 3) of rows (l >> 2) + 8 i, i < 4, so each store instruction writes 8 rows x 64 B.
-// dst(i, piece) returns the global address of that 16-byte piece, or nullptr for a row that does not exist.
+// Global stores go through a 4 KB per-warp staging buffer so that every store instruction writes full segments.  Layout of a
+// 64-byte-per-row piece (32 rows x 64 B = 2 KB): 16-byte chunk q of row r is parked at chunk q ^ ((r >> 1) & 3) of the row's
+// 64-byte slot (conflict-free both ways); in the read-out lane l takes piece (l & 3) of rows (l >> 2) + 8 i, i < 4, so each store
+// instruction writes 8 rows x 64 B.
+// A whole 32-column fp32 chunk (32 words = 128 B per thread = row) in ONE shared-memory round trip — the round
+// trip (two __syncwarp, store -> load latency) was ~450 cycles of a ~1400-cycle epilogue chunk and was paid twice per chunk.
+// 16-byte chunk q of row r is parked at chunk q ^ (r & 7) of the row's 128-byte slot (4 KB per warp); in the read-out lane l
+// takes piece (l & 7) of rows (l >> 3) + 4 i, i < 8, so each store instruction writes four FULL 128-byte lines.
+// dst(i) returns the global address of the 128-byte segment of row (l >> 3) + 4 i, or nullptr.
 template <typename DstFn>
-__device__ __forceinline__ void stage_store64(uint8_t* stage, int lane, const uint32_t (&v)[16], DstFn dst) {
+__device__ __forceinline__ void stage_store128(uint8_t* stage, int lane, const uint32_t (&v)[32], DstFn dst) {
   __syncwarp();
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
-    *reinterpret_cast<uint4*>(stage + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) =
-        make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  for (int q = 0; q < 8; ++q)
+    *reinterpret_cast<uint4*>(stage + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  __syncwarp();
+  const int piece = lane & 7;
+  uint4 val[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = (lane >> 3) + 4 * i;
+    val[i] = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((piece ^ (rr & 7)) << 4));
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint8_t* p = static_cast<uint8_t*>(dst(i));
+    if (p) st_global_v4(p + piece * 16, val[i]);
+  }
+}
+
+// Two 64-byte pieces per row (the hi and the lo image of a 32-column chunk) in one round trip: the two halves of the warp's
+// 4 KB staging buffer, stage_store64's layout in each.
+template <typename DstFn0, typename DstFn1>
+__device__ __forceinline__ void stage_store64x2(uint8_t* stage, int lane, const uint32_t (&v0)[16], const uint32_t (&v1)[16], bool second,
+                                                DstFn0 dst0, DstFn1 dst1) {
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    *reinterpret_cast<uint4*>(stage + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = make_uint4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]);
+    if (second)
+      *reinterpret_cast<uint4*>(stage + 2048 + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = make_uint4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]);
+  }
   __syncwarp();
   const int piece = lane & 3;
+  uint4 a0[4], a1[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int rr = (lane >> 2) + 8 * i;
-    const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
-    void* p = dst(i, piece);
-#ifdef PDSC_EXP_NO_CHAIN_STORES      // timing experiment only (tools/build_variant.py): results are wrong
-    if (p && val.x == 0x7fc12345u) st_global_v4(p, val);
-#else
-    if (p) st_global_v4(p, val);
-#endif
+    const int off = rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4);
+    a0[i] = *reinterpret_cast<const uint4*>(stage + off);
+    if (second) a1[i] = *reinterpret_cast<const uint4*>(stage + 2048 + off);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    void* p0 = dst0(i, piece);
+    if (p0) st_global_v4(p0, a0[i]);
+    if (second) {
+      void* p1 = dst1(i, piece);
+      if (p1) st_global_v4(p1, a1[i]);
+    }
   }
 }
 
@@ -320,7 +357,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
     if (MODE == kPCQ || MODE == kKV) {
       const int q4 = warp & 3;
       const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
-      uint8_t* stage = smem + kChStage + warp * 2048;
+      uint8_t* stage = smem + kChStage + warp * 4096;
       const float* bvec = bias + 128;
       uint8_t* const img = (MODE == kPCQ) ? a.qimg : a.kvimg;
       const uint32_t panel_bytes = (MODE == kPCQ) ? 16384u : 8192u;
@@ -373,13 +410,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           }
           const uint32_t poff = base_off + (uint32_t)(c >> 1) * panel_bytes;
           const uint32_t m = (uint32_t)(c & 1);  // which 64-byte half of the 128-byte row
-          stage_store64(stage, lane, hi, [&](int i, int piece) -> void* {
-            return rok[i] ? img + roff[i] + poff + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
-          });
-          if (a.split)
-            stage_store64(stage, lane, lo, [&](int i, int piece) -> void* {
-              return rok[i] ? img + roff[i] + poff + lo_off + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
-            });
+          stage_store64x2(stage, lane, hi, lo, a.split != 0,
+              [&](int i, int piece) -> void* {
+                return rok[i] ? img + roff[i] + poff + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
+              },
+              [&](int i, int piece) -> void* {
+                return rok[i] ? img + roff[i] + poff + lo_off + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
+              });
         }
       }
     }
@@ -423,7 +460,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
     // =================================== group A: thread = row ===================================
     const int q4 = warp & 3;
     const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
-    uint8_t* stage = smem + kChStage + warp * 2048;          // PCQ / KV
+    uint8_t* stage = smem + kChStage + warp * 4096;          // PCQ / KV
     uint8_t* resq = smem + kChRes + q4 * 32 * 512;           // MSG: the 32 residual rows of this lane quarter
     const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
     int it = 0;
@@ -465,17 +502,11 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
             mbar_arrive(a1_par + 8 * par);
             if (stamp) PDSC_STAMP1(a.dbg, it, 2, 2);
           }
-          // fp32 rows -> HBM, 16 columns (64 B) at a time
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            uint32_t seg[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) seg[i] = xb[16 * hf + i];
-            stage_store64(stage, lane, seg, [&](int i, int piece) -> void* {
-              const long long g = row0 + (lane >> 2) + 8 * i;
-              return g < rows ? (void*)(a.out_f32 + g * kC + c0 + 16 * hf + piece * 4) : nullptr;
-            });
-          }
+          // fp32 rows -> HBM, the chunk's 32 columns (128 B per row) in one staging round trip
+          stage_store128(stage, lane, xb, [&](int i) -> void* {
+            const long long g = row0 + (lane >> 3) + 4 * i;
+            return g < rows ? (void*)(a.out_f32 + g * kC + c0) : nullptr;
+          });
         }
         if (stamp) PDSC_STAMP1(a.dbg, it, 2, 3);
       } else if (MODE == kKV) {
@@ -515,13 +546,13 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           }
           const uint32_t poff = (uint32_t)(c >> 1) * 8192u;
           const uint32_t m = (uint32_t)(c & 1);
-          stage_store64(stage, lane, hi, [&](int i, int piece) -> void* {
-            return rok[i] ? a.kvimg + roff[i] + poff + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
-          });
-          if (a.split)
-            stage_store64(stage, lane, lo, [&](int i, int piece) -> void* {
-              return rok[i] ? a.kvimg + roff[i] + poff + 16384u + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
-            });
+          stage_store64x2(stage, lane, hi, lo, a.split != 0,
+              [&](int i, int piece) -> void* {
+                return rok[i] ? a.kvimg + roff[i] + poff + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
+              },
+              [&](int i, int piece) -> void* {
+                return rok[i] ? a.kvimg + roff[i] + poff + 16384u + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
+              });
         }
       } else {
         // ---- MSG, last step: feat = feat1 + (D2 + bm2), through the residual tile in shared memory ----
