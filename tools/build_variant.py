@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Developer tool: build a VARIANT of the library next to the product build, for A/B runs inside one gpurun call.
 
-    python tools/build_variant.py strict -DPDSC_STRICT_TMEM_WAR=1      ->  tools/bin/lib_strict.so
-    POINTDSC_B200_LIB=$PWD/tools/bin/lib_strict.so python tools/determinism_probe.py
+    python tools/build_variant.py nostore -DPDSC_EXP_SOMETHING=1       ->  tools/bin/lib_nostore.so
+    POINTDSC_B200_LIB=$PWD/tools/bin/lib_nostore.so python tools/stage_profile.py 3dmatch 1000 256
+(timing experiments guarded by a macro are added to the sources for the duration of the experiment only; see profiles/README.md)
 
 The product build (__graft_entry__.build) is untouched; tools/bin/ is git-ignored but travels to the GPU box."""
 import os, subprocess, sys
