@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(WPS == 1 ? 256 : 128) nsm_power_kernel(
     const int32_t* __restrict__ knn_idx, float* __restrict__ iterates, uint32_t* __restrict__ conv_mask,
     float* __restrict__ compat_out, int N, int S, int k, int iters, float sigma2, float sigmad2, int mask_stride,
     int groups_per_cta, int per_group_floats) {
+  const float rc_sigma2 = 1.0f / sigma2, rc_sigmad2 = 1.0f / sigmad2;   // IEEE divisions (correctly rounded reciprocals)
   extern __shared__ __align__(16) float sm[];
   constexpr int TS = 32 * WPS;             // threads per seed
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -329,10 +330,10 @@ __global__ void __launch_bounds__(WPS == 1 ? 256 : 128) nsm_power_kernel(
           for (int j = 0; j < 4; ++j) {
             const int a = 4 * bA[r] + i, c = 4 * bB[r] + j;
             if (a < c && c < k) {
-              const float fm = fmaxf(__fsub_rn(1.0f, __fdiv_rn(__fsub_rn(1.0f, acc[r][i][j]), sigma2)), 0.0f);
+              const float fm = fmaxf(__fsub_rn(1.0f, div_by_const(__fsub_rn(1.0f, acc[r][i][j]), sigma2, rc_sigma2)), 0.0f);
               const float la = length3_pow(pa[a * 3] - pa[c * 3], pa[a * 3 + 1] - pa[c * 3 + 1], pa[a * 3 + 2] - pa[c * 3 + 2]);
               const float lb = length3_pow(pb[a * 3] - pb[c * 3], pb[a * 3 + 1] - pb[c * 3 + 1], pb[a * 3 + 2] - pb[c * 3 + 2]);
-              const float val = __fmul_rn(fm, consistency(__fsub_rn(la, lb), sigmad2));
+              const float val = __fmul_rn(fm, consistency_rc(__fsub_rn(la, lb), sigmad2, rc_sigmad2));
               M[a * ms + c] = val;
               M[c * ms + a] = val;
             }

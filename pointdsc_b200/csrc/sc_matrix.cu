@@ -69,7 +69,8 @@ void launch_sc_matrix(const float* src, const float* tgt, float* sc, int B, int 
 constexpr int kScTStride = 129;   // smem transpose tile [32 i][128 j], odd stride: conflict-free both ways
 
 __global__ void __launch_bounds__(256) sc_matrix_tiled_kernel(const float* __restrict__ src, const float* __restrict__ tgt,
-                                                              float* __restrict__ sc, int N, int KT, int QT, float s2) {
+                                                              float* __restrict__ sc, int N, int KT, int QT, float s2,
+                                                              float rc_s2) {
   __shared__ float4 is4[128], it4[128];   // the A range's points (x, y, z, -), read as broadcast 16-byte loads
   __shared__ float tr[32 * kScTStride];
   const int b = blockIdx.y;
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(256) sc_matrix_tiled_kernel(const float* __res
       const float4 p = is4[il0 + ii], q = it4[il0 + ii];
       const float ds = length3(p.x - sx, p.y - sy, p.z - sz);
       const float dt = length3(q.x - tx, q.y - ty, q.z - tz);
-      const float v = consistency(__fsub_rn(ds, dt), s2);
+      const float v = consistency_rc(__fsub_rn(ds, dt), s2, rc_s2);
       vals[ii] = (col_ok && ii < i_lim) ? v : 0.0f;
     }
     if (kt1 < KT) {
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(256) sc_matrix_tiled_kernel(const float* __res
 void launch_sc_matrix_tiled(const float* src, const float* tgt, float* sc, int B, int N, float sigma_d, cudaStream_t st) {
   const float s2 = sigma_d * sigma_d;
   const int KT = (N + 63) / 64, QT = (N + 127) / 128;
-  sc_matrix_tiled_kernel<<<dim3(QT * (QT + 1) / 2, B), 256, 0, st>>>(src, tgt, sc, N, KT, QT, s2);
+  sc_matrix_tiled_kernel<<<dim3(QT * (QT + 1) / 2, B), 256, 0, st>>>(src, tgt, sc, N, KT, QT, s2, 1.0f / s2);
 }
 
 // tiled -> dense [B][N][N] (stage tap only)
