@@ -184,6 +184,31 @@ int pdsc_match(pdsc_engine* e, int32_t Ns, int32_t Nt, int32_t D, const void* d_
                int32_t* d_corr, int32_t* d_count, float* d_corr_pos, float* d_out_src, float* d_out_tgt, void* d_scratch,
                size_t scratch_bytes, void* cuda_stream);
 
+/* f2: the descriptor front end, replacing the open3d 0.9 calls of misc/cal_fpfh.py:21-26 (and demo_registration.py:37-44):
+ *   pcd.voxel_down_sample(voxel)                                                -> pdsc_voxel_down_sample
+ *   pcd.estimate_normals(KDTreeSearchParamHybrid(radius = 2 voxel, max_nn = 30)) -> pdsc_estimate_normals
+ *   compute_fpfh_feature(pcd, KDTreeSearchParamHybrid(5 voxel, 100))             -> pdsc_compute_fpfh
+ *   o3d.io.read_point_cloud(path).points                                         -> pdsc_read_ply (host)
+ * open3d is not part of the reference tree: these follow its published algorithms (oracle/fpfh_oracle.py; PARITY UNPINNED).
+ * d_points [n,3] float32.  pdsc_voxel_down_sample writes the voxel means to d_out_points (room for [n,3]; rows in ascending
+ * (ix, iy, iz) voxel order) and their number to d_count[0]; read d_count after synchronising the stream.  Normals are float64
+ * [m,3] (largest-magnitude component positive; (0,0,1) below three neighbours), FPFH float64 [m,33] — the dtype pdsc_match
+ * takes with desc_is_fp64 = 1 — with normalise != 0 applying x / (||x|| + 1e-6) per row (demo_registration.py:43).
+ * d_status[0] is a bit mask written on the stream: 1 = more than 2^21 voxels along an axis or a non-finite coordinate,
+ * 2 = a neighbourhood holds more than 4096 points inside the radius (the search is brute force over the m key points and
+ * sized for down-sampled clouds).  Scratch: 8-byte aligned, *_scratch_bytes() bytes. */
+size_t pdsc_voxel_down_sample_scratch_bytes(int64_t n);
+int pdsc_voxel_down_sample(pdsc_engine* e, int64_t n, const float* d_points, double voxel_size, float* d_out_points,
+                           int32_t* d_count, int32_t* d_status, void* d_scratch, size_t scratch_bytes, void* cuda_stream);
+size_t pdsc_fpfh_scratch_bytes(int32_t m, int32_t max_nn);
+int pdsc_estimate_normals(pdsc_engine* e, int32_t m, const float* d_points, double radius, int32_t max_nn, double* d_normals,
+                          int32_t* d_status, void* d_scratch, size_t scratch_bytes, void* cuda_stream);
+int pdsc_compute_fpfh(pdsc_engine* e, int32_t m, const float* d_points, const double* d_normals, double radius, int32_t max_nn,
+                      int32_t normalise, double* d_fpfh, int32_t* d_status, void* d_scratch, size_t scratch_bytes, void* cuda_stream);
+/* Vertex positions of a PLY file (ascii or binary_little_endian; x, y, z float or double) into host memory as [n,3] float32.
+ * Call with points = NULL to learn *n_vertices, then with a buffer of `capacity` >= n vertices. */
+int pdsc_read_ply(const char* path, float* points, int64_t capacity, int64_t* n_vertices);
+
 /* f4: leading eigenvector of N x N compatibility matrices by power iteration, replacing cal_leading_eigenvector(M, 'power')
  * (models/PointDSC.py:338-358) in its N x N uses: the learned feature-similarity matrix of the non-testing forward (:170) and
  * the classical spectral-matching baseline (baseline_scripts/baseline_3DMatch.py:40-44, ten fixed iterations = early_exit 0).

@@ -3,9 +3,11 @@
 // and the C ABI declared in include/pointdsc_b200.h.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -679,6 +681,142 @@ int pdsc_leading_eigenvector(pdsc_engine* e, int32_t B, int32_t N, const float* 
   const int rc = pdsc::launch_leading_eigenvector(d_M, d_eigenvector, d_iterations_run, B, N, num_iterations, early_exit, d_scratch,
                                                   static_cast<cudaStream_t>(cuda_stream));
   if (rc) return fail(PDSC_ERR_CUDA, "power iteration launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  return PDSC_OK;
+}
+
+size_t pdsc_voxel_down_sample_scratch_bytes(int64_t n) { return n > 0 ? pdsc::voxel_scratch_bytes(n) : 0; }
+
+int pdsc_voxel_down_sample(pdsc_engine* e, int64_t n, const float* d_points, double voxel_size, float* d_out_points,
+                           int32_t* d_count, int32_t* d_status, void* d_scratch, size_t scratch_bytes, void* cuda_stream) {
+  if (!e) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine");
+  if (n <= 0 || n > (1ll << 30)) return fail(PDSC_ERR_SHAPE, "need 1 <= n <= 2^30 points (got %lld)", (long long)n);
+  if (!(voxel_size > 0.0)) return fail(PDSC_ERR_INVALID_ARGUMENT, "voxel_size must be positive (got %g)", voxel_size);
+  if (!d_points || !d_out_points || !d_count || !d_status) return fail(PDSC_ERR_INVALID_ARGUMENT, "pdsc_voxel_down_sample: null tensor pointer");
+  if (!d_scratch || scratch_bytes < pdsc::voxel_scratch_bytes(n) || reinterpret_cast<uintptr_t>(d_scratch) % 8)
+    return fail(PDSC_ERR_WORKSPACE, "pdsc_voxel_down_sample: scratch too small or not 8-byte aligned (%zu bytes given, %zu needed)",
+                scratch_bytes, pdsc::voxel_scratch_bytes(n));
+  DeviceGuard g(e->cfg.device);
+  pdsc::launch_voxel_down_sample(d_points, n, voxel_size, d_out_points, d_count, d_status, d_scratch, static_cast<cudaStream_t>(cuda_stream));
+  PDSC_CUDA(cudaGetLastError());
+  return PDSC_OK;
+}
+
+size_t pdsc_fpfh_scratch_bytes(int32_t m, int32_t max_nn) { return (m > 0 && max_nn > 0) ? pdsc::fpfh_scratch_bytes(m, max_nn) : 0; }
+
+static int check_search_args(const char* who, pdsc_engine* e, int32_t m, double radius, int32_t max_nn, const void* a, const void* b,
+                             const void* c, void* d_scratch, size_t scratch_bytes) {
+  if (!e) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine");
+  if (m <= 0) return fail(PDSC_ERR_SHAPE, "%s: need m >= 1 points (got %d)", who, m);
+  if (!(radius > 0.0)) return fail(PDSC_ERR_INVALID_ARGUMENT, "%s: radius must be positive (got %g)", who, radius);
+  if (max_nn < 1 || max_nn > 256) return fail(PDSC_ERR_UNSUPPORTED, "%s: max_nn %d outside [1, 256]", who, max_nn);
+  if (!a || !b || !c) return fail(PDSC_ERR_INVALID_ARGUMENT, "%s: null tensor pointer", who);
+  if (!d_scratch || scratch_bytes < pdsc::fpfh_scratch_bytes(m, max_nn) || reinterpret_cast<uintptr_t>(d_scratch) % 8)
+    return fail(PDSC_ERR_WORKSPACE, "%s: scratch too small or not 8-byte aligned (%zu bytes given, %zu needed)", who, scratch_bytes,
+                pdsc::fpfh_scratch_bytes(m, max_nn));
+  return PDSC_OK;
+}
+
+int pdsc_estimate_normals(pdsc_engine* e, int32_t m, const float* d_points, double radius, int32_t max_nn, double* d_normals,
+                          int32_t* d_status, void* d_scratch, size_t scratch_bytes, void* cuda_stream) {
+  const int bad = check_search_args("pdsc_estimate_normals", e, m, radius, max_nn, d_points, d_normals, d_status, d_scratch, scratch_bytes);
+  if (bad) return bad;
+  DeviceGuard g(e->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  PDSC_CUDA(cudaMemsetAsync(d_status, 0, 4, st));
+  const int rc = pdsc::launch_estimate_normals(d_points, m, radius, max_nn, d_normals, d_status, d_scratch, st);
+  if (rc) return fail(PDSC_ERR_CUDA, "normal estimation launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  return PDSC_OK;
+}
+
+int pdsc_compute_fpfh(pdsc_engine* e, int32_t m, const float* d_points, const double* d_normals, double radius, int32_t max_nn,
+                      int32_t normalise, double* d_fpfh, int32_t* d_status, void* d_scratch, size_t scratch_bytes, void* cuda_stream) {
+  const int bad = check_search_args("pdsc_compute_fpfh", e, m, radius, max_nn, d_points, d_fpfh, d_status, d_scratch, scratch_bytes);
+  if (bad) return bad;
+  if (!d_normals) return fail(PDSC_ERR_INVALID_ARGUMENT, "pdsc_compute_fpfh: null normals");
+  DeviceGuard g(e->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  PDSC_CUDA(cudaMemsetAsync(d_status, 0, 4, st));
+  const int rc = pdsc::launch_compute_fpfh(d_points, d_normals, m, radius, max_nn, normalise, d_fpfh, d_status, d_scratch, st);
+  if (rc) return fail(PDSC_ERR_CUDA, "FPFH launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+  return PDSC_OK;
+}
+
+// Host-side PLY vertex reader (ascii / binary_little_endian; x, y, z as float or double; other vertex properties skipped).
+int pdsc_read_ply(const char* path, float* points, int64_t capacity, int64_t* n_vertices) {
+  if (!path || !n_vertices) return fail(PDSC_ERR_INVALID_ARGUMENT, "pdsc_read_ply: null argument");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(PDSC_ERR_INVALID_ARGUMENT, "pdsc_read_ply: cannot open %s", path);
+  struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+  char line[512];
+  if (!fgets(line, sizeof line, f) || strncmp(line, "ply", 3) != 0) return fail(PDSC_ERR_INVALID_ARGUMENT, "%s is not a PLY file", path);
+  int format = -1;                    // 0 ascii, 1 binary little endian
+  long long n = -1;
+  bool in_vertex = false, vertex_first = true, seen_element = false;
+  struct Prop { int size; bool is_float; int axis; };
+  std::vector<Prop> props;
+  while (true) {
+    if (!fgets(line, sizeof line, f)) return fail(PDSC_ERR_INVALID_ARGUMENT, "%s: header ends before end_header", path);
+    char a[64] = {0}, b[64] = {0}, c[64] = {0};
+    const int got = sscanf(line, "%63s %63s %63s", a, b, c);
+    if (got < 1) continue;
+    if (!strcmp(a, "end_header")) break;
+    if (!strcmp(a, "format")) {
+      if (!strcmp(b, "ascii")) format = 0;
+      else if (!strcmp(b, "binary_little_endian")) format = 1;
+      else return fail(PDSC_ERR_UNSUPPORTED, "%s: PLY format %s is not supported", path, b);
+    } else if (!strcmp(a, "element")) {
+      in_vertex = !strcmp(b, "vertex");
+      if (in_vertex) { n = atoll(c); vertex_first = !seen_element; }
+      seen_element = true;
+    } else if (!strcmp(a, "property") && in_vertex) {
+      if (!strcmp(b, "list")) return fail(PDSC_ERR_UNSUPPORTED, "%s: list properties on vertices are not supported", path);
+      Prop p{0, false, -1};
+      if (!strcmp(b, "char") || !strcmp(b, "uchar") || !strcmp(b, "int8") || !strcmp(b, "uint8")) p.size = 1;
+      else if (!strcmp(b, "short") || !strcmp(b, "ushort") || !strcmp(b, "int16") || !strcmp(b, "uint16")) p.size = 2;
+      else if (!strcmp(b, "int") || !strcmp(b, "uint") || !strcmp(b, "int32") || !strcmp(b, "uint32")) p.size = 4;
+      else if (!strcmp(b, "float") || !strcmp(b, "float32")) { p.size = 4; p.is_float = true; }
+      else if (!strcmp(b, "double") || !strcmp(b, "float64")) { p.size = 8; p.is_float = true; }
+      else return fail(PDSC_ERR_UNSUPPORTED, "%s: unknown property type %s", path, b);
+      if (!strcmp(c, "x")) p.axis = 0; else if (!strcmp(c, "y")) p.axis = 1; else if (!strcmp(c, "z")) p.axis = 2;
+      if (p.axis >= 0 && !p.is_float) return fail(PDSC_ERR_UNSUPPORTED, "%s: integer coordinates are not supported", path);
+      props.push_back(p);
+    }
+  }
+  if (format < 0 || n < 0) return fail(PDSC_ERR_INVALID_ARGUMENT, "%s: no format / vertex element in the header", path);
+  if (!vertex_first) return fail(PDSC_ERR_UNSUPPORTED, "%s: the vertex element must come first", path);
+  int have = 0;
+  for (const Prop& p : props) if (p.axis >= 0) have |= 1 << p.axis;
+  if (have != 7) return fail(PDSC_ERR_INVALID_ARGUMENT, "%s: vertex properties x, y, z not all present", path);
+  *n_vertices = n;
+  if (!points) return PDSC_OK;                        // size query
+  if (capacity < n) return fail(PDSC_ERR_SHAPE, "pdsc_read_ply: buffer holds %lld vertices, the file has %lld", (long long)capacity, n);
+  if (format == 0) {
+    for (long long i = 0; i < n; ++i) {
+      for (const Prop& p : props) {
+        double v;
+        if (fscanf(f, "%lf", &v) != 1) return fail(PDSC_ERR_INVALID_ARGUMENT, "%s: truncated at vertex %lld", path, i);
+        if (p.axis >= 0) points[3 * i + p.axis] = (float)v;
+      }
+    }
+  } else {
+    size_t stride = 0;
+    for (const Prop& p : props) stride += (size_t)p.size;
+    std::vector<unsigned char> row(stride * 4096);
+    for (long long i0 = 0; i0 < n; i0 += 4096) {
+      const size_t rows = (size_t)std::min<long long>(4096, n - i0);
+      if (fread(row.data(), stride, rows, f) != rows) return fail(PDSC_ERR_INVALID_ARGUMENT, "%s: truncated at vertex %lld", path, i0);
+      for (size_t r = 0; r < rows; ++r) {
+        size_t off = r * stride;
+        for (const Prop& p : props) {
+          if (p.axis >= 0) {
+            if (p.size == 4) { float v; memcpy(&v, &row[off], 4); points[3 * (i0 + (long long)r) + p.axis] = v; }
+            else { double v; memcpy(&v, &row[off], 8); points[3 * (i0 + (long long)r) + p.axis] = (float)v; }
+          }
+          off += (size_t)p.size;
+        }
+      }
+    }
+  }
   return PDSC_OK;
 }
 

@@ -92,6 +92,16 @@ size_t eig_scratch_bytes(int B, int N);
 int launch_leading_eigenvector(const float* M, float* v, int* iters_run, int B, int N, int iters, int early_exit, void* scratch,
                                cudaStream_t st);   // returns cudaError_t
 
+// ---- f2: descriptor front end (fpfh.cu): voxel down-sampling, normals, FPFH -------------------------------------
+size_t voxel_scratch_bytes(long long n);
+void launch_voxel_down_sample(const float* pts, long long n, double voxel, float* out_pts, int32_t* out_count, int32_t* status,
+                              void* scratch, cudaStream_t st);
+size_t fpfh_scratch_bytes(int m, int max_nn);
+int launch_estimate_normals(const float* pts, int m, double radius, int max_nn, double* normals, int32_t* status, void* scratch,
+                            cudaStream_t st);      // returns cudaError_t
+int launch_compute_fpfh(const float* pts, const double* normals, int m, double radius, int max_nn, int normalise, double* out,
+                        int32_t* status, void* scratch, cudaStream_t st);      // returns cudaError_t
+
 // ---- per-device launch configuration (device_state.cu) ----------------------------------------------------
 // opt `kernel` in to `bytes` of dynamic shared memory on the CURRENT device (no-op if already granted there)
 cudaError_t ensure_dynamic_smem(const void* kernel, int bytes);
