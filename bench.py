@@ -554,7 +554,7 @@ def measure_extras(args, model, rank, world, dev, barrier, max_over_ranks):
 
 
 def measure_next_rows(model, dev):
-    """f1 (front end), f3 (evaluation statistics), f4 (non-testing forward with M, N x N power iteration): milliseconds per call
+    """f1 (front end), f2 (descriptors), f3 (evaluation statistics), f4 (non-testing forward with M, N x N power iteration): milliseconds per call
     and the achieved rate against the bound that applies (algorithmic bytes or FLOPs)."""
     import torch
     from pointdsc_b200.frontend import match
@@ -604,6 +604,19 @@ def measure_next_rows(model, dev):
     ms = timed(lambda: model.run_eval(*dv, want_M=True), reps=3)
     res["f4_forward_without_testing_key_B16_N1000_with_M"] = {"ms": ms, "sets_per_s": 16 / (ms * 1e-3)}
     model.train(was)
+    # f2: a 3DMatch-fragment-sized synthetic scene (300 k points -> ~5 k key points at 5 cm), stage by stage
+    from pointdsc_b200 import descriptors as D
+    from pointdsc_b200.synth_scene import scene
+    cloud = torch.from_numpy(scene(300000, seed=0)).to(dev)
+    voxel = 0.05
+    kp = D.voxel_down_sample(cloud, voxel)
+    nrm = D.estimate_normals(kp, 2 * voxel, 30)
+    m = int(kp.shape[0])
+    res["f2_voxel_down_sample_n300k_5cm"] = {"ms": timed(lambda: D.voxel_down_sample(cloud, voxel)), "key_points": m,
+                                              "note": "includes the device->host read of the key-point count"}
+    res["f2_estimate_normals"] = {"ms": timed(lambda: D.estimate_normals(kp, 2 * voxel, 30)), "points": m, "distance_evaluations": m * m}
+    res["f2_compute_fpfh"] = {"ms": timed(lambda: D.compute_fpfh(kp, nrm, 5 * voxel, 100, normalise=True)), "points": m,
+                              "distance_evaluations": m * m}
     return res
 
 

@@ -49,6 +49,21 @@ __device__ __forceinline__ void st_global_v4(void* p, const uint4& v) {
                : "memory");
 }
 
+// the 64-byte half `m` (16 packed 16-bit pairs = 32 K elements) of this thread's 128-byte image row, whose 16-byte pieces are
+// XOR-swizzled by x = (image row & 7): a 32-byte pair of pieces stays one 32-byte sector (its halves swap when x is odd)
+__device__ __forceinline__ void store_image_half(uint8_t* row, uint32_t x, uint32_t m, const uint32_t (&v)[16]) {
+  const uint32_t half = m ^ (x >> 2);
+  const bool sw = (x & 1u) != 0u;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const uint32_t pair = (uint32_t)k ^ ((x >> 1) & 1u);
+    uint8_t* p = row + (half << 6) + (pair << 5);
+    st_global_v8(p, sw ? v[8 * k + 4] : v[8 * k], sw ? v[8 * k + 5] : v[8 * k + 1], sw ? v[8 * k + 6] : v[8 * k + 2],
+                 sw ? v[8 * k + 7] : v[8 * k + 3], sw ? v[8 * k] : v[8 * k + 4], sw ? v[8 * k + 1] : v[8 * k + 5],
+                 sw ? v[8 * k + 2] : v[8 * k + 6], sw ? v[8 * k + 3] : v[8 * k + 7]);
+  }
+}
+
 // D[128 x NOUT] (+)= A[128 x 32 KCH] * B[NOUT x 32 KCH]^T, A in tensor memory in the chunked in-place layout described
 // above (chunk q at a_base + 32 q), B K-major SWIZZLE_128B panels of 64 K elements in shared memory.
 template <int KCH, int NOUT>
@@ -390,6 +405,18 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
             rx[i] = rit & 7u;
           }
         }
+#ifdef PDSC_STG256_IMG
+        size_t own_off;
+        uint32_t own_x;
+        const bool own_ok = row0 + lane < rows;
+        {
+          int bb, nn;
+          locate_row(b0, n0, lane, N, bb, nn);
+          const uint32_t rit = (MODE == kPCQ) ? (uint32_t)(nn & 127) : (uint32_t)(nn & 63);
+          own_off = ((MODE == kPCQ) ? ((size_t)bb * a.QT + (nn >> 7)) : ((size_t)bb * a.KT + (nn >> 6))) * 65536 + rit * 128u;
+          own_x = rit & 7u;
+        }
+#endif
         mbar_wait(d_full + 8 * (1 * 2 + par), (uint32_t)(u & 1));
         tc_fence_after();
 #pragma unroll 1
@@ -410,6 +437,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           }
           const uint32_t poff = base_off + (uint32_t)(c >> 1) * panel_bytes;
           const uint32_t m = (uint32_t)(c & 1);  // which 64-byte half of the 128-byte row
+#ifdef PDSC_STG256_IMG
+          if (own_ok) {
+            store_image_half(img + own_off + poff, own_x, m, hi);
+            if (a.split) store_image_half(img + own_off + poff + lo_off, own_x, m, lo);
+          }
+#else
           stage_store64x2(stage, lane, hi, lo, a.split != 0,
               [&](int i, int piece) -> void* {
                 return rok[i] ? img + roff[i] + poff + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
@@ -417,6 +450,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
               [&](int i, int piece) -> void* {
                 return rok[i] ? img + roff[i] + poff + lo_off + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
               });
+#endif
         }
       }
     }
@@ -503,10 +537,20 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
             if (stamp) PDSC_STAMP1(a.dbg, it, 2, 2);
           }
           // fp32 rows -> HBM, the chunk's 32 columns (128 B per row) in one staging round trip
+#ifdef PDSC_STG256_F32
+          if (row0 + lane < rows) {
+            float* dstrow = a.out_f32 + (row0 + lane) * kC + c0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              st_global_v8(dstrow + 8 * k, xb[8 * k], xb[8 * k + 1], xb[8 * k + 2], xb[8 * k + 3], xb[8 * k + 4], xb[8 * k + 5], xb[8 * k + 6],
+                           xb[8 * k + 7]);
+          }
+#else
           stage_store128(stage, lane, xb, [&](int i) -> void* {
             const long long g = row0 + (lane >> 3) + 4 * i;
             return g < rows ? (void*)(a.out_f32 + g * kC + c0) : nullptr;
           });
+#endif
         }
         if (stamp) PDSC_STAMP1(a.dbg, it, 2, 3);
       } else if (MODE == kKV) {
@@ -526,6 +570,18 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           roff[i] = ((size_t)bb * a.KT + (nn >> 6)) * 65536 + rit * 128u;
           rx[i] = rit & 7u;
         }
+#ifdef PDSC_STG256_IMG
+        size_t own_off;
+        uint32_t own_x;
+        const bool own_ok = row0 + lane < rows;
+        {
+          int bb, nn;
+          locate_row(b0, n0, lane, N, bb, nn);
+          const uint32_t rit = (uint32_t)(nn & 63);
+          own_off = ((size_t)bb * a.KT + (nn >> 6)) * 65536 + rit * 128u;
+          own_x = rit & 7u;
+        }
+#endif
         mbar_wait(d_full + 8 * (0 * 2 + par), (uint32_t)(u & 1));
         tc_fence_after();
 #pragma unroll 1
@@ -546,6 +602,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           }
           const uint32_t poff = (uint32_t)(c >> 1) * 8192u;
           const uint32_t m = (uint32_t)(c & 1);
+#ifdef PDSC_STG256_IMG
+          if (own_ok) {
+            store_image_half(a.kvimg + own_off + poff, own_x, m, hi);
+            if (a.split) store_image_half(a.kvimg + own_off + poff + 16384u, own_x, m, lo);
+          }
+#else
           stage_store64x2(stage, lane, hi, lo, a.split != 0,
               [&](int i, int piece) -> void* {
                 return rok[i] ? a.kvimg + roff[i] + poff + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
@@ -553,6 +615,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
               [&](int i, int piece) -> void* {
                 return rok[i] ? a.kvimg + roff[i] + poff + 16384u + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
               });
+#endif
         }
       } else {
         // ---- MSG, last step: feat = feat1 + (D2 + bm2), through the residual tile in shared memory ----

@@ -89,4 +89,13 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_hi, uint3
   }
 }
 
+// 256-bit store (STG.256, sm_100+): a thread that owns a row writes whole 32-byte sectors of it, so a row-per-thread epilogue can
+// store straight from registers without a shared-memory transposition
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
+                                             uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(__cvta_generic_to_global(p)), "r"(a0), "r"(a1), "r"(a2),
+               "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+
 }  // namespace pdsc
