@@ -183,6 +183,16 @@ __global__ void tc_decode_kernel(const uint8_t* qimg, const uint8_t* kvimg, floa
   v[idx] = rd(kb + 32768 + ko) + (split ? rd(kb + 49152 + ko) : 0.f);
 }
 
+// debug tap: feat1 from its blocked layout (tc_chain.cuh) to plain [rows][128]
+__global__ void tc_unblock_f32_kernel(const float* __restrict__ blocked, float* __restrict__ plain, long long rows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // 16-byte piece index
+  if (i >= rows * 32) return;
+  const long long g = i >> 5;
+  const uint32_t piece = (uint32_t)(i & 31);
+  reinterpret_cast<float4*>(plain)[i] =
+      *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(blocked) + blocked_f32_offset(g, piece));
+}
+
 // =========================================================================================================
 // host orchestration
 // =========================================================================================================
@@ -239,7 +249,7 @@ static int tc_encoder_forward_fmt(const TcWeights& w, const TcForwardArgs& a, cu
     if (a.attn_events) cudaEventRecord(a.attn_events[2 * l + 1], st);
     if (a.debug_out && a.debug_layer == l) {
       const size_t plane = (size_t)rows * kC;
-      cudaMemcpyAsync(a.debug_out, a.feat1, plane * sizeof(float), cudaMemcpyDeviceToDevice, st);
+      tc_unblock_f32_kernel<<<(unsigned)((plane / 4 + 255) / 256), 256, 0, st>>>(a.feat1, a.debug_out, rows);
       tc_decode_kernel<FMT><<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(qimg, kvimg, a.debug_out + plane, a.debug_out + 2 * plane,
                                                                              a.debug_out + 3 * plane, rows, a.N, QT, KT, a.split);
       cudaMemcpyAsync(a.debug_out + 4 * plane, a.msg, plane * sizeof(float), cudaMemcpyDeviceToDevice, st);

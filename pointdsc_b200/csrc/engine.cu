@@ -141,7 +141,7 @@ Workspace carve(const pdsc_engine* e, void* ptr, int B, int N) {
     w.sc = c.take<float>(R * NS > tiled ? R * NS : tiled);
   }
   w.feat_a = c.take<float>(R * kC);
-  w.feat_b = c.take<float>(R * kC);
+  w.feat_b = c.take<float>((R + 127) / 128 * 128 * kC);   // tensor-core modes keep feat1 blocked by 128-row tile (tc_chain.cuh)
   w.msg = c.take<float>(R * kC);
   if (e->cfg.precision == PDSC_FP32_SIMT) {
     w.q = c.take<float>(R * kC);

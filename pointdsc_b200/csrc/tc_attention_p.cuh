@@ -389,31 +389,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
       // four full 128-byte lines.  The buffer is free here: both halves of the next Q have already gone through it.
       // (split formats: group 1 moves the lo image, which fills the whole buffer, so group 0 waits for it; single formats: only
       // group 0 moves an image - the hi one, also the whole buffer - so group 1 waits for that)
-#ifdef PDSC_STG256_ATTN
-      {
-        float* drow = (partial ? a.part_o + (size_t)witem * (128 * kC) : a.msg + ((size_t)b * a.N + qt * 128) * kC) + (size_t)r * kC + 64 * g;
-        const bool rok = partial || qt * 128 + r < a.N;
-#pragma unroll
-        for (int sr = 0; sr < 2; ++sr) {
-          uint32_t o[32];
-          tmem_ld32(tO + lane_base + 64 * g + 32 * sr, o);
-          tmem_ld_wait();
-          if (sr == 1) {
-            tc_fence_before();
-            mbar_arrive(o_free);
-          }
-          if (rok) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              st_global_v8(drow + 32 * sr + 8 * k, __float_as_uint(__uint_as_float(o[8 * k]) * inv_l), __float_as_uint(__uint_as_float(o[8 * k + 1]) * inv_l),
-                           __float_as_uint(__uint_as_float(o[8 * k + 2]) * inv_l), __float_as_uint(__uint_as_float(o[8 * k + 3]) * inv_l),
-                           __float_as_uint(__uint_as_float(o[8 * k + 4]) * inv_l), __float_as_uint(__uint_as_float(o[8 * k + 5]) * inv_l),
-                           __float_as_uint(__uint_as_float(o[8 * k + 6]) * inv_l), __float_as_uint(__uint_as_float(o[8 * k + 7]) * inv_l));
-          }
-        }
-        mbar_arrive(stage_free);
-      }
-#else
       if (it + 1 < my_items) {
         if (a.split && g == 0) mbar_wait(ql_used, (uint32_t)((it + 1) & 1));
         if (!a.split && g == 1) mbar_wait(qh_used, (uint32_t)((it + 1) & 1));
@@ -445,7 +420,6 @@ __global__ void __launch_bounds__(kAttnThreads, 1) tc_attention_persistent_kerne
         group_sync(g);
       }
       mbar_arrive(stage_free);
-#endif
       if (stamp) PDSC_STAMP1(a.dbg, it, 1 + g, 6);
     }
   }

@@ -18,8 +18,16 @@
 // Chained steps never go back through shared memory: the epilogue writes the next step's A operand over the accumulator
 // columns it has just read, and the next MMA takes A FROM TENSOR MEMORY.  Chunk q (K elements 32 q .. 32 q + 31) of such
 // an operand sits at columns 32 q .. 32 q + 31 of the producing accumulator as [hi: 16 columns | lo: 16 columns].
-// Accumulators are double-buffered in TMEM by tile parity (2 x 256 columns).  Global stores go through a 2 KB per-warp
-// staging buffer, 32 rows x 64 B at a time, so that every store instruction writes eight full 64-byte segments.
+// Accumulators are double-buffered in TMEM by tile parity (2 x 256 columns).  The 16-bit operand images (Q, K, V) are stored
+// straight from registers: a thread owns a row, a 32-column chunk is 64 bytes of its hi and 64 of its lo image row, written as
+// 256-bit stores (STG.256, whole 32-byte sectors; the 128-byte swizzle only swaps the halves of a sector).  Same-box A/B against
+// the staged form (transposition through shared memory, 8 rows x 64 B per instruction): chain kernels 3.51 -> 3.29 ms per step.
+// feat1 (fp32, PCQ -> KV and MSG) lives in HBM in a BLOCKED layout keyed by the 128-row chain tile:
+//     [tile][32-column chunk cc][128 rows][128 B], 16-byte piece q of row r at piece q ^ (r & 7)
+// so that the 32 rows x 128 B a warp produces per chunk are 4 KB contiguous and leave as ONE bulk async copy (TMA engine) from
+// the warp's shared-memory staging buffer — no read-back, no store instructions, and the warp does not wait for the data to
+// leave the SM (two buffers per warp; the direct STG.256 form measured slower for these 128-byte pieces).  The KV loaders and
+// the MSG residual loader read it with the same address function (blocked_f32_offset).
 #pragma once
 #include "tc_common.cuh"
 
@@ -108,67 +116,9 @@ __device__ __forceinline__ void locate_row(int b0, int n0, int rr, int N, int& b
   }
 }
 
-// Global stores go through a 4 KB per-warp staging buffer so that every store instruction writes full segments.  Layout of a
-// 64-byte-per-row piece (32 rows x 64 B = 2 KB): 16-byte chunk q of row r is parked at chunk q ^ ((r >> 1) & 3) of the row's
-// 64-byte slot (conflict-free both ways); in the read-out lane l takes piece (l & 3) of rows (l >> 2) + 8 i, i < 4, so each store
-// instruction writes 8 rows x 64 B.
-// A whole 32-column fp32 chunk (32 words = 128 B per thread = row) in ONE shared-memory round trip — the round
-// trip (two __syncwarp, store -> load latency) was ~450 cycles of a ~1400-cycle epilogue chunk and was paid twice per chunk.
-// 16-byte chunk q of row r is parked at chunk q ^ (r & 7) of the row's 128-byte slot (4 KB per warp); in the read-out lane l
-// takes piece (l & 7) of rows (l >> 3) + 4 i, i < 8, so each store instruction writes four FULL 128-byte lines.
-// dst(i) returns the global address of the 128-byte segment of row (l >> 3) + 4 i, or nullptr.
-template <typename DstFn>
-__device__ __forceinline__ void stage_store128(uint8_t* stage, int lane, const uint32_t (&v)[32], DstFn dst) {
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    *reinterpret_cast<uint4*>(stage + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-  __syncwarp();
-  const int piece = lane & 7;
-  uint4 val[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rr = (lane >> 3) + 4 * i;
-    val[i] = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((piece ^ (rr & 7)) << 4));
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    uint8_t* p = static_cast<uint8_t*>(dst(i));
-    if (p) st_global_v4(p + piece * 16, val[i]);
-  }
-}
-
-// Two 64-byte pieces per row (the hi and the lo image of a 32-column chunk) in one round trip: the two halves of the warp's
-// 4 KB staging buffer, stage_store64's layout in each.
-template <typename DstFn0, typename DstFn1>
-__device__ __forceinline__ void stage_store64x2(uint8_t* stage, int lane, const uint32_t (&v0)[16], const uint32_t (&v1)[16], bool second,
-                                                DstFn0 dst0, DstFn1 dst1) {
-  __syncwarp();
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    *reinterpret_cast<uint4*>(stage + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = make_uint4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]);
-    if (second)
-      *reinterpret_cast<uint4*>(stage + 2048 + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4)) = make_uint4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]);
-  }
-  __syncwarp();
-  const int piece = lane & 3;
-  uint4 a0[4], a1[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int rr = (lane >> 2) + 8 * i;
-    const int off = rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4);
-    a0[i] = *reinterpret_cast<const uint4*>(stage + off);
-    if (second) a1[i] = *reinterpret_cast<const uint4*>(stage + 2048 + off);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    void* p0 = dst0(i, piece);
-    if (p0) st_global_v4(p0, a0[i]);
-    if (second) {
-      void* p1 = dst1(i, piece);
-      if (p1) st_global_v4(p1, a1[i]);
-    }
-  }
+// byte offset of the 16-byte piece `piece` (0..31) of global row `g` in the blocked fp32 layout described in the header
+__host__ __device__ __forceinline__ size_t blocked_f32_offset(long long g, uint32_t piece) {
+  return (size_t)(g >> 7) * 65536 + (size_t)(piece >> 3) * 16384 + (size_t)(g & 127) * 128 + (size_t)(((piece & 7u) ^ ((uint32_t)g & 7u)) << 4);
 }
 
 template <int MODE, int FMT>
@@ -324,13 +274,20 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
     int it = 0;
     for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const long long row0 = tile * 128;
+      // blocked feat1 (KV: the input; MSG: the residual): this tile's 64 KB block, this lane's 32-column chunk
+      const uint8_t* blk_base = reinterpret_cast<const uint8_t*>(MODE == kKV ? a.in : a.res) + (size_t)tile * 65536 + (size_t)(lane >> 3) * 16384;
       float4 v[kChLoaderRows];
 #pragma unroll
       for (int i = 0; i < kChLoaderRows; ++i) {
         const int rr = lw + kChLoaderWarps * i;
         const long long grow = row0 + rr;
-        v[i] = (rr < 128 && grow < rows) ? __ldg(reinterpret_cast<const float4*>(a.in + grow * kC) + lane)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == kKV)   // feat1: blocked layout (tile base + a 32-bit offset: row rr of the tile, this lane's 16-byte piece)
+          v[i] = (rr < 128 && grow < rows)
+                     ? __ldg(reinterpret_cast<const float4*>(blk_base + (uint32_t)rr * 128u + ((((uint32_t)lane & 7u) ^ ((uint32_t)rr & 7u)) << 4)))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        else
+          v[i] = (rr < 128 && grow < rows) ? __ldg(reinterpret_cast<const float4*>(a.in + grow * kC) + lane)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (stamp_ld) PDSC_STAMP1(a.dbg, it, 1, 0);
       if (it > 0) mbar_wait(a_free, (uint32_t)((it - 1) & 1));
@@ -361,7 +318,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
             const long long grow = row0 + r;
             const uint32_t dst = s0 + kChRes + (uint32_t)r * 512u + (uint32_t)(((lane & ~7) | ((lane ^ r) & 7)) << 4);
             const bool ok = grow < rows;
-            cp_async16(dst, ok ? (const void*)(a.res + grow * kC + lane * 4) : (const void*)a.res, ok ? 16u : 0u);
+            cp_async16(dst, ok ? (const void*)(blk_base + (uint32_t)r * 128u + ((((uint32_t)lane & 7u) ^ ((uint32_t)r & 7u)) << 4))
+                                 : (const void*)a.res, ok ? 16u : 0u);
           }
         }
         cp_async_arrive_noinc(r_ready);
@@ -372,7 +330,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
     if (MODE == kPCQ || MODE == kKV) {
       const int q4 = warp & 3;
       const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
-      uint8_t* stage = smem + kChStage + warp * 4096;
       const float* bvec = bias + 128;
       uint8_t* const img = (MODE == kPCQ) ? a.qimg : a.kvimg;
       const uint32_t panel_bytes = (MODE == kPCQ) ? 16384u : 8192u;
@@ -385,27 +342,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
         const long long row0 = tile * 128 + q4 * 32;
         const int b0 = (int)((unsigned)row0 / (unsigned)N);
         const int n0 = (int)((unsigned)row0 - (unsigned)b0 * (unsigned)N);
-        // image rows of the 4 rows this lane stores in the read-out phase
-        size_t roff[4];
-        uint32_t rx[4];
-        bool rok[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = (lane >> 2) + 8 * i;
-          int bb, nn;
-          locate_row(b0, n0, rr, N, bb, nn);
-          rok[i] = row0 + rr < rows;
-          if (MODE == kPCQ) {
-            const uint32_t rit = (uint32_t)(nn & 127);
-            roff[i] = ((size_t)bb * a.QT + (nn >> 7)) * 65536 + rit * 128u;
-            rx[i] = rit & 7u;
-          } else {
-            const uint32_t rit = (uint32_t)(nn & 63);
-            roff[i] = ((size_t)bb * a.KT + (nn >> 6)) * 65536 + rit * 128u;
-            rx[i] = rit & 7u;
-          }
-        }
-#ifdef PDSC_STG256_IMG
+        // this thread's row of the image (thread = row: it stores its own 64-byte pieces as two 32-byte sectors each)
         size_t own_off;
         uint32_t own_x;
         const bool own_ok = row0 + lane < rows;
@@ -416,7 +353,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           own_off = ((MODE == kPCQ) ? ((size_t)bb * a.QT + (nn >> 7)) : ((size_t)bb * a.KT + (nn >> 6))) * 65536 + rit * 128u;
           own_x = rit & 7u;
         }
-#endif
         mbar_wait(d_full + 8 * (1 * 2 + par), (uint32_t)(u & 1));
         tc_fence_after();
 #pragma unroll 1
@@ -437,20 +373,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           }
           const uint32_t poff = base_off + (uint32_t)(c >> 1) * panel_bytes;
           const uint32_t m = (uint32_t)(c & 1);  // which 64-byte half of the 128-byte row
-#ifdef PDSC_STG256_IMG
           if (own_ok) {
             store_image_half(img + own_off + poff, own_x, m, hi);
             if (a.split) store_image_half(img + own_off + poff + lo_off, own_x, m, lo);
           }
-#else
-          stage_store64x2(stage, lane, hi, lo, a.split != 0,
-              [&](int i, int piece) -> void* {
-                return rok[i] ? img + roff[i] + poff + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
-              },
-              [&](int i, int piece) -> void* {
-                return rok[i] ? img + roff[i] + poff + lo_off + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
-              });
-#endif
         }
       }
     }
@@ -494,7 +420,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
     // =================================== group A: thread = row ===================================
     const int q4 = warp & 3;
     const uint32_t lane_base = ((uint32_t)(q4 * 32)) << 16;
-    uint8_t* stage = smem + kChStage + warp * 4096;          // PCQ / KV
+    uint8_t* stage = smem + kChStage + warp * 8192;          // PCQ: two 4 KB buffers per warp (feat1 chunks on their way to the TMA engine)
     uint8_t* resq = smem + kChRes + q4 * 32 * 512;           // MSG: the 32 residual rows of this lane quarter
     const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && tid == 0;
     int it = 0;
@@ -536,41 +462,30 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
             mbar_arrive(a1_par + 8 * par);
             if (stamp) PDSC_STAMP1(a.dbg, it, 2, 2);
           }
-          // fp32 rows -> HBM, the chunk's 32 columns (128 B per row) in one staging round trip
-#ifdef PDSC_STG256_F32
-          if (row0 + lane < rows) {
-            float* dstrow = a.out_f32 + (row0 + lane) * kC + c0;
+          // fp32 rows -> HBM (blocked layout): park the chunk's 32 rows x 128 B in one of the warp's two staging buffers and hand
+          // them to the TMA engine as one contiguous 4 KB copy; the buffer used two chunks ago must have been read by then
+          {
+            uint8_t* buf = stage + (cc & 1) * 4096;
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              st_global_v8(dstrow + 8 * k, xb[8 * k], xb[8 * k + 1], xb[8 * k + 2], xb[8 * k + 3], xb[8 * k + 4], xb[8 * k + 5], xb[8 * k + 6],
-                           xb[8 * k + 7]);
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<uint4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_uint4(xb[4 * q], xb[4 * q + 1], xb[4 * q + 2], xb[4 * q + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            const long long valid = rows - row0;      // rows of this lane quarter that exist (the last tile may be ragged)
+            if (lane == 0 && valid > 0) {
+              bulk_s2g(reinterpret_cast<uint8_t*>(a.out_f32) + (size_t)tile * 65536 + (size_t)cc * 16384 + (size_t)q4 * 4096, smem_u32(buf),
+                       (uint32_t)(valid < 32 ? valid : 32) * 128u);
+              bulk_commit();
+            }
           }
-#else
-          stage_store128(stage, lane, xb, [&](int i) -> void* {
-            const long long g = row0 + (lane >> 3) + 4 * i;
-            return g < rows ? (void*)(a.out_f32 + g * kC + c0) : nullptr;
-          });
-#endif
         }
         if (stamp) PDSC_STAMP1(a.dbg, it, 2, 3);
       } else if (MODE == kKV) {
         // ---- K image: 32 columns = half of one 128-byte image row of panel c >> 1 ----
         const int b0 = (int)((unsigned)row0 / (unsigned)N);
         const int n0 = (int)((unsigned)row0 - (unsigned)b0 * (unsigned)N);
-        size_t roff[4];
-        uint32_t rx[4];
-        bool rok[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = (lane >> 2) + 8 * i;
-          int bb, nn;
-          locate_row(b0, n0, rr, N, bb, nn);
-          rok[i] = row0 + rr < rows;
-          const uint32_t rit = (uint32_t)(nn & 63);
-          roff[i] = ((size_t)bb * a.KT + (nn >> 6)) * 65536 + rit * 128u;
-          rx[i] = rit & 7u;
-        }
-#ifdef PDSC_STG256_IMG
         size_t own_off;
         uint32_t own_x;
         const bool own_ok = row0 + lane < rows;
@@ -581,7 +496,6 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           own_off = ((size_t)bb * a.KT + (nn >> 6)) * 65536 + rit * 128u;
           own_x = rit & 7u;
         }
-#endif
         mbar_wait(d_full + 8 * (0 * 2 + par), (uint32_t)(u & 1));
         tc_fence_after();
 #pragma unroll 1
@@ -602,20 +516,10 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
           }
           const uint32_t poff = (uint32_t)(c >> 1) * 8192u;
           const uint32_t m = (uint32_t)(c & 1);
-#ifdef PDSC_STG256_IMG
           if (own_ok) {
             store_image_half(a.kvimg + own_off + poff, own_x, m, hi);
             if (a.split) store_image_half(a.kvimg + own_off + poff + 16384u, own_x, m, lo);
           }
-#else
-          stage_store64x2(stage, lane, hi, lo, a.split != 0,
-              [&](int i, int piece) -> void* {
-                return rok[i] ? a.kvimg + roff[i] + poff + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
-              },
-              [&](int i, int piece) -> void* {
-                return rok[i] ? a.kvimg + roff[i] + poff + 16384u + ((m ^ (rx[i] >> 2)) << 6) + (((uint32_t)piece ^ (rx[i] & 3u)) << 4) : nullptr;
-              });
-#endif
         }
       } else {
         // ---- MSG, last step: feat = feat1 + (D2 + bm2), through the residual tile in shared memory ----
@@ -655,6 +559,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) tc_chain_kernel(ChainArgs a)
       }
     }
   }
+  if (MODE == kPCQ && warp < 4 && lane == 0) bulk_wait_all<0>();   // the staged feat1 chunks have left shared memory (and are complete)
   tc_fence_before();
   __syncthreads();
   if (warp == 15) tmem_dealloc(tmem, 512);

@@ -75,6 +75,25 @@ def test_no_cpu_fallback():
         m({k: v for k, v in data.items() if k != "testing"})
 
 
+def test_descriptor_entry_points_reject_bad_arguments_without_a_device():
+    """Row f2's C-ABI entries validate before they touch CUDA; the Python wrappers refuse CPU tensors (no fallback)."""
+    from pointdsc_b200 import PdscError, _capi, descriptors
+    lib = _capi.load()
+    assert lib.pdsc_voxel_down_sample(None, 10, None, 0.05, None, None, None, None, 0, None) != 0
+    assert b"null engine" in lib.pdsc_last_error()
+    assert lib.pdsc_estimate_normals(None, 10, None, 0.1, 30, None, None, None, 0, None) != 0
+    assert lib.pdsc_compute_fpfh(None, 10, None, None, 0.25, 100, 0, None, None, None, 0, None) != 0
+    assert lib.pdsc_voxel_down_sample_scratch_bytes(0) == 0 and lib.pdsc_fpfh_scratch_bytes(0, 100) == 0
+    n = 100000
+    slots = 262144                      # the next power of two >= 2 n
+    assert lib.pdsc_voxel_down_sample_scratch_bytes(n) == 32 + slots * 36 + n * 12
+    assert lib.pdsc_fpfh_scratch_bytes(5000, 100) == 5000 * 100 * 4 + 5000 * 4 + 16 + 5000 * 33 * 8
+    for fn in (lambda: descriptors.voxel_down_sample(torch.zeros(8, 3), 0.05), lambda: descriptors.estimate_normals(torch.zeros(8, 3), 0.1),
+               lambda: descriptors.compute_fpfh(torch.zeros(8, 3), torch.zeros(8, 3), 0.25)):
+        with pytest.raises(PdscError):
+            fn()
+
+
 def test_engine_creation_fails_without_a_device():
     if torch.cuda.is_available():
         pytest.skip("GPU present")

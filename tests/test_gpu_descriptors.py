@@ -130,13 +130,13 @@ def test_descriptor_chain_registers_a_synthetic_pair(tmp_path):
             f.write(f"ply\nformat binary_little_endian 1.0\nelement vertex {len(pts)}\nproperty float x\nproperty float y\nproperty float z\nend_header\n".encode())
             f.write(pts.astype("<f4").tobytes())
         clouds.append(torch.from_numpy(read_ply(str(path))).cuda())
-    voxel = 0.05
+    voxel = 0.08
     (skp, sf), (tkp, tf) = fpfh_descriptors(clouds[0], voxel), fpfh_descriptors(clouds[1], voxel)
     assert sf.dtype == torch.float64 and sf.shape[1] == 33 and 2000 < skp.shape[0] < 20000
     data = match(sf, tf, skp, tkp, use_mutual=False)
     model = PointDSC(in_dim=6, num_layers=12, num_channels=128, num_iterations=10, ratio=0.1, inlier_threshold=0.10, sigma_d=0.10,
                      k=40, nms_radius=0.10).cuda().eval()
-    model.load_state_dict(load_snapshot("3dmatch"))
+    model.load_state_dict(load_snapshot("3dmatch"), strict=False)
     data["testing"] = True
     res = model(data)
     T = res["final_trans"][0].double().cpu().numpy()
