@@ -14,6 +14,7 @@ for k, n, b in ((40, 300, 3), (80, 257, 2)):
     h = bench.make_inputs(n, b, "3dmatch", 0)
     d = [h[x].cuda() for x in ("corr_pos", "src_keypts", "tgt_keypts")]
     out = m.run(*d, taps=["best"])                      # eager
+    dbg = m.run(*d, taps=["layer_debug"], layer_tap=3)   # the debug tap un-blocks feat1
     out2 = m.run(*d)                                    # graph path (capture + replay)
     out2 = m.run(*d)
     ev = m({"corr_pos": d[0], "src_keypts": d[1], "tgt_keypts": d[2]})
@@ -26,5 +27,8 @@ for dt in (torch.float32, torch.float64):
     td = torch.nn.functional.normalize(torch.randn(277, 33, generator=g, dtype=dt), dim=1).cuda()
     for mutual in (False, True):
         r = match(sd, td, torch.rand(301, 3).cuda(), torch.rand(277, 3).cuda(), use_mutual=mutual)
+from pointdsc_b200 import descriptors as D
+from pointdsc_b200.synth_scene import scene
+kp, feat = D.fpfh_descriptors(torch.from_numpy(scene(4000, seed=0)).cuda(), 0.15)
 torch.cuda.synchronize()
-print("sanitize_smoke ok", float(st.sum()), int(it.sum()), r["corr"].shape)
+print("sanitize_smoke ok", float(st.sum()), int(it.sum()), r["corr"].shape, tuple(feat.shape))
