@@ -21,7 +21,8 @@ constexpr int kSeedMaxN = 16384;
 // `d2_min` is the smallest fp32 squared length whose correctly rounded square root is >= R (found on the host by
 // stepping floats around R^2): sqrt is monotonic, so  length3(d) >= R  <=>  fma-chain(d) >= d2_min  exactly,
 // and the kernel needs no square root at all.
-// TILE rows per CTA: 256 for big batches; 32 when the whole call is a handful of CTAs (bs = 1 at N = 1000 was 4 CTAs and 60 us)
+// Big batches: 256 rows per CTA.  Small calls (bs = 1 at N = 1000 is four such CTAs, 60 us of one latency-bound loop per thread) use
+// nms_key_warp_kernel below instead.
 template <int kNmsTile>
 __global__ void __launch_bounds__(kNmsTile) nms_key_kernel(const float* __restrict__ src, const float* __restrict__ conf,
                                                            float* __restrict__ key, int N, float d2_min) {
@@ -52,6 +53,34 @@ __global__ void __launch_bounds__(kNmsTile) nms_key_kernel(const float* __restri
     }
   }
   if (live) key[(size_t)b * N + i] = si * (ok ? 1.0f : 0.0f);
+}
+
+// Small calls: one WARP per row i, the lanes stride over the candidates j, the verdict is a warp vote; a row is decided in
+// N / 32 iterations with 32 loads in flight, and N rows spread over N / 8 CTAs.  Same arithmetic, same result.
+__global__ void __launch_bounds__(256) nms_key_warp_kernel(const float* __restrict__ src, const float* __restrict__ conf,
+                                                           float* __restrict__ key, int N, float d2_min) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= N) return;
+  const float* p = src + (size_t)b * N * 3;
+  const float* s = conf + (size_t)b * N;
+  const float si = s[i];
+  const float xi = p[(size_t)i * 3], yi = p[(size_t)i * 3 + 1], zi = p[(size_t)i * 3 + 2];
+  bool ok = true;
+  for (int j0 = 0; j0 < N; j0 += 128) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + 32 * u + lane;
+      if (j < N) {
+        const float dx = xi - p[(size_t)j * 3], dy = yi - p[(size_t)j * 3 + 1], dz = zi - p[(size_t)j * 3 + 2];
+        const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+        ok = ok && ((si >= s[j]) || (d2 >= d2_min));
+      }
+    }
+    if (!__all_sync(0xffffffffu, ok)) break;
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (lane == 0) key[(size_t)b * N + i] = si * (ok ? 1.0f : 0.0f);
 }
 
 __device__ __forceinline__ uint32_t orderable(float f) {
@@ -113,7 +142,7 @@ void launch_pick_seeds(const float* src, const float* conf, int32_t* seeds, floa
   if ((long long)B * ((N + 255) / 256) >= 2LL * device_sm_count())
     nms_key_kernel<256><<<dim3((N + 255) / 256, B), 256, 0, st>>>(src, conf, key_scratch, N, d2_min);
   else
-    nms_key_kernel<32><<<dim3((N + 31) / 32, B), 32, 0, st>>>(src, conf, key_scratch, N, d2_min);
+    nms_key_warp_kernel<<<dim3((N + 7) / 8, B), 256, 0, st>>>(src, conf, key_scratch, N, d2_min);
   launch_seed_sort(key_scratch, seeds, B, N, S, st);
 }
 
