@@ -32,6 +32,42 @@ __device__ __forceinline__ int warp_sum(int v) {
   return v;
 }
 
+// Two independent fp32 FMAs in one instruction (Blackwell FFMA2, PTX fma.rn.f32x2): d0 += a * b0, d1 += a * b1, each rounded
+// exactly like a scalar fmaf.  ptxas folds the broadcast of `a` into the instruction's scalar-operand form and needs no moves
+// when (d0, d1) and (b0, b1) are neighbouring registers (array elements 2p, 2p + 1; the halves of a float4).
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\tmov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a), "f"(b0), "f"(b1));
+}
+
+// element-wise pairs (FADD2 / FMUL2 / FFMA2): every lane of the pair is rounded exactly like the scalar operation
+__device__ __forceinline__ float2 fsub2_scalar(float a, float2 b) {      // (a - b.x, a - b.y)
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\tsub.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2_pair(float2 a, float2 b, float2 c) {   // a * b + c
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+
 // Euclidean length exactly as the reference's `torch.norm(x, dim=-1)` produces it on CPU (fp32 accumulate,
 // compiled with FMA contraction: x*x, then fma(y,y,.), then fma(z,z,.), IEEE sqrt) — verified bit for bit
 // against torch 2.11 on 4M vectors.  Used for src_dist / SC (reference models/PointDSC.py:151-152).

@@ -16,7 +16,7 @@ namespace pdsc {
 // weights arrive as warp-wide BROADCAST 16-byte loads (32 FMAs per 8 weight loads), and the normalised rows leave the
 // tile again as full 512-byte rows.  Eight warps per CTA, one tile each: while a warp waits for its next tile the other
 // warp of its scheduler computes.  Accumulation order is the reference's: bias first, then ascending input channel, one
-// fp32 FMA each.  (Round 1 staged the tile transposed through 4-way conflicting scalar stores with 2 x 4 warps per SM and
+// fp32 FMA each — issued two outputs at a time as FFMA2 (the activation is the instruction's scalar operand).  (Round 1 staged the tile transposed through 4-way conflicting scalar stores with 2 x 4 warps per SM and
 // no overlap of load and compute: 0.20 ms for 262 MB.)
 constexpr int kHeadWarps = 8;
 constexpr int kHeadStride = 132;       // floats per staged row
@@ -73,10 +73,8 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(const float* __re
 #pragma unroll
           for (int o4 = 0; o4 < 8; ++o4) {
             const float4 wv = *reinterpret_cast<const float4*>(w0t + (c4 + q) * 32 + o4 * 4);
-            h1[o4 * 4 + 0] = fmaf(f, wv.x, h1[o4 * 4 + 0]);
-            h1[o4 * 4 + 1] = fmaf(f, wv.y, h1[o4 * 4 + 1]);
-            h1[o4 * 4 + 2] = fmaf(f, wv.z, h1[o4 * 4 + 2]);
-            h1[o4 * 4 + 3] = fmaf(f, wv.w, h1[o4 * 4 + 3]);
+            ffma2(h1[o4 * 4 + 0], h1[o4 * 4 + 1], f, wv.x, wv.y);      // two outputs per instruction, each a plain fp32 FMA
+            ffma2(h1[o4 * 4 + 2], h1[o4 * 4 + 3], f, wv.z, wv.w);
           }
         }
       }
@@ -98,10 +96,8 @@ __global__ void __launch_bounds__(kHeadWarps * 32) head_kernel(const float* __re
 #pragma unroll
         for (int o4 = 0; o4 < 8; ++o4) {
           const float4 wv = *reinterpret_cast<const float4*>(w2t + c * 32 + o4 * 4);
-          h2[o4 * 4 + 0] = fmaf(a, wv.x, h2[o4 * 4 + 0]);
-          h2[o4 * 4 + 1] = fmaf(a, wv.y, h2[o4 * 4 + 1]);
-          h2[o4 * 4 + 2] = fmaf(a, wv.z, h2[o4 * 4 + 2]);
-          h2[o4 * 4 + 3] = fmaf(a, wv.w, h2[o4 * 4 + 3]);
+          ffma2(h2[o4 * 4 + 0], h2[o4 * 4 + 1], a, wv.x, wv.y);
+          ffma2(h2[o4 * 4 + 2], h2[o4 * 4 + 3], a, wv.z, wv.w);
         }
       }
       float o = 0.f;

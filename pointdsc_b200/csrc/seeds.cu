@@ -26,7 +26,9 @@ constexpr int kSeedMaxN = 16384;
 template <int kNmsTile>
 __global__ void __launch_bounds__(kNmsTile) nms_key_kernel(const float* __restrict__ src, const float* __restrict__ conf,
                                                            float* __restrict__ key, int N, float d2_min) {
-  __shared__ float4 pts[kNmsTile];
+  // candidates staged as four arrays so that an 8-byte load yields the same coordinate of TWO neighbours: the distance chain
+  // then runs as FADD2 / FMUL2 / FFMA2 (two candidates per instruction, each lane rounded like the scalar operation)
+  __shared__ __align__(8) float sx[kNmsTile], sy[kNmsTile], sz[kNmsTile], sw[kNmsTile];
   const int b = blockIdx.y;
   const int i = blockIdx.x * kNmsTile + threadIdx.x;
   const float* p = src + (size_t)b * N * 3;
@@ -39,16 +41,20 @@ __global__ void __launch_bounds__(kNmsTile) nms_key_kernel(const float* __restri
   for (int j0 = 0; j0 < N; j0 += kNmsTile) {
     __syncthreads();
     const int j = j0 + threadIdx.x;
-    if (j < N) pts[threadIdx.x] = make_float4(p[(size_t)j * 3], p[(size_t)j * 3 + 1], p[(size_t)j * 3 + 2], s[j]);
+    const bool have = j < N;      // a pad candidate has score -inf: it suppresses nobody
+    sx[threadIdx.x] = have ? p[(size_t)j * 3] : 0.f;
+    sy[threadIdx.x] = have ? p[(size_t)j * 3 + 1] : 0.f;
+    sz[threadIdx.x] = have ? p[(size_t)j * 3 + 2] : 0.f;
+    sw[threadIdx.x] = have ? s[j] : -INFINITY;
     __syncthreads();
-    const int cnt = min(kNmsTile, N - j0);
     if (ok) {
 #pragma unroll 4
-      for (int t = 0; t < cnt; ++t) {
-        const float4 q = pts[t];
-        const float dx = xi - q.x, dy = yi - q.y, dz = zi - q.z;
-        const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));  // the argument of length3()'s sqrt
-        ok = ok && ((si >= q.w) || (d2 >= d2_min));
+      for (int t = 0; t < kNmsTile; t += 2) {
+        const float2 qx = *reinterpret_cast<const float2*>(sx + t), qy = *reinterpret_cast<const float2*>(sy + t),
+                     qz = *reinterpret_cast<const float2*>(sz + t), qs = *reinterpret_cast<const float2*>(sw + t);
+        const float2 dx = fsub2_scalar(xi, qx), dy = fsub2_scalar(yi, qy), dz = fsub2_scalar(zi, qz);
+        const float2 d2 = ffma2_pair(dz, dz, ffma2_pair(dy, dy, fmul2(dx, dx)));  // the argument of length3()'s sqrt, twice
+        ok = ok && ((si >= qs.x) || (d2.x >= d2_min)) && ((si >= qs.y) || (d2.y >= d2_min));
       }
     }
   }

@@ -9,6 +9,8 @@
 // the host once per refinement iteration (`int(inlier_num ...)`, PointDSC.py:426).  Here the SVD is a
 // register-resident Jacobi (svd3.cuh), one warp per seed problem, and the refinement is one CTA per
 // set that iterates on the device — no host round trips anywhere on the path.
+#include <cmath>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "svd3.cuh"
@@ -26,16 +28,20 @@ __device__ __forceinline__ float residual(const float* T, float x, float y, floa
 // -------------------------------------------------------------------------------------------------
 // one warp per (set, seed): eigenvector -> weights -> weighted Kabsch -> inlier count over all N
 // -------------------------------------------------------------------------------------------------
+constexpr int kHypChunk = 1024;      // points staged per pass (24 KB)
 __global__ void __launch_bounds__(256) seed_hypotheses_kernel(
     const float* __restrict__ src, const float* __restrict__ tgt, const int32_t* __restrict__ knn_idx,
     const float* __restrict__ iterates, const uint32_t* __restrict__ conv_mask, const float* __restrict__ seed_trans_in,
     float* __restrict__ seed_trans, int32_t* __restrict__ inlier_counts, unsigned long long* __restrict__ best_key,
-    float* __restrict__ eig_out, int32_t* __restrict__ power_iters, int N, int S, int k, int iters, float thr,
+    float* __restrict__ eig_out, int32_t* __restrict__ power_iters, int N, int S, int k, int iters, float d2_lim,
     int mask_stride) {
+  // the set's points, staged once per CTA for its eight seeds: six arrays so that an 8-byte load is the same coordinate of two points
+  __shared__ __align__(8) float pts_s[6][kHypChunk];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int s = blockIdx.x * 8 + warp;
-  if (s >= S) return;
+  const int s_raw = blockIdx.x * 8 + warp;
+  const bool active = s_raw < S;            // inactive warps still take part in the staging barriers
+  const int s = active ? s_raw : S - 1;
   const size_t row = (size_t)b * S + s;
   const float* ps = src + (size_t)b * N * 3;
   const float* pt = tgt + (size_t)b * N * 3;
@@ -43,7 +49,7 @@ __global__ void __launch_bounds__(256) seed_hypotheses_kernel(
   // exit iteration of this set: first iteration at which every seed passed allclose, else the cap
   const uint32_t m = conv_mask[(size_t)b * mask_stride] & ((iters >= 32) ? 0xFFFFFFFFu : ((1u << iters) - 1u));
   const int t_exit = m ? (__ffs(m) - 1) : (iters - 1);
-  if (s == 0 && lane == 0 && power_iters) power_iters[b] = t_exit + 1;
+  if (active && s == 0 && lane == 0 && power_iters) power_iters[b] = t_exit + 1;
 
   float T[12];
   if (seed_trans_in) {
@@ -59,7 +65,7 @@ __global__ void __launch_bounds__(256) seed_hypotheses_kernel(
       w[q] = 0.f; ax[q] = ay[q] = az[q] = bx[q] = by[q] = bz[q] = 0.f;
       if (a < k) {
         float e = iterates[(row * iters + t_exit) * k + a];
-        if (eig_out) eig_out[row * k + a] = e;
+        if (eig_out && active) eig_out[row * k + a] = e;
         w[q] = e;
         int j = knn_idx[row * k + a];
         j = min(max(j, 0), N - 1);
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(256) seed_hypotheses_kernel(
     T[4] = R[3]; T[5] = R[4]; T[6] = R[5];  T[7] = cby - (R[3] * cax + R[4] * cay + R[5] * caz);
     T[8] = R[6]; T[9] = R[7]; T[10] = R[8]; T[11] = cbz - (R[6] * cax + R[7] * cay + R[8] * caz);
   }
-  if (lane < 16) {
+  if (lane < 16 && active) {
     float val = (lane == 15) ? 1.0f : 0.0f;
 #pragma unroll
     for (int i = 0; i < 12; ++i)
@@ -113,13 +119,39 @@ __global__ void __launch_bounds__(256) seed_hypotheses_kernel(
     seed_trans[row * 16 + lane] = val;
   }
 
-  // inlier count of this hypothesis over all N correspondences
+  // inlier count of this hypothesis over all N correspondences: ||R p + t - q|| < thr  <=>  the squared length < d2_lim (the smallest
+  // float whose correctly rounded root is >= thr: sqrt is monotonic), two points per instruction (FMUL2 / FFMA2 / FADD2, every lane
+  // rounded exactly like residual(): fma(T0, x, fma(T1, y, T2 z)) + T3, then dx^2, fma(dy, dy, .), fma(dz, dz, .))
   int cnt = 0;
-  for (int j = lane; j < N; j += 32) {
-    const float d = residual(T, ps[(size_t)j * 3], ps[(size_t)j * 3 + 1], ps[(size_t)j * 3 + 2], pt[(size_t)j * 3],
-                             pt[(size_t)j * 3 + 1], pt[(size_t)j * 3 + 2]);
-    cnt += (d < thr) ? 1 : 0;
+  for (int j0 = 0; j0 < N; j0 += kHypChunk) {
+    __syncthreads();
+    for (int f = threadIdx.x; f < 3 * kHypChunk; f += 256) {
+      const int j = f / 3, c = f - 3 * j;
+      const bool have = j0 + j < N;
+      pts_s[c][j] = have ? ps[(size_t)(j0 + j) * 3 + c] : 0.f;
+      pts_s[3 + c][j] = have ? pt[(size_t)(j0 + j) * 3 + c] : INFINITY;   // a pad target is infinitely far away
+    }
+    __syncthreads();
+    const int lim = min(kHypChunk, (N - j0 + 1) & ~1);
+    for (int j = 2 * lane; j < lim; j += 64) {
+      const float2 x = *reinterpret_cast<const float2*>(&pts_s[0][j]), y = *reinterpret_cast<const float2*>(&pts_s[1][j]),
+                   z = *reinterpret_cast<const float2*>(&pts_s[2][j]);
+      const float2 tx = *reinterpret_cast<const float2*>(&pts_s[3][j]), ty = *reinterpret_cast<const float2*>(&pts_s[4][j]),
+                   tz = *reinterpret_cast<const float2*>(&pts_s[5][j]);
+      float2 px = make_float2(__fmul_rn(T[2], z.x), __fmul_rn(T[2], z.y));
+      float2 py = make_float2(__fmul_rn(T[6], z.x), __fmul_rn(T[6], z.y));
+      float2 pz = make_float2(__fmul_rn(T[10], z.x), __fmul_rn(T[10], z.y));
+      ffma2(px.x, px.y, T[1], y.x, y.y); ffma2(px.x, px.y, T[0], x.x, x.y);
+      ffma2(py.x, py.y, T[5], y.x, y.y); ffma2(py.x, py.y, T[4], x.x, x.y);
+      ffma2(pz.x, pz.y, T[9], y.x, y.y); ffma2(pz.x, pz.y, T[8], x.x, x.y);
+      const float2 dx = make_float2(__fsub_rn(__fadd_rn(px.x, T[3]), tx.x), __fsub_rn(__fadd_rn(px.y, T[3]), tx.y));
+      const float2 dy = make_float2(__fsub_rn(__fadd_rn(py.x, T[7]), ty.x), __fsub_rn(__fadd_rn(py.y, T[7]), ty.y));
+      const float2 dz = make_float2(__fsub_rn(__fadd_rn(pz.x, T[11]), tz.x), __fsub_rn(__fadd_rn(pz.y, T[11]), tz.y));
+      const float2 d2 = ffma2_pair(dz, dz, ffma2_pair(dy, dy, fmul2(dx, dx)));
+      cnt += (d2.x < d2_lim ? 1 : 0) + (d2.y < d2_lim ? 1 : 0);
+    }
   }
+  if (!active) return;
   cnt = warp_sum(cnt);
   if (lane == 0) {
     if (inlier_counts) inlier_counts[row] = cnt;
@@ -134,9 +166,13 @@ void launch_seed_hypotheses(const float* src, const float* tgt, const int32_t* k
                             int B, int N, int S, int k, int iters, float inlier_threshold, int mask_stride,
                             cudaStream_t st) {
   if (S <= 0) return;
+  // smallest float x with sqrtf(x) >= threshold (IEEE sqrt on the host == the device's sqrt.rn): residual < threshold <=> its square < x
+  float d2_lim = inlier_threshold * inlier_threshold;
+  while (std::sqrt(d2_lim) >= inlier_threshold && d2_lim > 0.f) d2_lim = std::nextafter(d2_lim, 0.0f);
+  while (std::sqrt(d2_lim) < inlier_threshold) d2_lim = std::nextafter(d2_lim, INFINITY);
   seed_hypotheses_kernel<<<dim3((S + 7) / 8, B), 256, 0, st>>>(src, tgt, knn_idx, iterates, conv_mask, seed_trans_in,
                                                               seed_trans, inlier_counts, best_key, eig_out, power_iters,
-                                                              N, S, k, iters, inlier_threshold, mask_stride);
+                                                              N, S, k, iters, d2_lim, mask_stride);
 }
 
 // -------------------------------------------------------------------------------------------------
