@@ -52,6 +52,20 @@ __device__ __forceinline__ float2 fsub2_scalar(float a, float2 b) {      // (a -
       : "f"(a), "f"(b.x), "f"(b.y));
   return d;
 }
+__device__ __forceinline__ float2 fsub2_pair_scalar(float2 a, float b) {   // (a.x - b, a.y - b)
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tsub.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tsub.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   float2 d;
   asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
@@ -98,6 +112,16 @@ __device__ __forceinline__ float div_by_const(float x, float c, float rc) {
 }
 __device__ __forceinline__ float consistency_rc(float d, float s2, float rc_s2) {
   return fmaxf(__fsub_rn(1.0f, div_by_const(__fmul_rn(d, d), s2, rc_s2)), 0.0f);
+}
+// the same for two values at once: every lane runs the identical rounded sequence (FMUL2, FMUL2, FFMA2, FFMA2, FADD2, max)
+__device__ __forceinline__ float2 consistency_rc2(float2 d, float s2, float rc_s2) {
+  const float2 x = fmul2(d, d);
+  float2 q0 = fmul2(x, make_float2(rc_s2, rc_s2));      // q0 = RN(x rc)
+  float2 r = x;
+  ffma2(r.x, r.y, -s2, q0.x, q0.y);                     // r = x - q0 c, exact
+  ffma2(q0.x, q0.y, rc_s2, r.x, r.y);                   // q = RN(q0 + r rc)
+  const float2 one_minus = fsub2_scalar(1.0f, q0);
+  return make_float2(fmaxf(one_minus.x, 0.0f), fmaxf(one_minus.y, 0.0f));
 }
 
 }  // namespace pdsc

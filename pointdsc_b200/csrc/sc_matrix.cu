@@ -71,7 +71,9 @@ constexpr int kScTStride = 129;   // smem transpose tile [32 i][128 j], odd stri
 __global__ void __launch_bounds__(256) sc_matrix_tiled_kernel(const float* __restrict__ src, const float* __restrict__ tgt,
                                                               float* __restrict__ sc, int N, int KT, int QT, float s2,
                                                               float rc_s2) {
-  __shared__ float4 is4[128], it4[128];   // the A range's points (x, y, z, -), read as broadcast 16-byte loads
+  // the A range's points as six arrays: an 8-byte broadcast load is the same coordinate of TWO consecutive rows, so the distance
+  // chains of two matrix elements run as FADD2 / FMUL2 / FFMA2 (each lane rounded exactly like the scalar sequence)
+  __shared__ __align__(8) float isx[128], isy[128], isz[128], itx[128], ity[128], itz[128];
   __shared__ float tr[32 * kScTStride];
   const int b = blockIdx.y;
   // blockIdx.x enumerates the pairs A <= Bq
@@ -82,8 +84,8 @@ __global__ void __launch_bounds__(256) sc_matrix_tiled_kernel(const float* __res
   const float* pt = tgt + (size_t)b * N * 3;
   if (threadIdx.x < 128) {
     const int i = min(A * 128 + (int)threadIdx.x, N - 1);
-    is4[threadIdx.x] = make_float4(ps[(size_t)i * 3], ps[(size_t)i * 3 + 1], ps[(size_t)i * 3 + 2], 0.f);
-    it4[threadIdx.x] = make_float4(pt[(size_t)i * 3], pt[(size_t)i * 3 + 1], pt[(size_t)i * 3 + 2], 0.f);
+    isx[threadIdx.x] = ps[(size_t)i * 3]; isy[threadIdx.x] = ps[(size_t)i * 3 + 1]; isz[threadIdx.x] = ps[(size_t)i * 3 + 2];
+    itx[threadIdx.x] = pt[(size_t)i * 3]; ity[threadIdx.x] = pt[(size_t)i * 3 + 1]; itz[threadIdx.x] = pt[(size_t)i * 3 + 2];
   }
   __syncthreads();
   const int jl = threadIdx.x & 127, half = threadIdx.x >> 7;
@@ -103,12 +105,22 @@ __global__ void __launch_bounds__(256) sc_matrix_tiled_kernel(const float* __res
     const int i_lim = N - A * 128 - il0;       // rows ii < i_lim are real correspondences
     float vals[16];
 #pragma unroll
-    for (int ii = 0; ii < 16; ++ii) {
-      const float4 p = is4[il0 + ii], q = it4[il0 + ii];
-      const float ds = length3(p.x - sx, p.y - sy, p.z - sz);
-      const float dt = length3(q.x - tx, q.y - ty, q.z - tz);
-      const float v = consistency_rc(__fsub_rn(ds, dt), s2, rc_s2);
-      vals[ii] = (col_ok && ii < i_lim) ? v : 0.0f;
+    for (int ii = 0; ii < 16; ii += 2) {
+      const int r = il0 + ii;
+      const float2 px = *reinterpret_cast<const float2*>(isx + r), py = *reinterpret_cast<const float2*>(isy + r),
+                   pz = *reinterpret_cast<const float2*>(isz + r);
+      const float2 qx = *reinterpret_cast<const float2*>(itx + r), qy = *reinterpret_cast<const float2*>(ity + r),
+                   qz = *reinterpret_cast<const float2*>(itz + r);
+      // length3(): sqrt(fma(dz, dz, fma(dy, dy, dx dx))), the two rows side by side
+      const float2 ax = fsub2_pair_scalar(px, sx), ay = fsub2_pair_scalar(py, sy), az = fsub2_pair_scalar(pz, sz);
+      const float2 bx = fsub2_pair_scalar(qx, tx), by = fsub2_pair_scalar(qy, ty), bz = fsub2_pair_scalar(qz, tz);
+      const float2 a2 = ffma2_pair(az, az, ffma2_pair(ay, ay, fmul2(ax, ax)));
+      const float2 b2 = ffma2_pair(bz, bz, ffma2_pair(by, by, fmul2(bx, bx)));
+      const float2 ds = make_float2(__fsqrt_rn(a2.x), __fsqrt_rn(a2.y));
+      const float2 dt = make_float2(__fsqrt_rn(b2.x), __fsqrt_rn(b2.y));
+      const float2 v = consistency_rc2(fsub2(ds, dt), s2, rc_s2);
+      vals[ii] = (col_ok && ii < i_lim) ? v.x : 0.0f;
+      vals[ii + 1] = (col_ok && ii + 1 < i_lim) ? v.y : 0.0f;
     }
     if (kt1 < KT) {
       // keys (il0 & 63) + ii, ii < 16: four key groups, each one float4 per query
