@@ -5,9 +5,10 @@
 //   MSG : msg --Wm0,relu--> --Wm1,relu--> --Wm2--> + feat1 --> feat (fp32 -> HBM)
 // (reference models/PointDSC.py:56-61 PointCN, :21-23/:36-38 projections, :12-20/:43-44 fc_message + residual)
 //
-// Persistent CTAs (one per SM), weights resident in shared memory, 128-row tiles.  The kernels are bound by the latency
-// of their epilogues (TMEM -> registers -> bias / ReLU / hi-lo split -> stores), not by the tensor core or by HBM, so
-// the two GEMM steps of a tile are drained by DIFFERENT warps working concurrently.  Warp roles (512 threads, so that the
+// Persistent CTAs (one per SM), weights resident in shared memory, 128-row tiles.  An epilogue (TMEM -> registers -> bias /
+// ReLU / hi-lo split -> stores) is a latency chain, so the two GEMM steps of a tile are drained by DIFFERENT warps working
+// concurrently; with the stores off the shared-memory round trip the kernels run at 15-17 B/clk/SM of mixed read + write
+// traffic (0.66-0.73 of the copy peak), and a version with two complete tile chains in flight was no faster.  Warp roles (512 threads, so that the
 // register file divides into 128 registers per thread):
 //   warps 0-3   group A: thread = row r (TMEM lane), all columns.  PCQ: PointCN step (feat1 -> HBM and, as 16-bit hi | lo
 //               images, back into tensor memory for the Q GEMM).  KV: K image.  MSG: last step (+ residual, store).
@@ -37,7 +38,7 @@ constexpr int kChainThreads = 512;
 constexpr int kChLoaderWarps = 7, kChLoaderRows = 19;   // rows lw + 7 i, i < 19 (the last one only for lw < 2)
 constexpr int kChA = 0;                          // A image: [hi p0 16K][hi p1 16K][lo p0 16K][lo p1 16K]
 constexpr int kChW = 65536;                      // weight images (128 KB for PCQ / KV, 80 KB for MSG)
-constexpr int kChStage = 65536 + 131072;         // PCQ / KV: 8 x 4 KB store staging (one 32-column chunk of 32 rows per warp)
+constexpr int kChStage = 65536 + 131072;         // PCQ: 4 warps x two 4 KB staging buffers of feat1 chunks (32 KB; unused by KV)
 constexpr int kChRes = 65536 + 81920;            // MSG: 64 KB residual tile (also the fp32 store staging)
 constexpr int kChBias = kChStage + 32768;        // 256 floats: this mode's biases
 constexpr int kChBars = kChBias + 1024;
