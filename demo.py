@@ -47,7 +47,7 @@ def coverage(src, tgt, radius, trans=None, chunk=4096):
 
 
 @torch.no_grad()
-def register(pcd1, pcd2, snapshot="PointDSC_3DMatch_release", device="cuda", verbose=True):
+def register(pcd1, pcd2, snapshot="PointDSC_3DMatch_release", device="cuda", verbose=True, return_data=False):
     from pointdsc_b200 import PointDSC
     from pointdsc_b200.descriptors import fpfh_descriptors, read_ply
     from pointdsc_b200.frontend import match
@@ -73,10 +73,14 @@ def register(pcd1, pcd2, snapshot="PointDSC_3DMatch_release", device="cuda", ver
            "coverage_before": coverage(src_pts, tgt_pts, 2 * cfg["downsample"]),
            "coverage_after": coverage(src_pts, tgt_pts, 2 * cfg["downsample"], trans),
            "seconds_read": t1 - t0, "seconds_device": t2 - t1}
+    if return_data:       # the network input and the labels, for the parity test against the CPU checker
+        out["data"] = {k: v for k, v in data.items() if k != "testing"}
+        out["final_labels"] = res["final_labels"]
     if verbose:
         print(miss)
         for k, v in out.items():
-            print(f"{k}:\n{v}" if k == "final_trans" else f"{k}: {v}")
+            if k not in ("data", "final_labels"):
+                print(f"{k}:\n{v}" if k == "final_trans" else f"{k}: {v}")
     return out
 
 

@@ -157,7 +157,7 @@ def test_demo_registers_the_reference_clouds():
         pytest.skip("the reference's demo clouds are not installed (baseline/_ref/demo_data)")
     sys.path.insert(0, REPO)
     import demo
-    a = demo.register(paths[0], paths[1], verbose=False)
+    a = demo.register(paths[0], paths[1], verbose=False, return_data=True)
     b = demo.register(paths[0], paths[1], verbose=False)
     assert a["missing_keys"] == [] and a["vertices"] == [258342, 268977]
     assert 4000 < a["key_points"][0] < 7000 and a["correspondences"] == a["key_points"][0]
@@ -166,3 +166,44 @@ def test_demo_registers_the_reference_clouds():
     R = a["final_trans"][:3, :3]
     assert np.allclose(R @ R.T, np.eye(3), atol=1e-5) and np.linalg.det(R) > 0
     assert np.array_equal(a["final_trans"], b["final_trans"]) and a["inliers"] == b["inliers"]
+    # the hot path on REAL correspondences (N = 5 333, ~20 % inliers) against the CPU checker: the 1e-4 bar on R / t
+    from oracle import pointdsc_oracle as O
+    sd = load_snapshot("3dmatch")
+    d = {k: v[0].float().cpu() for k, v in a["data"].items()}
+    want = O.forward_testing(sd, O.default_config("3dmatch"), d["corr_pos"], d["src_keypts"], d["tgt_keypts"])
+    assert np.abs(a["final_trans"] - want["final_trans"].numpy()).max() <= 1e-4
+    assert int((a["final_labels"][0].cpu() != want["final_labels"]).sum()) <= 2
+
+
+@pytest.mark.parametrize("precision", ["fp16x3", "fp32"])
+def test_reference_fixture_of_the_demo_pair(precision):
+    """Real data, reference-generated: tests/golden/demo_pair_3dmatch.npz holds the 5 333 correspondences of the reference's demo
+    pair and what the UNMODIFIED reference module returned for them on CPU (tests/golden/make_demo_golden.py).
+
+    On this pair the reference's argmax over the hypotheses' inlier counts is razor thin — 1061 for its winner, 1060 for SEVEN
+    others, 1059 / 1058 behind them — so WHICH of these near-identical hypotheses wins is decided by rounding-level differences of
+    the features (profiles/r02_demo_pair_diag.txt).  The exact-arithmetic mode (fp32) reproduces the reference's choice and meets
+    the 1e-4 bar; the default fp16x3 mode picks another member of the tied group (seed 96: 1060 in the reference, 1063 here), and
+    the refinement then settles 6e-4 away.  The test pins exactly that: fp32 to the bar, fp16x3 to "a hypothesis the reference
+    itself scores within 2 of its maximum, the same registration to 2e-3"."""
+    import os
+    from conftest import GOLDEN
+    from pointdsc_b200 import PointDSC
+    z = np.load(os.path.join(GOLDEN, "demo_pair_3dmatch.npz"))
+    n = len(z["final_labels"])
+    model = PointDSC(in_dim=6, num_layers=12, num_channels=128, num_iterations=10, ratio=0.1, inlier_threshold=0.10, sigma_d=0.10,
+                     k=40, nms_radius=0.10, precision=precision).cuda().eval()
+    model.load_state_dict(load_snapshot("3dmatch"), strict=False)
+    d = [_dev(z[k])[None] for k in ("corr_pos", "src_keypts", "tgt_keypts")]
+    for batch in (1, 3):                      # bs = 1 (key-split attention) and a small batch (unsplit)
+        out = model.run(*[x.repeat(batch, 1, 1) for x in d], taps=["best", "seeds"])
+        dT = np.abs(out["final_trans"][batch - 1].cpu().numpy() - z["final_trans"]).max()
+        flips = int((out["final_labels"][batch - 1].cpu().numpy() != z["final_labels"]).sum())
+        best = int(out["best"][batch - 1])
+        ref_counts = np.round(z["fitness"] * n)
+        assert ref_counts[best] >= ref_counts.max() - 2, (best, ref_counts[best], ref_counts.max())
+        assert np.array_equal(out["seeds"][batch - 1].cpu().numpy()[:100], z["seeds"][:100])     # the untied head of the seed list
+        if precision == "fp32":
+            assert best == int(z["best"]) and dT <= 1e-4 and flips <= 2, (dT, flips, best)
+        else:
+            assert dT <= 2e-3 and flips <= n // 100, (dT, flips, best)
