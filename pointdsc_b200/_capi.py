@@ -61,6 +61,9 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "pdsc_forward_host": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
+    "pdsc_forward_host_submit": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "pdsc_forward_host_wait": (C.c_int, [C.c_void_p, C.c_int32]),
     "pdsc_forward_eval": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.POINTER(StageIO), C.c_void_p, C.c_size_t, C.c_void_p]),
     "pdsc_eval_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

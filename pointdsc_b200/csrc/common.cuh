@@ -66,6 +66,13 @@ __device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
       : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
   return d;
 }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   float2 d;
   asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
@@ -114,14 +121,21 @@ __device__ __forceinline__ float consistency_rc(float d, float s2, float rc_s2) 
   return fmaxf(__fsub_rn(1.0f, div_by_const(__fmul_rn(d, d), s2, rc_s2)), 0.0f);
 }
 // the same for two values at once: every lane runs the identical rounded sequence (FMUL2, FMUL2, FFMA2, FFMA2, FADD2, max)
-__device__ __forceinline__ float2 consistency_rc2(float2 d, float s2, float rc_s2) {
-  const float2 x = fmul2(d, d);
-  float2 q0 = fmul2(x, make_float2(rc_s2, rc_s2));      // q0 = RN(x rc)
+__device__ __forceinline__ float2 div_by_const2(float2 x, float c, float rc) {
+  float2 q0 = fmul2(x, make_float2(rc, rc));            // q0 = RN(x rc)
   float2 r = x;
-  ffma2(r.x, r.y, -s2, q0.x, q0.y);                     // r = x - q0 c, exact
-  ffma2(q0.x, q0.y, rc_s2, r.x, r.y);                   // q = RN(q0 + r rc)
-  const float2 one_minus = fsub2_scalar(1.0f, q0);
+  ffma2(r.x, r.y, -c, q0.x, q0.y);                      // r = x - q0 c, exact
+  ffma2(q0.x, q0.y, rc, r.x, r.y);                      // q = RN(q0 + r rc)
+  return q0;
+}
+__device__ __forceinline__ float2 consistency_rc2(float2 d, float s2, float rc_s2) {
+  const float2 one_minus = fsub2_scalar(1.0f, div_by_const2(fmul2(d, d), s2, rc_s2));
   return make_float2(fmaxf(one_minus.x, 0.0f), fmaxf(one_minus.y, 0.0f));
+}
+// length3_pow() of two difference vectors side by side
+__device__ __forceinline__ float2 length3_pow2(float2 dx, float2 dy, float2 dz) {
+  const float2 s = fadd2(fadd2(fmul2(dx, dx), fmul2(dy, dy)), fmul2(dz, dz));
+  return make_float2(__fsqrt_rn(s.x), __fsqrt_rn(s.y));
 }
 
 }  // namespace pdsc

@@ -83,6 +83,17 @@ struct pdsc_engine {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_fork = nullptr, corr_ready = nullptr;
   bool corr_pending = false;             // the next pdsc_forward waits for corr_ready before its first reader of corr_pos
+  // pdsc_forward_host_submit / _wait: two calls in flight.  Each slot owns its device copies of the inputs and outputs and
+  // three events; the forwards themselves stay serialised on the caller's stream (one workspace), while the host->device
+  // copies of call t + 1 (h2d_stream) and the device->host copies of call t - 1 (d2h_stream) run beside the forward of call t.
+  struct HostSlot {
+    float* io = nullptr;
+    size_t io_floats = 0;
+    cudaEvent_t in_ready = nullptr, fwd_done = nullptr, out_done = nullptr;
+    bool busy = false;                   // submitted and not yet waited for
+  } slots[2];
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  int next_slot = 0;
   // live profiling (pdsc_profile_*)
   bool profiling = false;
   bool profile_pending = false;
@@ -305,6 +316,15 @@ int pdsc_destroy(pdsc_engine* e) {
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->copy_fork) cudaEventDestroy(e->copy_fork);
   if (e->corr_ready) cudaEventDestroy(e->corr_ready);
+  for (auto& sl : e->slots) {
+    if (sl.busy && sl.out_done) cudaEventSynchronize(sl.out_done);
+    cudaFree(sl.io);
+    if (sl.in_ready) cudaEventDestroy(sl.in_ready);
+    if (sl.fwd_done) cudaEventDestroy(sl.fwd_done);
+    if (sl.out_done) cudaEventDestroy(sl.out_done);
+  }
+  if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream);
+  if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
   for (auto& ev : e->ev) cudaEventDestroy(ev);
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
   if (e->capture_stream) cudaStreamDestroy(e->capture_stream);
@@ -543,7 +563,7 @@ static int forward_impl(pdsc_engine* e, int mode, int32_t B, int32_t N, const fl
     launch_fill_u32(w.conv_mask, 0xFFFFFFFFu, B, st);
     launch_fill_u64(w.best_key, 0ull, B, st);
     launch_nsm_power(w.normed, d_src, d_tgt, w.knn, w.iterates, w.conv_mask, io ? io->out_compat : nullptr, B, N, S, k, T,
-                     e->sigma, e->sigma_spat, mask_stride, st);
+                     e->sigma, e->sigma_spat, mask_stride, e->cfg.precision != PDSC_FP32_SIMT, st);
     mark(6);
     // ---- a10 + a11 --------------------------------------------------------------------------------
     launch_seed_hypotheses(d_src, d_tgt, w.knn, w.iterates, w.conv_mask, io ? io->in_seed_trans : nullptr, w.seed_trans,
@@ -956,6 +976,80 @@ int pdsc_forward_host(pdsc_engine* e, int32_t B, int32_t N, const float* h_corr_
   PDSC_CUDA(cudaMemcpyAsync(h_final_trans, d_tr, (size_t)B * 16 * sizeof(float), cudaMemcpyDeviceToHost, st));
   PDSC_CUDA(cudaMemcpyAsync(h_final_labels, d_lab, R * sizeof(float), cudaMemcpyDeviceToHost, st));
   PDSC_CUDA(cudaStreamSynchronize(st));
+  return PDSC_OK;
+}
+
+int pdsc_forward_host_submit(pdsc_engine* e, int32_t B, int32_t N, const float* h_corr_pos, const float* h_src,
+                             const float* h_tgt, float* h_final_trans, float* h_final_labels, void* cuda_stream,
+                             int32_t* slot_out) {
+  if (!e || !slot_out) return fail(PDSC_ERR_INVALID_ARGUMENT, "null engine / slot pointer");
+  if (!h_corr_pos || !h_src || !h_tgt || !h_final_trans || !h_final_labels) return fail(PDSC_ERR_INVALID_ARGUMENT, "null host pointer");
+  if (B <= 0 || N <= 1) return fail(PDSC_ERR_SHAPE, "need B >= 1 and N >= 2 (got B=%d N=%d)", B, N);
+  pdsc_engine::HostSlot& sl = e->slots[e->next_slot];
+  if (sl.busy)
+    return fail(PDSC_ERR_INVALID_ARGUMENT, "both pipeline slots are in flight: pdsc_forward_host_wait(%d) first", e->next_slot);
+  DeviceGuard g(e->cfg.device);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const size_t R = (size_t)B * N;
+  const size_t need_ws = pdsc_workspace_bytes(e, B, N);
+  if (need_ws > e->host_ws_bytes) {
+    PDSC_CUDA(cudaDeviceSynchronize());          // the other slot's forward may still be using the old workspace
+    cudaFree(e->host_ws);
+    e->host_ws = nullptr; e->host_ws_bytes = 0;
+    PDSC_CUDA(cudaMalloc(&e->host_ws, need_ws));
+    e->host_ws_bytes = need_ws;
+  }
+  const size_t in_dim = (size_t)e->cfg.in_dim;
+  const size_t io_floats = R * (in_dim + 3 + 3 + 1) + (size_t)B * 16 + 64;
+  if (io_floats > sl.io_floats) {                // the slot is idle (its last call was waited for): safe to replace
+    cudaFree(sl.io);
+    sl.io = nullptr; sl.io_floats = 0;
+    PDSC_CUDA(cudaMalloc(&sl.io, io_floats * sizeof(float)));
+    sl.io_floats = io_floats;
+  }
+  if (!e->h2d_stream) {
+    PDSC_CUDA(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
+    PDSC_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+  }
+  if (!sl.in_ready) {
+    PDSC_CUDA(cudaEventCreateWithFlags(&sl.in_ready, cudaEventDisableTiming));
+    PDSC_CUDA(cudaEventCreateWithFlags(&sl.fwd_done, cudaEventDisableTiming));
+    PDSC_CUDA(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+  }
+  float* d_corr = sl.io;
+  float* d_src = d_corr + R * in_dim;
+  float* d_tgt = d_src + R * 3;
+  float* d_lab = d_tgt + R * 3;
+  float* d_tr = d_lab + R;
+  // inputs: the slot's previous call has been waited for, so its buffers are free; nothing orders these copies behind the
+  // forward that is running now — that is the overlap
+  PDSC_CUDA(cudaMemcpyAsync(d_src, h_src, R * 3 * sizeof(float), cudaMemcpyHostToDevice, e->h2d_stream));
+  PDSC_CUDA(cudaMemcpyAsync(d_tgt, h_tgt, R * 3 * sizeof(float), cudaMemcpyHostToDevice, e->h2d_stream));
+  PDSC_CUDA(cudaMemcpyAsync(d_corr, h_corr_pos, R * in_dim * sizeof(float), cudaMemcpyHostToDevice, e->h2d_stream));
+  PDSC_CUDA(cudaEventRecord(sl.in_ready, e->h2d_stream));
+  PDSC_CUDA(cudaStreamWaitEvent(st, sl.in_ready, 0));
+  const int rc = (R <= kGraphRows && !e->profiling)
+                     ? pdsc_forward_graph(e, B, N, d_corr, d_src, d_tgt, d_tr, d_lab, e->host_ws, e->host_ws_bytes, cuda_stream)
+                     : pdsc_forward(e, B, N, d_corr, d_src, d_tgt, d_tr, d_lab, nullptr, e->host_ws, e->host_ws_bytes, cuda_stream);
+  if (rc) return rc;
+  PDSC_CUDA(cudaEventRecord(sl.fwd_done, st));
+  PDSC_CUDA(cudaStreamWaitEvent(e->d2h_stream, sl.fwd_done, 0));
+  PDSC_CUDA(cudaMemcpyAsync(h_final_trans, d_tr, (size_t)B * 16 * sizeof(float), cudaMemcpyDeviceToHost, e->d2h_stream));
+  PDSC_CUDA(cudaMemcpyAsync(h_final_labels, d_lab, R * sizeof(float), cudaMemcpyDeviceToHost, e->d2h_stream));
+  PDSC_CUDA(cudaEventRecord(sl.out_done, e->d2h_stream));
+  sl.busy = true;
+  *slot_out = e->next_slot;
+  e->next_slot ^= 1;
+  return PDSC_OK;
+}
+
+int pdsc_forward_host_wait(pdsc_engine* e, int32_t slot) {
+  if (!e || slot < 0 || slot > 1) return fail(PDSC_ERR_INVALID_ARGUMENT, "pdsc_forward_host_wait: bad engine / slot %d", slot);
+  pdsc_engine::HostSlot& sl = e->slots[slot];
+  if (!sl.busy) return fail(PDSC_ERR_INVALID_ARGUMENT, "pdsc_forward_host_wait: slot %d has no call in flight", slot);
+  DeviceGuard g(e->cfg.device);
+  sl.busy = false;
+  PDSC_CUDA(cudaEventSynchronize(sl.out_done));
   return PDSC_OK;
 }
 

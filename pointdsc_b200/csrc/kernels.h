@@ -60,7 +60,7 @@ void launch_knn_select(const float* dist, int32_t* knn_idx, int B, int N, int S,
 // ---- a8 + a9: compatibility + power iteration -----------------------------------------------------
 void launch_nsm_power(const float* normed, const float* src, const float* tgt, const int32_t* knn_idx, float* iterates,
                       uint32_t* conv_mask, float* compat_out, int B, int N, int S, int k, int iters, float sigma,
-                      float sigma_d, int mask_stride, cudaStream_t st);
+                      float sigma_d, int mask_stride, int tensor_gram, cudaStream_t st);   // tensor_gram: fp16 hi/lo mma.sync Gram (k <= 40)
 
 // ---- a10 + a11: weighted Kabsch per seed, hypothesis scoring, selection -----------------------------
 void launch_seed_hypotheses(const float* src, const float* tgt, const int32_t* knn_idx, const float* iterates,

@@ -14,6 +14,8 @@
 // at once (bs == 1), i.e. the exit iteration is a per-set quantity.  Each seed CTA therefore runs the
 // full `num_iterations`, stores every iterate, and ANDs a "converged at iteration t" bit mask into a
 // per-set word; the consumer (select_refine.cu) takes the iterate at the first all-converged bit.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "warp_select.cuh"
@@ -369,11 +371,241 @@ __global__ void __launch_bounds__(WPS == 1 ? 256 : 128) nsm_power_kernel(
   if (tg == 0) atomicAnd(conv_mask + (size_t)b * mask_stride, mask);
 }
 
+// ---- k <= 40 in the tensor-core precisions: the Gram on the warp-level tensor-core path -------------------------------------
+// The FFMA kernel above spends 43 % of its ~12.7 k warp instructions per seed in the 40 x 40 x 128 Gram and 19 % in the
+// compatibility block.  Here one warp still owns one seed from the gather to the last iterate, but
+//   Gram     F F^T as fp16 hi/lo split products (hi*hi + hi*lo + lo*hi, fp32 accumulate: the arithmetic of the encoder's default
+//            mode and of the seed-row distances in knn_tc.cu) through mma.sync.m16n8k16.  The rows are padded to 48 = three
+//            16-row tiles; a lane loads its fragment elements STRAIGHT from the normalised rows in global memory (8 bytes per
+//            lane, the four lanes of a row cover one 32-byte sector; the next 16-channel step is in flight while the current one
+//            is multiplied) and splits each element exactly once: the A fragment of a 16-row tile is at the same time the B
+//            fragment of its two 8-column tiles.  Only the 9 tiles on or above the diagonal are computed (216 HMMA per seed).
+//            The features are L2-normalised (|x| <= 1): they are scaled by 2^6 before the split so that the low parts stay
+//            normal fp16 numbers, and the accumulator is scaled back by 2^-12 (both exact).
+//   compat   the accumulator fragment holds two neighbouring columns of a row: feature and spatial compatibility of the two
+//            matrix elements run as one FADD2 / FMUL2 / FFMA2 chain (each lane rounded exactly like the scalar sequence of the
+//            FFMA kernel), key points staged as six arrays so that a column pair is one 8-byte load.
+//   power    unchanged (lane-parallel, matrix slice in registers).
+// No feature tile in shared memory: 8 KB per warp (M, key points, iterate).
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                              uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// (a, b) -> packed fp16 pairs hi = round(x), lo = round(x - hi); a in the low half
+__device__ __forceinline__ void split_f16_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+constexpr int kMmaRows = 48;       // 40 neighbours padded to three 16-row tiles
+constexpr int kMmaTiles = 9;       // (i, j): 16-row tile i, 8-column tile j >= 2 i, j < 5
+
+__global__ void __launch_bounds__(256, 2) nsm_power_mma_kernel(
+    const float* __restrict__ normed, const float* __restrict__ src, const float* __restrict__ tgt,
+    const int32_t* __restrict__ knn_idx, float* __restrict__ iterates, uint32_t* __restrict__ conv_mask,
+    float* __restrict__ compat_out, int N, int S, int k, int iters, float sigma2, float sigmad2, int mask_stride,
+    int groups_per_cta, int per_group_floats) {
+  const float rc_sigma2 = 1.0f / sigma2, rc_sigmad2 = 1.0f / sigmad2;   // IEEE divisions (correctly rounded reciprocals)
+  extern __shared__ __align__(16) float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int s = blockIdx.x * groups_per_cta + warp;
+  if (s >= S) return;                      // whole warps leave: nothing below synchronises the block
+  const int ms = k | 1;                    // odd row stride of M: conflict-free column reads
+  float* P = sm + (size_t)warp * per_group_floats;   // six coordinate arrays [48]: src x y z, tgt x y z (8-byte aligned)
+  float* v = P + 6 * kMmaRows;                        // [48]
+  int* idx = reinterpret_cast<int*>(v + kMmaRows);    // [48]
+  float* M = reinterpret_cast<float*>(idx + kMmaRows);   // [k][ms]
+  const size_t seed_row = (size_t)b * S + s;
+
+  for (int a = lane; a < kMmaRows; a += 32) {
+    int j = -1;
+    float sx = 0.f, sy = 0.f, sz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
+    if (a < k) {
+      j = knn_idx[seed_row * k + a];
+      j = min(max(j, 0), N - 1);
+      const float* ps = src + ((size_t)b * N + j) * 3;
+      const float* pt = tgt + ((size_t)b * N + j) * 3;
+      sx = ps[0]; sy = ps[1]; sz = ps[2];
+      tx = pt[0]; ty = pt[1]; tz = pt[2];
+      M[a * ms + a] = 0.0f;                // total_knn_M[:, i, i] = 0  (PointDSC.py:278)
+    }
+    idx[a] = j;
+    P[a] = sx; P[kMmaRows + a] = sy; P[2 * kMmaRows + a] = sz;
+    P[3 * kMmaRows + a] = tx; P[4 * kMmaRows + a] = ty; P[5 * kMmaRows + a] = tz;
+    v[a] = 1.0f;
+  }
+  __syncwarp();
+
+  // ---- Gram ----
+  const int g = lane >> 2, t = lane & 3;
+  const float* rowp[5];                    // rows g + 8 m, m < 5 (rows 40..47 are padding: zero fragments)
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+    const int j = idx[g + 8 * m];
+    rowp[m] = (j >= 0) ? normed + ((size_t)b * N + j) * kC + 2 * t : nullptr;
+  }
+  float acc[kMmaTiles][4];
+#pragma unroll
+  for (int q = 0; q < kMmaTiles; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
+  float2 nxt[5][2];
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+    nxt[m][0] = rowp[m] ? __ldg(reinterpret_cast<const float2*>(rowp[m])) : make_float2(0.f, 0.f);
+    nxt[m][1] = rowp[m] ? __ldg(reinterpret_cast<const float2*>(rowp[m] + 8)) : make_float2(0.f, 0.f);
+  }
+#pragma unroll 1
+  for (int ks = 0; ks < kC / 16; ++ks) {
+    uint32_t hi[6][2], lo[6][2];
+#pragma unroll
+    for (int m = 0; m < 5; ++m)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) split_f16_pair(nxt[m][h].x * 64.0f, nxt[m][h].y * 64.0f, hi[m][h], lo[m][h]);
+    hi[5][0] = hi[5][1] = lo[5][0] = lo[5][1] = 0u;
+    if (ks + 1 < kC / 16) {
+#pragma unroll
+      for (int m = 0; m < 5; ++m) {
+        if (rowp[m]) {
+          nxt[m][0] = __ldg(reinterpret_cast<const float2*>(rowp[m] + 16 * (ks + 1)));
+          nxt[m][1] = __ldg(reinterpret_cast<const float2*>(rowp[m] + 16 * (ks + 1) + 8));
+        }
+      }
+    }
+    // tile q = (i, j): A = rows 16 i + {g, g + 8} = fragments m = 2 i, 2 i + 1;  B = rows 8 j + g = fragment m = j
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 2 * i; j < 5; ++j) {
+        mma_f16_16816(acc[q], hi[2 * i][0], hi[2 * i + 1][0], hi[2 * i][1], hi[2 * i + 1][1], hi[j][0], hi[j][1]);
+        mma_f16_16816(acc[q], hi[2 * i][0], hi[2 * i + 1][0], hi[2 * i][1], hi[2 * i + 1][1], lo[j][0], lo[j][1]);
+        mma_f16_16816(acc[q], lo[2 * i][0], lo[2 * i + 1][0], lo[2 * i][1], lo[2 * i + 1][1], hi[j][0], hi[j][1]);
+        ++q;
+      }
+    }
+  }
+
+  // ---- compatibility: accumulator (q, half) = row 16 i + g + 8 half, columns 8 j + 2 t, 8 j + 2 t + 1 ----
+  {
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 2 * i; j < 5; ++j) {
+        const int c = 8 * j + 2 * t;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int a = 16 * i + g + 8 * half;
+          if (a < c + 1 && c < k) {          // at least the element (a, c + 1) or (a, c) is above the diagonal and real
+            const float2 dot = make_float2(acc[q][2 * half] * (1.0f / 4096.0f), acc[q][2 * half + 1] * (1.0f / 4096.0f));
+            const float2 one_minus = fsub2_scalar(1.0f, div_by_const2(fsub2_scalar(1.0f, dot), sigma2, rc_sigma2));
+            const float2 fm = make_float2(fmaxf(one_minus.x, 0.0f), fmaxf(one_minus.y, 0.0f));
+            const float2 la = length3_pow2(fsub2_scalar(P[a], *reinterpret_cast<const float2*>(P + c)),
+                                           fsub2_scalar(P[kMmaRows + a], *reinterpret_cast<const float2*>(P + kMmaRows + c)),
+                                           fsub2_scalar(P[2 * kMmaRows + a], *reinterpret_cast<const float2*>(P + 2 * kMmaRows + c)));
+            const float2 lb = length3_pow2(fsub2_scalar(P[3 * kMmaRows + a], *reinterpret_cast<const float2*>(P + 3 * kMmaRows + c)),
+                                           fsub2_scalar(P[4 * kMmaRows + a], *reinterpret_cast<const float2*>(P + 4 * kMmaRows + c)),
+                                           fsub2_scalar(P[5 * kMmaRows + a], *reinterpret_cast<const float2*>(P + 5 * kMmaRows + c)));
+            const float2 val = fmul2(fm, consistency_rc2(fsub2(la, lb), sigmad2, rc_sigmad2));
+            if (a < c) {
+              M[a * ms + c] = val.x;
+              M[c * ms + a] = val.x;
+            }
+            if (c + 1 < k) {                 // a < c + 1 holds
+              M[a * ms + c + 1] = val.y;
+              M[(c + 1) * ms + a] = val.y;
+            }
+          }
+        }
+        ++q;
+      }
+    }
+  }
+  __syncwarp();
+  if (compat_out) {
+    float* dst = compat_out + seed_row * k * k;
+    for (int e = lane; e < k * k; e += 32) dst[e] = M[(e / k) * ms + (e % k)];
+  }
+
+  // ---- power iteration from the all-ones vector (as in nsm_power_kernel<1>, k <= 40) ----
+  uint32_t mask = 0u;
+  float* it_out = iterates + seed_row * (size_t)iters * k;
+  const int rg = lane >> 2, cq = lane & 3;
+  const int CQ = (k + 3) >> 2;                       // columns per quarter
+  const int c_lo = cq * CQ, c_hi = min(k, c_lo + CQ);
+  constexpr int RI = 5, CW = 10;
+  float m[RI][CW], vq[CW], vrow[RI];
+#pragma unroll
+  for (int i = 0; i < RI; ++i) {
+    const int row = rg + 8 * i;
+#pragma unroll
+    for (int c = 0; c < CW; ++c) m[i][c] = (row < k && c_lo + c < c_hi) ? M[row * ms + c_lo + c] : 0.f;
+    vrow[i] = 1.0f;
+  }
+#pragma unroll
+  for (int c = 0; c < CW; ++c) vq[c] = (c_lo + c < c_hi) ? 1.0f : 0.f;
+  for (int it = 0; it < iters; ++it) {
+    float u[RI], ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < RI; ++i) {
+      float p = 0.f;
+#pragma unroll
+      for (int c = 0; c < CW; ++c) p = fmaf(m[i][c], vq[c], p);
+      p += __shfl_xor_sync(0xffffffffu, p, 1);
+      p += __shfl_xor_sync(0xffffffffu, p, 2);
+      u[i] = p;
+      ss += (rg + 8 * i < k) ? p * p : 0.f;
+    }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+    const float nrm = sqrtf(ss) + 1e-6f;
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < RI; ++i) {
+      const int row = rg + 8 * i;
+      const float vn = u[i] / nrm;
+      // torch.allclose(new, last): |new - last| <= atol + rtol * |last|, atol 1e-8, rtol 1e-5
+      ok = ok && (row >= k || fabsf(vn - vrow[i]) <= 1e-8f + 1e-5f * fabsf(vrow[i]));
+      vrow[i] = vn;
+      if (row < k && cq == 0) {
+        v[row] = vn;
+        it_out[(size_t)it * k + row] = vn;
+      }
+    }
+    if (__all_sync(0xffffffffu, ok)) mask |= (1u << it);
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < CW; ++c) vq[c] = (c_lo + c < c_hi) ? v[c_lo + c] : 0.f;
+    __syncwarp();
+  }
+  if (lane == 0) atomicAnd(conv_mask + (size_t)b * mask_stride, mask);
+}
+
 void launch_nsm_power(const float* normed, const float* src, const float* tgt, const int32_t* knn_idx, float* iterates,
                       uint32_t* conv_mask, float* compat_out, int B, int N, int S, int k, int iters, float sigma,
-                      float sigma_d, int mask_stride, cudaStream_t st) {
+                      float sigma_d, int mask_stride, int tensor_gram, cudaStream_t st) {
   if (S <= 0) return;
   const int ms = k | 1;
+  if (tensor_gram && k <= 40) {
+    // one warp per seed, two CTAs of eight warps per SM; per warp: key points 6 x 48, iterate 48, indices 48, M k x ms
+    int per_group_floats = 8 * kMmaRows + k * ms;
+    per_group_floats = (per_group_floats + 3) & ~3;
+    const int warps = 8;
+    const int smem = warps * per_group_floats * (int)sizeof(float);
+    ensure_dynamic_smem(reinterpret_cast<const void*>(nsm_power_mma_kernel), smem);
+    nsm_power_mma_kernel<<<dim3((S + warps - 1) / warps, B), warps * 32, smem, st>>>(
+        normed, src, tgt, knn_idx, iterates, conv_mask, compat_out, N, S, k, iters, sigma * sigma, sigma_d * sigma_d, mask_stride,
+        warps, per_group_floats);
+    return;
+  }
   const int kp = (k + 3) & ~3;
   int per_group_floats = kp * 32 + k * ms + 6 * k + k + k + 8;     // F quarter, M, pa, pb, v, idx, red
   per_group_floats = (per_group_floats + 3) & ~3;                  // keep every group's slice 16-byte aligned

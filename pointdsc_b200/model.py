@@ -217,6 +217,69 @@ class PointDSC(nn.Module):
         out = self.run(data["corr_pos"], data["src_keypts"], data["tgt_keypts"])
         return {"final_trans": out["final_trans"], "final_labels": out["final_labels"], "M": None}
 
+    @torch.no_grad()
+    def forward_stream(self, batches: Iterable[Dict[str, torch.Tensor]]):
+        """Testing-mode forwards over an iterable of HOST batches as a two-deep pipeline: yields, in order, what `forward`
+        returns for each element (host tensors).  This is the evaluation drivers' loop (`for data in loader: res = model(data)`,
+        evaluation/test_3DMatch.py:64-101) with the copies taken off the critical path: while the device runs the forward of
+        batch t, the inputs of batch t + 1 are already crossing to the device and the results of batch t - 1 are crossing back
+        (pdsc_forward_host_submit / _wait).  Results are bit-identical to `forward`'s.  Page-locked input tensors
+        (`tensor.pin_memory()`, or a DataLoader with pin_memory=True) are needed for the overlap, not for correctness.
+        Batches already on the device are simply run in order."""
+        lib = self._ensure_engine()
+        dev = self._device()
+        bufs = [None, None]        # page-locked result buffers of the two calls in flight
+        pending = None             # (slot, trans, labels, inputs kept alive)
+        count = 0
+
+        def collect(p):
+            _capi.check(lib.pdsc_forward_host_wait(self._engine, p[0]))
+            return {"final_trans": p[1].clone(), "final_labels": p[2].clone(), "M": None}
+
+        try:
+            for data in batches:
+                if "testing" not in data.keys():
+                    raise ValueError("forward_stream is the testing-mode loop: every batch needs the 'testing' key")
+                cp, s, t = data["corr_pos"], data["src_keypts"], data["tgt_keypts"]
+                if cp.device.type != "cpu":
+                    if pending is not None:
+                        p, pending = pending, None
+                        yield collect(p)
+                    yield self.forward(data)
+                    continue
+                if cp.dim() != 3 or s.shape[:2] != cp.shape[:2] or t.shape != s.shape or s.shape[-1] != 3 \
+                        or cp.shape[-1] != self.in_dim:
+                    raise ValueError(f"expected corr_pos [bs,N,{self.in_dim}] and src/tgt_keypts [bs,N,3], got "
+                                     f"{tuple(cp.shape)}, {tuple(s.shape)}, {tuple(t.shape)}")
+                cp, s, t = (x.to(torch.float32).contiguous() for x in (cp, s, t))
+                B, N = int(cp.shape[0]), int(cp.shape[1])
+                b = bufs[count & 1]
+                if b is None or b[0].shape[0] != B or b[1].shape[1] != N:
+                    b = bufs[count & 1] = (torch.empty(B, 4, 4, dtype=torch.float32).pin_memory(),
+                                           torch.empty(B, N, dtype=torch.float32).pin_memory())
+                slot = C.c_int32(-1)
+                with torch.cuda.device(dev):
+                    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                    _capi.check(lib.pdsc_forward_host_submit(
+                        self._engine, B, N, C.c_void_p(cp.data_ptr()), C.c_void_p(s.data_ptr()), C.c_void_p(t.data_ptr()),
+                        C.c_void_p(b[0].data_ptr()), C.c_void_p(b[1].data_ptr()), stream, C.byref(slot)))
+                cur = (int(slot.value), b[0], b[1], (cp, s, t))
+                count += 1
+                if pending is not None:
+                    p, pending = pending, cur
+                    yield collect(p)
+                else:
+                    pending = cur
+            if pending is not None:
+                p, pending = pending, None
+                yield collect(p)
+        finally:
+            if pending is not None:      # the consumer stopped early: do not leave a call in flight
+                try:
+                    lib.pdsc_forward_host_wait(self._engine, pending[0])
+                except Exception:
+                    pass
+
     def _workspace_for(self, dev, need: int, stream_handle: int) -> torch.Tensor:
         ws = self._workspaces.get(stream_handle)
         if ws is None or ws.numel() < need or ws.device != dev:
