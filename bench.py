@@ -386,21 +386,25 @@ def run_engine(args, rank, world, local_rank):
     hdata = {"corr_pos": pinned["corr_pos"], "src_keypts": pinned["src_keypts"], "tgt_keypts": pinned["tgt_keypts"], "testing": True}
     for _ in model.forward_stream(hdata for _ in range(min(3, args.warmup))):
         pass
+    want_t, want_l = out["final_trans"].cpu(), out["final_labels"].cpu()
     barrier()
     th0 = time.perf_counter()
-    hos = list(model.forward_stream(hdata for _ in range(args.steps)))
+    # every result is read on the host inside the timed region (compared with the device path's) and then dropped, as an
+    # evaluation loop does; retaining all K results would time the first touch of K fresh megabytes instead (slow in the
+    # GPU boxes' virtual machines: ~4 ms per result)
+    streamed, same = 0, True
+    for ho in model.forward_stream(hdata for _ in range(args.steps)):
+        same = same and torch.equal(ho["final_trans"], want_t) and torch.equal(ho["final_labels"], want_l)
+        streamed += 1
     torch.cuda.synchronize()
     th1 = time.perf_counter()
     e2e_s = max_over_ranks(th1 - th0)
     e2e_value = B * world * args.steps / e2e_s
-    ho = hos[-1]
-    assert len(hos) == args.steps and all(torch.equal(o["final_trans"], ho["final_trans"]) and
-                                          torch.equal(o["final_labels"], ho["final_labels"]) for o in hos), "streamed steps differ"
+    assert streamed == args.steps and same, "streamed steps differ from the device path"
     h2d = sum(pinned[k].numel() * 4 for k in pinned)
     d2h = ho["final_trans"].numel() * 4 + ho["final_labels"].numel() * 4
     assert torch.equal(ho["final_trans"], out["final_trans"].cpu()) and torch.equal(ho["final_labels"], out["final_labels"].cpu()), \
         "host path and device path disagree"
-    del hos
     for _ in range(min(2, args.warmup)):
         model.run(pinned["corr_pos"], pinned["src_keypts"], pinned["tgt_keypts"])
     barrier()

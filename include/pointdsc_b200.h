@@ -154,14 +154,15 @@ int pdsc_forward_host(pdsc_engine* e, int32_t B, int32_t N, const float* h_corr_
 
 /* The host form as a two-deep pipeline, for loops over many batches (the evaluation drivers' `for data in loader`,
  * evaluation/test_3DMatch.py:64-101, whose DataLoader workers prefetch the next batch while the model runs the current one):
- * _submit enqueues the host->device copies of this call's inputs on an engine-owned copy stream, the forward on
- * `cuda_stream` behind them, and the device->host copies of the two results on a second engine-owned stream behind the
- * forward, then returns WITHOUT synchronising; `*slot_out` (0 or 1) names the call.  _wait(slot) blocks until that call's
- * results are in the host buffers.  Two calls may be in flight: the copies of call t + 1 and t - 1 then run beside the
- * forward of call t (the forwards themselves stay serialised on `cuda_stream`: they share one workspace).  The host buffers
- * must stay valid until _wait returns and should be page-locked (a pageable buffer makes the copy synchronous and removes the
- * overlap, not the correctness).  A third _submit before a _wait fails with PDSC_ERR_INVALID_ARGUMENT.  Results are
- * bit-identical to pdsc_forward_host's. */
+ * _submit enqueues the host->device copies of this call's inputs on an engine-owned copy stream and the forward on
+ * `cuda_stream` behind them, then returns WITHOUT synchronising; `*slot_out` (0 or 1) names the call.  _wait(slot) blocks until
+ * that call's forward has finished, copies the two results into the host buffers given to _submit (on a second engine-owned
+ * stream, i.e. beside the next call's forward) and returns when they have arrived.  Two calls may be in flight: the input copies
+ * of call t + 1 and the result copies of call t - 1 then run beside the forward of call t (the forwards themselves stay
+ * serialised on `cuda_stream`: they share one workspace).  All five host buffers must stay valid until _wait returns; the INPUT
+ * buffers should be page-locked (from a pageable buffer the copy is synchronous: correct, but without the overlap), the result
+ * buffers may be pageable.  A third _submit before a _wait fails with PDSC_ERR_INVALID_ARGUMENT.  Results are bit-identical to
+ * pdsc_forward_host's. */
 int pdsc_forward_host_submit(pdsc_engine* e, int32_t B, int32_t N, const float* h_corr_pos, const float* h_src_keypts,
                              const float* h_tgt_keypts, float* h_final_trans, float* h_final_labels, void* cuda_stream,
                              int32_t* slot_out);

@@ -89,8 +89,11 @@ struct pdsc_engine {
   struct HostSlot {
     float* io = nullptr;
     size_t io_floats = 0;
-    cudaEvent_t in_ready = nullptr, fwd_done = nullptr, out_done = nullptr;
+    cudaEvent_t in_ready = nullptr, fwd_done = nullptr;
     bool busy = false;                   // submitted and not yet waited for
+    float *h_trans = nullptr, *h_labels = nullptr;   // where _wait delivers the results ...
+    const float *d_trans = nullptr, *d_labels = nullptr;   // ... from
+    size_t trans_bytes = 0, labels_bytes = 0;
   } slots[2];
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   int next_slot = 0;
@@ -317,11 +320,10 @@ int pdsc_destroy(pdsc_engine* e) {
   if (e->copy_fork) cudaEventDestroy(e->copy_fork);
   if (e->corr_ready) cudaEventDestroy(e->corr_ready);
   for (auto& sl : e->slots) {
-    if (sl.busy && sl.out_done) cudaEventSynchronize(sl.out_done);
+    if (sl.busy && sl.fwd_done) cudaEventSynchronize(sl.fwd_done);
     cudaFree(sl.io);
     if (sl.in_ready) cudaEventDestroy(sl.in_ready);
     if (sl.fwd_done) cudaEventDestroy(sl.fwd_done);
-    if (sl.out_done) cudaEventDestroy(sl.out_done);
   }
   if (e->h2d_stream) cudaStreamDestroy(e->h2d_stream);
   if (e->d2h_stream) cudaStreamDestroy(e->d2h_stream);
@@ -1014,7 +1016,6 @@ int pdsc_forward_host_submit(pdsc_engine* e, int32_t B, int32_t N, const float* 
   if (!sl.in_ready) {
     PDSC_CUDA(cudaEventCreateWithFlags(&sl.in_ready, cudaEventDisableTiming));
     PDSC_CUDA(cudaEventCreateWithFlags(&sl.fwd_done, cudaEventDisableTiming));
-    PDSC_CUDA(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
   }
   float* d_corr = sl.io;
   float* d_src = d_corr + R * in_dim;
@@ -1033,10 +1034,11 @@ int pdsc_forward_host_submit(pdsc_engine* e, int32_t B, int32_t N, const float* 
                      : pdsc_forward(e, B, N, d_corr, d_src, d_tgt, d_tr, d_lab, nullptr, e->host_ws, e->host_ws_bytes, cuda_stream);
   if (rc) return rc;
   PDSC_CUDA(cudaEventRecord(sl.fwd_done, st));
-  PDSC_CUDA(cudaStreamWaitEvent(e->d2h_stream, sl.fwd_done, 0));
-  PDSC_CUDA(cudaMemcpyAsync(h_final_trans, d_tr, (size_t)B * 16 * sizeof(float), cudaMemcpyDeviceToHost, e->d2h_stream));
-  PDSC_CUDA(cudaMemcpyAsync(h_final_labels, d_lab, R * sizeof(float), cudaMemcpyDeviceToHost, e->d2h_stream));
-  PDSC_CUDA(cudaEventRecord(sl.out_done, e->d2h_stream));
+  // the results leave in _wait (on d2h_stream, beside the NEXT call's forward): a device->host copy into pageable memory blocks
+  // its caller until the data has arrived, so issuing it here would hold the host inside _submit for the whole forward
+  sl.h_trans = h_final_trans; sl.h_labels = h_final_labels;
+  sl.d_trans = d_tr; sl.d_labels = d_lab;
+  sl.trans_bytes = (size_t)B * 16 * sizeof(float); sl.labels_bytes = R * sizeof(float);
   sl.busy = true;
   *slot_out = e->next_slot;
   e->next_slot ^= 1;
@@ -1049,7 +1051,10 @@ int pdsc_forward_host_wait(pdsc_engine* e, int32_t slot) {
   if (!sl.busy) return fail(PDSC_ERR_INVALID_ARGUMENT, "pdsc_forward_host_wait: slot %d has no call in flight", slot);
   DeviceGuard g(e->cfg.device);
   sl.busy = false;
-  PDSC_CUDA(cudaEventSynchronize(sl.out_done));
+  PDSC_CUDA(cudaStreamWaitEvent(e->d2h_stream, sl.fwd_done, 0));
+  PDSC_CUDA(cudaMemcpyAsync(sl.h_trans, sl.d_trans, sl.trans_bytes, cudaMemcpyDeviceToHost, e->d2h_stream));
+  PDSC_CUDA(cudaMemcpyAsync(sl.h_labels, sl.d_labels, sl.labels_bytes, cudaMemcpyDeviceToHost, e->d2h_stream));
+  PDSC_CUDA(cudaStreamSynchronize(e->d2h_stream));
   return PDSC_OK;
 }
 

@@ -228,13 +228,15 @@ class PointDSC(nn.Module):
         Batches already on the device are simply run in order."""
         lib = self._ensure_engine()
         dev = self._device()
-        bufs = [None, None]        # page-locked result buffers of the two calls in flight
+        # results go straight into fresh caller-owned (pageable) tensors, written by the library's device->host copies inside
+        # _wait: on the GPU boxes a CPU read of page-locked memory is slow (a 1 MB torch-side clone out of a pinned result buffer
+        # took ~5 ms and made the host the bottleneck of the loop), and allocating page-locked memory synchronises the device
         pending = None             # (slot, trans, labels, inputs kept alive)
         count = 0
 
         def collect(p):
             _capi.check(lib.pdsc_forward_host_wait(self._engine, p[0]))
-            return {"final_trans": p[1].clone(), "final_labels": p[2].clone(), "M": None}
+            return {"final_trans": p[1], "final_labels": p[2], "M": None}
 
         try:
             for data in batches:
@@ -253,10 +255,7 @@ class PointDSC(nn.Module):
                                      f"{tuple(cp.shape)}, {tuple(s.shape)}, {tuple(t.shape)}")
                 cp, s, t = (x.to(torch.float32).contiguous() for x in (cp, s, t))
                 B, N = int(cp.shape[0]), int(cp.shape[1])
-                b = bufs[count & 1]
-                if b is None or b[0].shape[0] != B or b[1].shape[1] != N:
-                    b = bufs[count & 1] = (torch.empty(B, 4, 4, dtype=torch.float32).pin_memory(),
-                                           torch.empty(B, N, dtype=torch.float32).pin_memory())
+                b = (torch.empty(B, 4, 4, dtype=torch.float32), torch.empty(B, N, dtype=torch.float32))
                 slot = C.c_int32(-1)
                 with torch.cuda.device(dev):
                     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
