@@ -21,6 +21,10 @@ for k, n, b in ((40, 300, 3), (80, 257, 2)):
     st = eval_stats(out["final_trans"], h["gt_trans"].cuda(), d[1], d[2], out["final_labels"], h["gt_labels"].cuda())
     v, it = leading_eigenvector(ev["M"], 10, True)
     host = m.run(h["corr_pos"], h["src_keypts"], h["tgt_keypts"])
+    hd = {"corr_pos": h["corr_pos"].pin_memory(), "src_keypts": h["src_keypts"].pin_memory(), "tgt_keypts": h["tgt_keypts"].pin_memory(),
+          "testing": True}
+    streamed = list(m.forward_stream(hd for _ in range(3)))      # pdsc_forward_host_submit / _wait, two calls in flight
+    assert all(torch.equal(o["final_trans"], host["final_trans"]) for o in streamed)
 g = torch.Generator().manual_seed(0)
 for dt in (torch.float32, torch.float64):
     sd = torch.nn.functional.normalize(torch.randn(301, 33, generator=g, dtype=dt), dim=1).cuda()
