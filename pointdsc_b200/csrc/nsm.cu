@@ -589,6 +589,216 @@ __global__ void __launch_bounds__(256, 2) nsm_power_mma_kernel(
   if (lane == 0) atomicAnd(conv_mask + (size_t)b * mask_stride, mask);
 }
 
+// ---- 40 < k <= 80 in the tensor-core precisions (BASELINE config C: k = 80): the same tensor-core Gram, four warps per seed ----
+// Rows padded to 80 = five 16-row tiles x ten 8-column tiles; the 30 tiles on or above the diagonal are dealt to the four warps
+// by 16-row tile so that a warp's A fragments are shared by its tiles (7 / 8 / 8 / 7 tiles; a warp loads and splits only the row
+// groups its tiles touch).  Compatibility as in nsm_power_mma_kernel; the power iteration is the four-warp one of nsm_power_kernel<4>.
+constexpr int kMma4Rows = 80;
+__host__ __device__ constexpr int mma4_count(int w) { return (w == 0 || w == 3) ? 7 : 8; }
+// tile q of warp w: 16-row tile i, 8-column tile j
+__host__ __device__ constexpr int mma4_i(int w, int q) {
+  return w == 0 ? 0 : w == 1 ? 1 : w == 2 ? (q < 6 ? 2 : 4) : (q < 4 ? 3 : 0);
+}
+__host__ __device__ constexpr int mma4_j(int w, int q) {
+  return w == 0 ? q : w == 1 ? 2 + q : w == 2 ? (q < 6 ? 4 + q : 8 + (q - 6)) : (q < 4 ? 6 + q : 7 + (q - 4));
+}
+// bit m set: the warp needs row group m (rows 8 m + g) as an A or a B fragment
+__host__ __device__ constexpr unsigned mma4_need(int w) {
+  unsigned need = 0u;
+  for (int q = 0; q < mma4_count(w); ++q) need |= (3u << (2 * mma4_i(w, q))) | (1u << mma4_j(w, q));
+  return need;
+}
+
+template <int W>
+__device__ __forceinline__ void mma4_gram_and_compat(const float* __restrict__ normed, size_t set_row0, const int* idx, const float* P,
+                                                     float* M, int k, int ms, int lane, float sigma2, float rc_sigma2, float sigmad2,
+                                                     float rc_sigmad2) {
+  constexpr int NT = mma4_count(W);
+  constexpr unsigned NEED = mma4_need(W);
+  const int g = lane >> 2, t = lane & 3;
+  const float* rowp[10];
+#pragma unroll
+  for (int m = 0; m < 10; ++m) {
+    rowp[m] = nullptr;
+    if ((NEED >> m) & 1u) {
+      const int j = idx[g + 8 * m];
+      rowp[m] = (j >= 0) ? normed + (set_row0 + (size_t)j) * kC + 2 * t : nullptr;
+    }
+  }
+  float acc[NT][4];
+#pragma unroll
+  for (int q = 0; q < NT; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
+  float2 nxt[10][2];
+#pragma unroll
+  for (int m = 0; m < 10; ++m) {
+    nxt[m][0] = nxt[m][1] = make_float2(0.f, 0.f);
+    if (((NEED >> m) & 1u) && rowp[m]) {
+      nxt[m][0] = __ldg(reinterpret_cast<const float2*>(rowp[m]));
+      nxt[m][1] = __ldg(reinterpret_cast<const float2*>(rowp[m] + 8));
+    }
+  }
+#pragma unroll 1
+  for (int ks = 0; ks < kC / 16; ++ks) {
+    uint32_t hi[10][2], lo[10][2];
+#pragma unroll
+    for (int m = 0; m < 10; ++m) {
+      hi[m][0] = hi[m][1] = lo[m][0] = lo[m][1] = 0u;
+      if ((NEED >> m) & 1u) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) split_f16_pair(nxt[m][h].x * 64.0f, nxt[m][h].y * 64.0f, hi[m][h], lo[m][h]);
+      }
+    }
+    if (ks + 1 < kC / 16) {
+#pragma unroll
+      for (int m = 0; m < 10; ++m) {
+        if (((NEED >> m) & 1u) && rowp[m]) {
+          nxt[m][0] = __ldg(reinterpret_cast<const float2*>(rowp[m] + 16 * (ks + 1)));
+          nxt[m][1] = __ldg(reinterpret_cast<const float2*>(rowp[m] + 16 * (ks + 1) + 8));
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NT; ++q) {
+      const int i = mma4_i(W, q), j = mma4_j(W, q);
+      mma_f16_16816(acc[q], hi[2 * i][0], hi[2 * i + 1][0], hi[2 * i][1], hi[2 * i + 1][1], hi[j][0], hi[j][1]);
+      mma_f16_16816(acc[q], hi[2 * i][0], hi[2 * i + 1][0], hi[2 * i][1], hi[2 * i + 1][1], lo[j][0], lo[j][1]);
+      mma_f16_16816(acc[q], lo[2 * i][0], lo[2 * i + 1][0], lo[2 * i][1], lo[2 * i + 1][1], hi[j][0], hi[j][1]);
+    }
+  }
+  // compatibility: accumulator (q, half) = row 16 i + g + 8 half, columns 8 j + 2 t, 8 j + 2 t + 1
+#pragma unroll
+  for (int q = 0; q < NT; ++q) {
+    const int i = mma4_i(W, q), j = mma4_j(W, q);
+    const int c = 8 * j + 2 * t;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int a = 16 * i + g + 8 * half;
+      if (a < c + 1 && c < k) {
+        const float2 dot = make_float2(acc[q][2 * half] * (1.0f / 4096.0f), acc[q][2 * half + 1] * (1.0f / 4096.0f));
+        const float2 one_minus = fsub2_scalar(1.0f, div_by_const2(fsub2_scalar(1.0f, dot), sigma2, rc_sigma2));
+        const float2 fm = make_float2(fmaxf(one_minus.x, 0.0f), fmaxf(one_minus.y, 0.0f));
+        const float2 la = length3_pow2(fsub2_scalar(P[a], *reinterpret_cast<const float2*>(P + c)),
+                                       fsub2_scalar(P[kMma4Rows + a], *reinterpret_cast<const float2*>(P + kMma4Rows + c)),
+                                       fsub2_scalar(P[2 * kMma4Rows + a], *reinterpret_cast<const float2*>(P + 2 * kMma4Rows + c)));
+        const float2 lb = length3_pow2(fsub2_scalar(P[3 * kMma4Rows + a], *reinterpret_cast<const float2*>(P + 3 * kMma4Rows + c)),
+                                       fsub2_scalar(P[4 * kMma4Rows + a], *reinterpret_cast<const float2*>(P + 4 * kMma4Rows + c)),
+                                       fsub2_scalar(P[5 * kMma4Rows + a], *reinterpret_cast<const float2*>(P + 5 * kMma4Rows + c)));
+        const float2 val = fmul2(fm, consistency_rc2(fsub2(la, lb), sigmad2, rc_sigmad2));
+        if (a < c) {
+          M[a * ms + c] = val.x;
+          M[c * ms + a] = val.x;
+        }
+        if (c + 1 < k) {
+          M[a * ms + c + 1] = val.y;
+          M[(c + 1) * ms + a] = val.y;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) nsm_power_mma4_kernel(
+    const float* __restrict__ normed, const float* __restrict__ src, const float* __restrict__ tgt,
+    const int32_t* __restrict__ knn_idx, float* __restrict__ iterates, uint32_t* __restrict__ conv_mask,
+    float* __restrict__ compat_out, int N, int S, int k, int iters, float sigma2, float sigmad2, int mask_stride) {
+  const float rc_sigma2 = 1.0f / sigma2, rc_sigmad2 = 1.0f / sigmad2;   // IEEE divisions (correctly rounded reciprocals)
+  extern __shared__ __align__(16) float sm[];
+  const int tg = threadIdx.x, lane = tg & 31, warp = tg >> 5;
+  const int b = blockIdx.y, s = blockIdx.x;
+  const int ms = k | 1;
+  float* P = sm;                                       // six coordinate arrays [80]
+  float* v = P + 6 * kMma4Rows;                        // [80]
+  int* idx = reinterpret_cast<int*>(v + kMma4Rows);    // [80]
+  float* red = reinterpret_cast<float*>(idx + kMma4Rows);   // [8]
+  float* M = red + 8;                                  // [k][ms]
+  const size_t seed_row = (size_t)b * S + s;
+
+  for (int a = tg; a < kMma4Rows; a += 128) {
+    int j = -1;
+    float sx = 0.f, sy = 0.f, sz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
+    if (a < k) {
+      j = knn_idx[seed_row * k + a];
+      j = min(max(j, 0), N - 1);
+      const float* ps = src + ((size_t)b * N + j) * 3;
+      const float* pt = tgt + ((size_t)b * N + j) * 3;
+      sx = ps[0]; sy = ps[1]; sz = ps[2];
+      tx = pt[0]; ty = pt[1]; tz = pt[2];
+      M[a * ms + a] = 0.0f;                // total_knn_M[:, i, i] = 0  (PointDSC.py:278)
+    }
+    idx[a] = j;
+    P[a] = sx; P[kMma4Rows + a] = sy; P[2 * kMma4Rows + a] = sz;
+    P[3 * kMma4Rows + a] = tx; P[4 * kMma4Rows + a] = ty; P[5 * kMma4Rows + a] = tz;
+    v[a] = 1.0f;
+  }
+  __syncthreads();
+  const size_t set_row0 = (size_t)b * N;
+  if (warp == 0) mma4_gram_and_compat<0>(normed, set_row0, idx, P, M, k, ms, lane, sigma2, rc_sigma2, sigmad2, rc_sigmad2);
+  else if (warp == 1) mma4_gram_and_compat<1>(normed, set_row0, idx, P, M, k, ms, lane, sigma2, rc_sigma2, sigmad2, rc_sigmad2);
+  else if (warp == 2) mma4_gram_and_compat<2>(normed, set_row0, idx, P, M, k, ms, lane, sigma2, rc_sigma2, sigmad2, rc_sigmad2);
+  else mma4_gram_and_compat<3>(normed, set_row0, idx, P, M, k, ms, lane, sigma2, rc_sigma2, sigmad2, rc_sigmad2);
+  __syncthreads();
+  if (compat_out) {
+    float* dst = compat_out + seed_row * k * k;
+    for (int e = tg; e < k * k; e += 128) dst[e] = M[(e / k) * ms + (e % k)];
+  }
+
+  // power iteration from the all-ones vector (the four-warp form of nsm_power_kernel<4>): thread = (row group rg, column
+  // quarter cq), rows rg + 32 i, the matrix in shared memory
+  uint32_t mask = 0u;
+  float* it_out = iterates + seed_row * (size_t)iters * k;
+  constexpr int RG = 32, RI = 3;                     // rows rg + 32 i < 96 covers k <= 80
+  const int rg = tg >> 2, cq = tg & 3;
+  const int CQ = (k + 3) >> 2;
+  const int c_lo = cq * CQ, c_hi = min(k, c_lo + CQ);
+  float vrow[RI];
+#pragma unroll
+  for (int i = 0; i < RI; ++i) vrow[i] = 1.0f;
+  for (int t = 0; t < iters; ++t) {
+    float u[RI], ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < RI; ++i) {
+      const int row = rg + RG * i;
+      float p = 0.f;
+      if (row < k) {
+        const float* mr = M + (size_t)row * ms;
+        for (int c = c_lo; c < c_hi; ++c) p = fmaf(mr[c], v[c], p);
+      }
+      p += __shfl_xor_sync(0xffffffffu, p, 1);
+      p += __shfl_xor_sync(0xffffffffu, p, 2);
+      u[i] = p;
+      ss += (row < k) ? p * p : 0.f;
+    }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    ss = ((red[0] + red[1]) + red[2]) + red[3];      // the four warps' sums in ascending warp order on every thread
+    const float nrm = sqrtf(ss) + 1e-6f;
+    bool ok = true;
+    __syncthreads();                                 // every thread has read the old v (and red)
+#pragma unroll
+    for (int i = 0; i < RI; ++i) {
+      const int row = rg + RG * i;
+      const float vn = u[i] / nrm;
+      ok = ok && (row >= k || fabsf(vn - vrow[i]) <= 1e-8f + 1e-5f * fabsf(vrow[i]));
+      vrow[i] = vn;
+      if (row < k && cq == 0) {
+        v[row] = vn;
+        it_out[(size_t)t * k + row] = vn;
+      }
+    }
+    bool all_ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) red[4 + warp] = all_ok ? 1.f : 0.f;
+    __syncthreads();
+    all_ok = (red[4] + red[5] + red[6] + red[7]) == 4.f;
+    if (all_ok) mask |= (1u << t);
+  }
+  if (tg == 0) atomicAnd(conv_mask + (size_t)b * mask_stride, mask);
+}
+
 void launch_nsm_power(const float* normed, const float* src, const float* tgt, const int32_t* knn_idx, float* iterates,
                       uint32_t* conv_mask, float* compat_out, int B, int N, int S, int k, int iters, float sigma,
                       float sigma_d, int mask_stride, int tensor_gram, cudaStream_t st) {
@@ -604,6 +814,14 @@ void launch_nsm_power(const float* normed, const float* src, const float* tgt, c
     nsm_power_mma_kernel<<<dim3((S + warps - 1) / warps, B), warps * 32, smem, st>>>(
         normed, src, tgt, knn_idx, iterates, conv_mask, compat_out, N, S, k, iters, sigma * sigma, sigma_d * sigma_d, mask_stride,
         warps, per_group_floats);
+    return;
+  }
+  if (tensor_gram && k <= kMma4Rows) {
+    // 40 < k <= 80: four warps per seed, one seed per CTA
+    const int smem = (8 * kMma4Rows + 8 + k * ms) * (int)sizeof(float);
+    ensure_dynamic_smem(reinterpret_cast<const void*>(nsm_power_mma4_kernel), smem);
+    nsm_power_mma4_kernel<<<dim3(S, B), 128, smem, st>>>(normed, src, tgt, knn_idx, iterates, conv_mask, compat_out, N, S, k, iters,
+                                                         sigma * sigma, sigma_d * sigma_d, mask_stride);
     return;
   }
   const int kp = (k + 3) & ~3;
