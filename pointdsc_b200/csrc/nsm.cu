@@ -630,33 +630,30 @@ __device__ __forceinline__ void mma4_gram_and_compat(const float* __restrict__ n
   for (int q = 0; q < NT; ++q)
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[q][e] = 0.f;
-  float2 nxt[10][2];
+  // a row's 512 B are four 128-byte lines, one line = two 16-channel steps: the line of steps ks + 2, ks + 3 is prefetched into L1
+  // while steps ks, ks + 1 are multiplied (no register-resident prefetch: 32 registers less, four CTAs per SM instead of three)
 #pragma unroll
-  for (int m = 0; m < 10; ++m) {
-    nxt[m][0] = nxt[m][1] = make_float2(0.f, 0.f);
-    if (((NEED >> m) & 1u) && rowp[m]) {
-      nxt[m][0] = __ldg(reinterpret_cast<const float2*>(rowp[m]));
-      nxt[m][1] = __ldg(reinterpret_cast<const float2*>(rowp[m] + 8));
-    }
-  }
+  for (int m = 0; m < 10; ++m)
+    if (((NEED >> m) & 1u) && rowp[m]) asm volatile("prefetch.global.L1 [%0];" ::"l"(rowp[m]));
 #pragma unroll 1
   for (int ks = 0; ks < kC / 16; ++ks) {
     uint32_t hi[10][2], lo[10][2];
+    if ((ks & 1) == 0 && ks + 2 < kC / 16) {
+#pragma unroll
+      for (int m = 0; m < 10; ++m)
+        if (((NEED >> m) & 1u) && rowp[m]) asm volatile("prefetch.global.L1 [%0];" ::"l"(rowp[m] + 16 * (ks + 2)));
+    }
 #pragma unroll
     for (int m = 0; m < 10; ++m) {
       hi[m][0] = hi[m][1] = lo[m][0] = lo[m][1] = 0u;
       if ((NEED >> m) & 1u) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) split_f16_pair(nxt[m][h].x * 64.0f, nxt[m][h].y * 64.0f, hi[m][h], lo[m][h]);
-      }
-    }
-    if (ks + 1 < kC / 16) {
-#pragma unroll
-      for (int m = 0; m < 10; ++m) {
-        if (((NEED >> m) & 1u) && rowp[m]) {
-          nxt[m][0] = __ldg(reinterpret_cast<const float2*>(rowp[m] + 16 * (ks + 1)));
-          nxt[m][1] = __ldg(reinterpret_cast<const float2*>(rowp[m] + 16 * (ks + 1) + 8));
+        float2 f0 = make_float2(0.f, 0.f), f1 = make_float2(0.f, 0.f);
+        if (rowp[m]) {
+          f0 = __ldg(reinterpret_cast<const float2*>(rowp[m] + 16 * ks));
+          f1 = __ldg(reinterpret_cast<const float2*>(rowp[m] + 16 * ks + 8));
         }
+        split_f16_pair(f0.x * 64.0f, f0.y * 64.0f, hi[m][0], lo[m][0]);
+        split_f16_pair(f1.x * 64.0f, f1.y * 64.0f, hi[m][1], lo[m][1]);
       }
     }
 #pragma unroll
@@ -699,7 +696,7 @@ __device__ __forceinline__ void mma4_gram_and_compat(const float* __restrict__ n
   }
 }
 
-__global__ void __launch_bounds__(128) nsm_power_mma4_kernel(
+__global__ void __launch_bounds__(128, 4) nsm_power_mma4_kernel(
     const float* __restrict__ normed, const float* __restrict__ src, const float* __restrict__ tgt,
     const int32_t* __restrict__ knn_idx, float* __restrict__ iterates, uint32_t* __restrict__ conv_mask,
     float* __restrict__ compat_out, int N, int S, int k, int iters, float sigma2, float sigmad2, int mask_stride) {
@@ -745,30 +742,35 @@ __global__ void __launch_bounds__(128) nsm_power_mma4_kernel(
   }
 
   // power iteration from the all-ones vector (the four-warp form of nsm_power_kernel<4>): thread = (row group rg, column
-  // quarter cq), rows rg + 32 i, the matrix in shared memory
+  // quarter cq), rows rg + 32 i; the thread's 3 x 20 slice of the matrix stays in registers for all iterations (columns beyond
+  // the quarter are zeros: fma(0, 0, p) == p, so the sums are those of the shared-memory form bit for bit)
   uint32_t mask = 0u;
   float* it_out = iterates + seed_row * (size_t)iters * k;
-  constexpr int RG = 32, RI = 3;                     // rows rg + 32 i < 96 covers k <= 80
+  constexpr int RG = 32, RI = 3, CW = 20;            // rows rg + 32 i < 96 and 4 x 20 columns cover k <= 80
   const int rg = tg >> 2, cq = tg & 3;
   const int CQ = (k + 3) >> 2;
   const int c_lo = cq * CQ, c_hi = min(k, c_lo + CQ);
-  float vrow[RI];
+  float mreg[RI][CW], vq[CW], vrow[RI];
 #pragma unroll
-  for (int i = 0; i < RI; ++i) vrow[i] = 1.0f;
+  for (int i = 0; i < RI; ++i) {
+    const int row = rg + RG * i;
+#pragma unroll
+    for (int c = 0; c < CW; ++c) mreg[i][c] = (row < k && c_lo + c < c_hi) ? M[row * ms + c_lo + c] : 0.f;
+    vrow[i] = 1.0f;
+  }
+#pragma unroll
+  for (int c = 0; c < CW; ++c) vq[c] = (c_lo + c < c_hi) ? 1.0f : 0.f;
   for (int t = 0; t < iters; ++t) {
     float u[RI], ss = 0.f;
 #pragma unroll
     for (int i = 0; i < RI; ++i) {
-      const int row = rg + RG * i;
       float p = 0.f;
-      if (row < k) {
-        const float* mr = M + (size_t)row * ms;
-        for (int c = c_lo; c < c_hi; ++c) p = fmaf(mr[c], v[c], p);
-      }
+#pragma unroll
+      for (int c = 0; c < CW; ++c) p = fmaf(mreg[i][c], vq[c], p);
       p += __shfl_xor_sync(0xffffffffu, p, 1);
       p += __shfl_xor_sync(0xffffffffu, p, 2);
       u[i] = p;
-      ss += (row < k) ? p * p : 0.f;
+      ss += (rg + RG * i < k) ? p * p : 0.f;
     }
     ss += __shfl_xor_sync(0xffffffffu, ss, 4);
     ss += __shfl_xor_sync(0xffffffffu, ss, 8);
@@ -778,7 +780,6 @@ __global__ void __launch_bounds__(128) nsm_power_mma4_kernel(
     ss = ((red[0] + red[1]) + red[2]) + red[3];      // the four warps' sums in ascending warp order on every thread
     const float nrm = sqrtf(ss) + 1e-6f;
     bool ok = true;
-    __syncthreads();                                 // every thread has read the old v (and red)
 #pragma unroll
     for (int i = 0; i < RI; ++i) {
       const int row = rg + RG * i;
@@ -786,7 +787,7 @@ __global__ void __launch_bounds__(128) nsm_power_mma4_kernel(
       ok = ok && (row >= k || fabsf(vn - vrow[i]) <= 1e-8f + 1e-5f * fabsf(vrow[i]));
       vrow[i] = vn;
       if (row < k && cq == 0) {
-        v[row] = vn;
+        v[row] = vn;                                 // nobody reads v before the barrier below (the iterate lives in vq)
         it_out[(size_t)t * k + row] = vn;
       }
     }
@@ -795,6 +796,10 @@ __global__ void __launch_bounds__(128) nsm_power_mma4_kernel(
     __syncthreads();
     all_ok = (red[4] + red[5] + red[6] + red[7]) == 4.f;
     if (all_ok) mask |= (1u << t);
+#pragma unroll
+    for (int c = 0; c < CW; ++c) vq[c] = (c_lo + c < c_hi) ? v[c_lo + c] : 0.f;
+    // no third barrier: v and red[4..7] are next written behind the next iteration's first barrier, red[0..3] were read before
+    // this iteration's second one
   }
   if (tg == 0) atomicAnd(conv_mask + (size_t)b * mask_stride, mask);
 }
