@@ -16,6 +16,8 @@
 // per-set word; the consumer (select_refine.cu) takes the iterate at the first all-converged bit.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "warp_select.cuh"
@@ -809,6 +811,9 @@ void launch_nsm_power(const float* normed, const float* src, const float* tgt, c
                       float sigma_d, int mask_stride, int tensor_gram, cudaStream_t st) {
   if (S <= 0) return;
   const int ms = k | 1;
+  // developer switch for same-box A/B of the two Gram paths (tools/exp_variant.sh style): PDSC_NSM_FFMA=1 forces the FFMA kernels
+  static const bool force_ffma = [] { const char* v = getenv("PDSC_NSM_FFMA"); return v && v[0] == '1'; }();
+  if (force_ffma) tensor_gram = 0;
   if (tensor_gram && k <= 40) {
     // one warp per seed, two CTAs of eight warps per SM; per warp: key points 6 x 48, iterate 48, indices 48, M k x ms
     int per_group_floats = 8 * kMmaRows + k * ms;
