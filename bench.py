@@ -182,8 +182,8 @@ class CpuPath:
 
 def pick_cpu_threads(cpu, sets):
     """torch's CPU ops on small tensors slow down badly when oversubscribed (128 threads: 26 s per N=1000 forward, 8 threads:
-    0.17 s), so "all the host threads it can use" is found by timing three forwards per candidate count and keeping its fastest (bounded: a candidate that
-    takes > 4x the best so far ends the search) and keeping the fastest."""
+    0.17 s), so "all the host threads it can use" is found by timing three back-to-back forwards per candidate count (bounded: a
+    candidate that takes > 4x the best so far ends the search) and keeping the fastest count."""
     import torch
     ncpu = os.cpu_count() or 1
     cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
@@ -192,12 +192,12 @@ def pick_cpu_threads(cpu, sets):
     for c in cands:
         torch.set_num_threads(c)
         cpu.forward(*one)                     # warm this pool size
-        dt = None
-        for _ in range(3):                    # the fastest of three: one sample picked 32 threads on a box where 16 sustain 1.5x more
-            t0 = time.perf_counter()
+        # the SUSTAINED time of three back-to-back forwards (what the measured loop then does), not the fastest single one: one
+        # sample, and later the fastest of three, picked 32 threads on boxes where 16 sustain 1.5x more
+        t0 = time.perf_counter()
+        for _ in range(3):
             cpu.forward(*one)
-            d = time.perf_counter() - t0
-            dt = d if dt is None else min(dt, d)
+        dt = (time.perf_counter() - t0) / 3
         if best_t is None or dt < best_t:
             best, best_t = c, dt
         elif dt > 4 * best_t:
